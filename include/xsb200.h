@@ -1,0 +1,131 @@
+/* libxsb200 -- C ABI of the B200-native backend for the XShinnosuke ("XS") data-parallel hot path.
+ *
+ * The reference (E1eveNn/xshinnosuke) has no FFI: its only backend seam is the module pointer
+ * GLOBAL.np (xs/core/__global.py:8). The drop-in boundary is therefore the Python function level
+ * (xs/nn/functional.py, xs/nn/grad_fn.py, xs/optim/*.py); each entry point below is what the
+ * replacement of one of those functions binds through ctypes. The "replaces" note on every entry
+ * names the reference code whose arithmetic it performs (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure (xsb_last_error() has the text);
+ *   - all pointers except xsb_memcpy_* host sides are DEVICE pointers, fp32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the device;
+ *   - activations are channels-last [N,H,W,C], filters [OC,KH,KW,C]; xsb_nchw_to_nhwc /
+ *     xsb_nhwc_to_nchw convert from/to the reference's logical NCHW at the tensor boundary;
+ *   - `accumulate` / `acc_*` = 1 means "+=" (the reference's closures always accumulate into
+ *     `in_bound.grad`), 0 means "=" (first write into a freshly zeroed gradient, no memset needed);
+ *   - `ws` is a caller-owned scratch buffer: zero-initialised once, reusable by every call on one stream.
+ */
+#ifndef XSB200_H
+#define XSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XSB_OK 0
+#define XSB_ERR_CUDA 1
+#define XSB_ERR_ARG 2
+#define XSB_ERR_UNSUPPORTED 3
+
+/* math modes of the GEMM-shaped entry points */
+#define XSB_MATH_FP32 0 /* CUDA-core FFMA, fp32 accumulate: <= 1e-5 vs the float64 reference      */
+#define XSB_MATH_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM: <= 2e-3 vs the reference  */
+
+/* ---- runtime (no reference counterpart; plumbing) ---- */
+int xsb_version(void);
+const char* xsb_last_error(void);
+int xsb_init(int device);
+int xsb_device_sm_count(void);
+int xsb_stream_sync(void* stream);
+int xsb_memcpy_h2d(void* dst_dev, const void* src_host, int64_t bytes, void* stream);
+int xsb_memcpy_d2h(void* dst_host, const void* src_dev, int64_t bytes, void* stream);
+
+/* ---- layout: logical NCHW (xs/core/base.py:69-75 `.eval` contract) <-> device channels-last ---- */
+int xsb_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int accumulate, void* stream);
+int xsb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int accumulate, void* stream);
+
+/* ---- ReLU. replaces xs/nn/functional.py:297-313 + xs/nn/td_functional.py:59-60 (forward),
+ *      xs/nn/grad_fn.py:146-157 + xs/layers/activators.py:37-50 (backward; mask is x < 0). ---- */
+int xsb_relu_fwd(const float* x, float* y, uint8_t* mask /* nullable, ceil(n/8) bytes */, int64_t n, void* stream);
+int xsb_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, int accumulate, void* stream);
+int xsb_relu_bwd_mask(const float* dy, const uint8_t* mask, float* dx, int64_t n, int accumulate, void* stream);
+
+/* ---- add / accumulate / fill. replaces xs/nn/functional.py:6-21, xs/nn/grad_fn.py:6-16,
+ *      xs/core/base.py:312-316 (zero_grad). ---- */
+int xsb_add(const float* a, const float* b, float* y, int64_t n, void* stream);
+int xsb_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream);
+int xsb_fill(float* dst, float value, int64_t n, void* stream);
+
+/* ---- mean/sum over one axis and its backward. replaces xs/nn/functional.py mean/sum + grad_fn.py:122-137 ---- */
+int xsb_reduce_axis(const float* x, float* y, int64_t outer, int64_t red, int64_t inner, float scale, void* stream);
+int xsb_broadcast_axis(const float* dy, float* dx, int64_t outer, int64_t red, int64_t inner, float scale,
+                       int accumulate, void* stream);
+
+/* ---- max_pool2d with argmax. replaces xs/nn/functional.py:445-491 (zero padding, first max wins,
+ *      argmax = ky*k+kx in (n,oh,ow,c) order) and xs/nn/grad_fn.py:206-235. ---- */
+int xsb_maxpool2d_fwd(const float* x, float* y, uint8_t* argmax /* nullable */, int N, int H, int W, int C, int k,
+                      int sh, int sw, int pad, void* stream);
+int xsb_maxpool2d_bwd(const float* dy, const uint8_t* argmax, float* dx, int N, int H, int W, int C, int k, int sh,
+                      int sw, int pad, int accumulate, void* stream);
+
+/* ---- avg_pool2d (padding 0). replaces xs/nn/functional.py:539-583, xs/nn/grad_fn.py:284-309 ---- */
+int xsb_avgpool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int sh, int sw, void* stream);
+int xsb_avgpool2d_bwd(const float* dy, float* dx, int N, int H, int W, int C, int k, int sh, int sw, int accumulate,
+                      void* stream);
+
+/* ---- BatchNorm, training branch, on [R, C] (R = N*H*W or N). replaces xs/nn/functional.py:676-706,730-740
+ *      and xs/nn/grad_fn.py:379-411. save_mean/save_invstd stand in for the cached xhat/sqrtvar. ---- */
+int64_t xsb_bn_workspace_floats(int64_t R, int C);
+int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float* y, float* save_mean, float* save_invstd, int64_t R, int C, float eps, float momentum,
+                     float* ws, void* stream);
+int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+               float* dx /* nullable */, float* dgamma /* nullable */, float* dbeta /* nullable */, int64_t R, int C,
+               int acc_dx, int acc_dgamma, int acc_dbeta, float* ws, void* stream);
+
+/* ---- out[c] (+)= sum_r x[r,c]: conv / Dense bias gradient. replaces xs/nn/grad_fn.py:196-197, 89-95 ---- */
+int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, float* ws, void* stream);
+
+/* ---- Dense. replaces xs/nn/functional.py:81-120 (mm / addmm) and xs/nn/grad_fn.py:73-99.
+ *      C[M,N] (+)= op(A).op(B) (+ bias[N]); transA: A stored [K,M]; transB: B stored [N,K]. ---- */
+int xsb_gemm(const float* A, const float* B, float* C, const float* bias /* nullable */, int M, int N, int K,
+             int transA, int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, void* stream);
+
+/* ---- conv2d as implicit GEMM (no materialised im2col). replaces xs/nn/functional.py:405-442 +
+ *      xs/utils/common.py:35-46 (forward), xs/nn/grad_fn.py:186-203 + xs/utils/common.py:49-65 (backward).
+ *      x [N,H,W,C], w [OC,KH,KW,C], y/dy [N,OH,OW,OC], OH = (H-KH+2*pad)/sh+1. ---- */
+int xsb_conv2d_fwd(const float* x, const float* w, const float* bias /* nullable */, float* y, int N, int H, int W,
+                   int C, int OC, int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws, int64_t ws_floats,
+                   void* stream);
+int xsb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int C, int OC, int KH, int KW,
+                     int sh, int sw, int pad, int accumulate, int math_mode, float* ws, int64_t ws_floats,
+                     void* stream);
+int xsb_conv2d_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int C, int OC, int KH, int KW,
+                     int sh, int sw, int pad, int accumulate, int math_mode, float* ws, int64_t ws_floats,
+                     void* stream);
+
+/* ---- losses. replaces xs/nn/functional.py:984-1010 + xs/nn/td_functional.py:73-78,115-128 +
+ *      xs/nn/grad_fn.py:604-620 (cross entropy; labels int64), xs/nn/functional.py:843-873 +
+ *      xs/nn/grad_fn.py:503-520 (XS mse). reduction: 0 = mean, 1 = sum. ---- */
+int xsb_softmax_xent_fwd(const float* logits, const int64_t* labels, float* probs, float* loss, int N, int C,
+                         int reduction, void* stream);
+int xsb_softmax_xent_bwd(const float* probs, const int64_t* labels, const float* dloss, float* dlogits, int N, int C,
+                         int reduction, int accumulate, void* stream);
+int xsb_mse_fwd(const float* a, const float* b, float* loss, int64_t n, int reduction, void* stream);
+int xsb_mse_bwd(const float* a, const float* b, const float* dloss, float* da /* nullable */, float* db /* nullable */,
+                int64_t n, int reduction, int acc_a, int acc_b, void* stream);
+
+/* ---- fused multi-tensor optimizer over the flat parameter buffer. replaces xs/optim/sgd.py:5-9 and
+ *      xs/optim/adam.py:13-30. grad_scale = 1/world for all-reduced (summed) gradients. ---- */
+int xsb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream);
+int xsb_adam_step(float* p, const float* g, float* v /* 1st moment */, float* m /* 2nd moment */, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float grad_scale, const int* step_dev, void* stream);
+int xsb_counter_inc(int* counter_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSB200_H */

@@ -1,0 +1,287 @@
+"""TEST INFRASTRUCTURE ONLY: a NumPy stand-in for libxsb200.so so that the HOST logic of
+xshinnosuke_b200 (graph wiring, autograd walk, lazy-zero gradients, flat optimizer buffers, static
+graph, data-parallel buckets) can be exercised by `-m "not gpu"` tests on a box without a GPU.
+
+Every function takes the same arguments as its C-ABI namesake (include/xsb200.h), with "device"
+pointers being addresses of CPU torch tensors, and computes the kernel's contract in float64
+(using the oracle where one exists). The product package never imports this module; GPU tests never
+install it. `install()` monkeypatches `xshinnosuke_b200._lib.lib` and the runtime singleton.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from oracle import xs_numpy as X
+
+
+def _view(ptr, n, ctype, dtype):
+    if ptr is None or n == 0:
+        return None
+    return np.ctypeslib.as_array((ctype * int(n)).from_address(int(ptr))).view(dtype)
+
+
+def f32(ptr, n):
+    return _view(ptr, n, ctypes.c_float, np.float32)
+
+
+def u8(ptr, n):
+    return _view(ptr, n, ctypes.c_uint8, np.uint8)
+
+
+def i64(ptr, n):
+    return _view(ptr, n, ctypes.c_int64, np.int64)
+
+
+def i32(ptr, n):
+    return _view(ptr, n, ctypes.c_int32, np.int32)
+
+
+def _store(dst, val, acc):
+    val = np.asarray(val, dtype=np.float64).reshape(dst.shape)
+    dst[...] = (dst.astype(np.float64) + val if acc else val).astype(np.float32)
+
+
+class FakeLib:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if not name.startswith("xsb_"):
+            raise AttributeError(name)
+        impl = getattr(self, "_" + name[4:])
+
+        def wrapped(*a):
+            self.calls.append(name)
+            r = impl(*a)
+            return 0 if r is None else r
+        return wrapped
+
+    # ---- runtime
+    def _version(self):
+        return 100
+
+    def _init(self, dev):
+        pass
+
+    def _device_sm_count(self):
+        return 148
+
+    def _stream_sync(self, s):
+        pass
+
+    # ---- elementwise
+    def _relu_fwd(self, x, y, mask, n, s):
+        xv = f32(x, n).copy()
+        f32(y, n)[...] = np.maximum(xv, 0)
+        if mask:
+            u8(mask, (n + 7) // 8)[...] = np.packbits(xv < 0, bitorder="little")
+
+    def _relu_bwd(self, dy, x, dx, n, acc, s):
+        g = f32(dy, n).astype(np.float64)
+        g[f32(x, n) < 0] = 0
+        _store(f32(dx, n), g, acc)
+
+    def _relu_bwd_mask(self, dy, mask, dx, n, acc, s):
+        m = np.unpackbits(u8(mask, (n + 7) // 8), bitorder="little")[:n].astype(bool)
+        g = f32(dy, n).astype(np.float64)
+        g[m] = 0
+        _store(f32(dx, n), g, acc)
+
+    def _add(self, a, b, y, n, s):
+        f32(y, n)[...] = f32(a, n) + f32(b, n)
+
+    def _axpy(self, dst, src, alpha, n, s):
+        f32(dst, n)[...] += np.float32(alpha) * f32(src, n)
+
+    def _fill(self, dst, v, n, s):
+        f32(dst, n)[...] = v
+
+    def _nchw_to_nhwc(self, src, dst, N, C, H, W, acc, s):
+        a = f32(src, N * C * H * W).reshape(N, C, H, W).transpose(0, 2, 3, 1)
+        _store(f32(dst, N * C * H * W).reshape(N, H, W, C), a, acc)
+
+    def _nhwc_to_nchw(self, src, dst, N, C, H, W, acc, s):
+        a = f32(src, N * C * H * W).reshape(N, H, W, C).transpose(0, 3, 1, 2)
+        _store(f32(dst, N * C * H * W).reshape(N, C, H, W), a, acc)
+
+    def _reduce_axis(self, x, y, outer, red, inner, scale, s):
+        a = f32(x, outer * red * inner).reshape(outer, red, inner).astype(np.float64)
+        f32(y, outer * inner)[...] = (a.sum(axis=1) * scale).reshape(-1)
+
+    def _broadcast_axis(self, dy, dx, outer, red, inner, scale, acc, s):
+        g = f32(dy, outer * inner).reshape(outer, 1, inner).astype(np.float64) * scale
+        _store(f32(dx, outer * red * inner).reshape(outer, red, inner), np.broadcast_to(g, (outer, red, inner)), acc)
+
+    # ---- pooling (channels-last buffers <-> oracle NCHW)
+    @staticmethod
+    def _nchw(ptr, N, H, W, C):
+        return f32(ptr, N * H * W * C).reshape(N, H, W, C).transpose(0, 3, 1, 2)
+
+    def _maxpool2d_fwd(self, x, y, amax, N, H, W, C, k, sh, sw, pad, s):
+        yv, am = X.max_pool2d_fwd(self._nchw(x, N, H, W, C), k, (sh, sw), pad)
+        OH, OW = yv.shape[2:]
+        f32(y, N * OH * OW * C)[...] = yv.transpose(0, 2, 3, 1).reshape(-1)
+        if amax:
+            u8(amax, am.size)[...] = am.astype(np.uint8)
+
+    def _maxpool2d_bwd(self, dy, amax, dx, N, H, W, C, k, sh, sw, pad, acc, s):
+        OH, OW = (H + 2 * pad - k) // sh + 1, (W + 2 * pad - k) // sw + 1
+        g = self._nchw(dy, N, OH, OW, C)
+        am = u8(amax, N * OH * OW * C).astype(np.int64)
+        d = X.max_pool2d_bwd(g, am, (N, C, H, W), k, (sh, sw), pad)
+        _store(f32(dx, N * H * W * C).reshape(N, H, W, C), d.transpose(0, 2, 3, 1), acc)
+
+    def _avgpool2d_fwd(self, x, y, N, H, W, C, k, sh, sw, s):
+        yv = X.avg_pool2d_fwd(self._nchw(x, N, H, W, C), k, (sh, sw))
+        f32(y, yv.size)[...] = yv.transpose(0, 2, 3, 1).reshape(-1)
+
+    def _avgpool2d_bwd(self, dy, dx, N, H, W, C, k, sh, sw, acc, s):
+        OH, OW = (H - k) // sh + 1, (W - k) // sw + 1
+        d = X.avg_pool2d_bwd(self._nchw(dy, N, OH, OW, C), (N, C, H, W), k, (sh, sw))
+        _store(f32(dx, N * H * W * C).reshape(N, H, W, C), d.transpose(0, 2, 3, 1), acc)
+
+    # ---- batch norm on [R, C]
+    def _bn_workspace_floats(self, R, C):
+        return 64
+
+    def _bn_train_fwd(self, x, gamma, beta, rm, rv, y, smean, sinv, R, C, eps, mom, ws, s):
+        xv = f32(x, R * C).reshape(R, C).astype(np.float64)
+        mean, var = xv.mean(axis=0), xv.var(axis=0)
+        inv = 1.0 / np.sqrt(var + eps)
+        f32(y, R * C).reshape(R, C)[...] = (xv - mean) * inv * f32(gamma, C) + f32(beta, C)
+        f32(smean, C)[...] = mean
+        f32(sinv, C)[...] = inv
+        if rm:
+            f32(rm, C)[...] = mom * f32(rm, C).astype(np.float64) + (1 - mom) * mean
+        if rv:
+            f32(rv, C)[...] = mom * f32(rv, C).astype(np.float64) + (1 - mom) * var
+
+    def _bn_bwd(self, dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, ws, s):
+        g = f32(dy, R * C).reshape(R, C).astype(np.float64)
+        xhat = (f32(x, R * C).reshape(R, C).astype(np.float64) - f32(smean, C)) * f32(sinv, C)
+        sdy, sdyx = g.sum(axis=0), (g * xhat).sum(axis=0)
+        if dgamma:
+            _store(f32(dgamma, C), sdyx, acc_dg)
+        if dbeta:
+            _store(f32(dbeta, C), sdy, acc_db)
+        if dx:
+            d = f32(gamma, C).astype(np.float64) * f32(sinv, C) * (g - sdy / R - xhat * sdyx / R)
+            _store(f32(dx, R * C).reshape(R, C), d, acc_dx)
+
+    def _colsum(self, x, out, R, C, acc, ws, s):
+        _store(f32(out, C), f32(x, R * C).reshape(R, C).astype(np.float64).sum(axis=0), acc)
+
+    # ---- GEMM / conv
+    def _gemm(self, A, B, C, bias, M, N, K, ta, tb, acc, mode, ws, wsn, s):
+        a = f32(A, M * K).reshape((K, M) if ta else (M, K)).astype(np.float64)
+        b = f32(B, K * N).reshape((N, K) if tb else (K, N)).astype(np.float64)
+        r = (a.T if ta else a) @ (b.T if tb else b)
+        if bias:
+            r = r + f32(bias, N)
+        _store(f32(C, M * N).reshape(M, N), r, acc)
+
+    @staticmethod
+    def _w_oihw(ptr, OC, KH, KW, C):
+        return f32(ptr, OC * KH * KW * C).reshape(OC, KH, KW, C).transpose(0, 3, 1, 2)
+
+    def _conv2d_fwd(self, x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, s):
+        b = f32(bias, OC).reshape(1, OC).astype(np.float64) if bias else None
+        yv, _ = X.conv2d_fwd(self._nchw(x, N, H, W, C).astype(np.float64), self._w_oihw(w, OC, KH, KW, C).astype(np.float64),
+                             b, (sh, sw), pad)
+        f32(y, yv.size)[...] = yv.transpose(0, 2, 3, 1).reshape(-1)
+
+    def _conv_bwd(self, dy, x, w, N, H, W, C, OC, KH, KW, sh, sw, pad, need_dx):
+        OH, OW = (H - KH + 2 * pad) // sh + 1, (W - KW + 2 * pad) // sw + 1
+        g = self._nchw(dy, N, OH, OW, OC).astype(np.float64)
+        xv = self._nchw(x, N, H, W, C).astype(np.float64) if x else np.zeros((N, C, H, W))
+        wv = self._w_oihw(w, OC, KH, KW, C).astype(np.float64) if w else np.zeros((OC, C, KH, KW))
+        col = X.unfold(np.pad(xv, ((0, 0), (0, 0), (pad, pad), (pad, pad))), OH, OW, KH, KW, (sh, sw))
+        return X.conv2d_bwd(g, (N, C, H, W), wv, col, (sh, sw), pad, need_dx)
+
+    def _conv2d_dgrad(self, dy, w, dx, N, H, W, C, OC, KH, KW, sh, sw, pad, acc, mode, ws, wsn, s):
+        d, _, _ = self._conv_bwd(dy, None, w, N, H, W, C, OC, KH, KW, sh, sw, pad, True)
+        _store(f32(dx, N * H * W * C).reshape(N, H, W, C), d.transpose(0, 2, 3, 1), acc)
+
+    def _conv2d_wgrad(self, dy, x, dw, N, H, W, C, OC, KH, KW, sh, sw, pad, acc, mode, ws, wsn, s):
+        _, g, _ = self._conv_bwd(dy, x, None, N, H, W, C, OC, KH, KW, sh, sw, pad, False)
+        _store(f32(dw, OC * KH * KW * C).reshape(OC, KH, KW, C), g.transpose(0, 2, 3, 1), acc)
+
+    # ---- losses
+    def _softmax_xent_fwd(self, z, labels, probs, loss, N, C, red, s):
+        zv = f32(z, N * C).reshape(N, C).astype(np.float64)
+        l, p = X.cross_entropy_fwd(zv, i64(labels, N), "mean" if red == 0 else "sum")
+        f32(probs, N * C)[...] = p.reshape(-1)
+        f32(loss, 1)[0] = l[0]
+
+    def _softmax_xent_bwd(self, probs, labels, dloss, dz, N, C, red, acc, s):
+        p = f32(probs, N * C).reshape(N, C).astype(np.float64)
+        g = X.cross_entropy_bwd(p, i64(labels, N), float(f32(dloss, 1)[0]), "mean" if red == 0 else "sum")
+        _store(f32(dz, N * C).reshape(N, C), g, acc)
+
+    def _mse_fwd(self, a, b, loss, n, red, s):
+        f32(loss, 1)[0] = X.mse_loss_fwd(f32(a, n).astype(np.float64), f32(b, n).astype(np.float64),
+                                         "mean" if red == 0 else "sum")[0]
+
+    def _mse_bwd(self, a, b, dloss, da, db, n, red, acc_a, acc_b, s):
+        g = X.mse_loss_bwd(f32(a, n).astype(np.float64), f32(b, n).astype(np.float64), float(f32(dloss, 1)[0]),
+                           "mean" if red == 0 else "sum")
+        if da:
+            _store(f32(da, n), g, acc_a)
+        if db:
+            _store(f32(db, n), -g, acc_b)
+
+    # ---- optimizers
+    def _sgd_step(self, p, g, n, lr, gscale, s):
+        f32(p, n)[...] = f32(p, n).astype(np.float64) - lr * gscale * f32(g, n).astype(np.float64)
+
+    def _counter_inc(self, c, s):
+        i32(c, 1)[0] += 1
+
+    def _adam_step(self, p, g, v, m, n, lr, b1, b2, eps, gscale, step, s):
+        t = int(i32(step, 1)[0])
+        gv = f32(g, n).astype(np.float64) * gscale
+        vv = b1 * f32(v, n).astype(np.float64) + (1 - b1) * gv
+        mv = b2 * f32(m, n).astype(np.float64) + (1 - b2) * gv * gv
+        f32(p, n)[...] = f32(p, n).astype(np.float64) - lr * (vv / (1 - b1 ** t)) / (np.sqrt(mv / (1 - b2 ** t)) + eps)
+        f32(v, n)[...] = vv
+        f32(m, n)[...] = mv
+
+
+def install(monkeypatch=None):
+    """Point xshinnosuke_b200 at the fake library and a CPU 'device'. Returns the FakeLib."""
+    import xshinnosuke_b200._lib as L
+    import xshinnosuke_b200.core.device as D
+    fake = FakeLib()
+    targets = [L, D]
+    import xshinnosuke_b200.nn.functional as F
+    import xshinnosuke_b200.nn.grad_fn as G
+    import xshinnosuke_b200.optim.optimizer as O
+    import xshinnosuke_b200.layers.graph_ops as GO
+    targets += [F, G, O, GO]
+    try:
+        import xshinnosuke_b200.parallel as P
+        targets.append(P)
+    except ImportError:
+        pass
+    saved = [(m, m.lib) for m in targets if hasattr(m, "lib")]
+    for m, _ in saved:
+        if monkeypatch is not None:
+            monkeypatch.setattr(m, "lib", fake)
+        else:
+            m.lib = fake
+    rt = D.rt
+    state = dict(ready=rt.ready, device=rt.device, ws_small=rt._ws_small, ws_big=rt._ws_big)
+
+    def set_(obj, name, val):
+        if monkeypatch is not None:
+            monkeypatch.setattr(obj, name, val, raising=False)
+        else:
+            setattr(obj, name, val)
+    set_(rt, "ready", True)
+    set_(rt, "device", torch.device("cpu"))
+    set_(rt, "_ws_small", torch.zeros(1024))
+    set_(rt, "_ws_big", torch.zeros(1024))
+    set_(rt, "stream", lambda: 0)
+    set_(rt, "synchronize", lambda: None)
+    return fake

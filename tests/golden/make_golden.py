@@ -262,9 +262,10 @@ def gen_test_conv():
     l1 = Conv2D(out_channels=3, kernel_size=3)
     bn1 = BatchNormalization(epsilon=1e-5, momentum=0.9)
     l2 = Conv2D(out_channels=5, kernel_size=3)
-    l1.parameters([nn.Parameter(w1), nn.Parameter(b1)])
-    l2.parameters([nn.Parameter(w2), nn.Parameter(b2)])
-    bn1.parameters([nn.Parameter(g1), nn.Parameter(be1)])
+    # Parameter() aliases the ndarray and training updates it in place: hand over copies
+    l1.parameters([nn.Parameter(w1.copy()), nn.Parameter(b1.copy())])
+    l2.parameters([nn.Parameter(w2.copy()), nn.Parameter(b2.copy())])
+    bn1.parameters([nn.Parameter(g1.copy()), nn.Parameter(be1.copy())])
     bn1.moving_mean = xs.zeros(3)
     bn1.moving_variance = xs.ones(3)
     net = nn.Sequential(l1, bn1, ReLU(), l2)

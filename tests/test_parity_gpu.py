@@ -1,0 +1,163 @@
+"""GPU (B200): parity of the CUDA path with the reference, through the public API -> ctypes -> C ABI.
+
+fp32 math mode: outputs and gradients within 1e-5 (max|a-b|/max|b|) of the reference's NumPy path;
+max-pool values, arg-max indices and all shapes bit-exact (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode():
+    import xshinnosuke_b200 as xs
+    import xshinnosuke_b200.core.state as G
+    from xshinnosuke_b200._lib import lib
+    lib.load()                      # fail loudly if the CUDA library is missing
+    xs.runtime.ensure()
+    xs.set_math_mode("fp32")
+    G.INPUTS = G.OUTPUTS = G.GRAPH = None
+    yield
+    G.INPUTS = G.OUTPUTS = G.GRAPH = None
+
+
+def test_library_is_the_cuda_one():
+    import xshinnosuke_b200 as xs
+    from xshinnosuke_b200._lib import LIB_PATH, lib
+    import os
+    assert os.path.exists(LIB_PATH)
+    assert type(lib).__name__ == "_Lib"
+    assert xs.runtime.device.type == "cuda"
+    assert lib.xsb_device_sm_count() >= 100
+
+
+def test_conv(golden):
+    import parity_suite as S
+    S.check_conv(golden, TOL)
+
+
+def test_pools(golden):
+    import parity_suite as S
+    S.check_maxpool(golden, TOL)
+    S.check_avgpool(golden, TOL)
+
+
+def test_relu_add(golden):
+    import parity_suite as S
+    S.check_relu_add(golden, TOL)
+    S.check_inplace_relu_layer(TOL)
+
+
+def test_bn(golden):
+    import parity_suite as S
+    S.check_bn(golden, TOL)
+
+
+def test_dense_losses(golden):
+    import parity_suite as S
+    S.check_dense_losses(golden, TOL)
+
+
+def test_optimizers(golden):
+    import parity_suite as S
+    S.check_optimizers(golden, TOL)
+
+
+def test_gradient_check_scripts(golden):
+    import parity_suite as S
+    S.check_gradient_check_scripts(golden, TOL)
+
+
+def test_trajectories(golden):
+    import parity_suite as S
+    S.check_test_fc(golden, TOL)
+    S.check_test_conv(golden, TOL, steps=50)
+
+
+@pytest.mark.parametrize("tag,n,hw", [("n2_33", 2, 33), ("n4_56", 4, 56), ("n32_56", 32, 56)])
+def test_resnet18(golden, tag, n, hw):
+    import parity_suite as S
+    S.check_resnet18(golden, tag, n, hw, tol_logits=5e-5, tol_loss=2e-5)
+
+
+def test_fit_static_graph(golden):
+    import parity_suite as S
+    S.check_fit_configs(golden, TOL)
+
+
+# ------------------------------------------------------------------ sizes beyond the golden file: vs the oracle
+@pytest.mark.parametrize("n,c,h,oc,k,s,p", [(8, 64, 28, 64, 3, 1, 1), (8, 64, 28, 128, 3, 2, 1), (8, 64, 28, 128, 1, 2, 0),
+                                           (4, 3, 56, 64, 7, 2, 3), (16, 256, 7, 512, 3, 1, 1), (5, 20, 9, 12, 3, 1, 1)])
+def test_conv_vs_oracle(n, c, h, oc, k, s, p):
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    rs = np.random.RandomState(n * 1000 + c)
+    x = rs.randn(n, c, h, h).astype(np.float32)
+    w = (rs.randn(oc, c, k, k) * 0.1).astype(np.float32)
+    b = rs.randn(1, oc).astype(np.float32)
+    tx, tw, tb = xs.tensor(x, requires_grad=True), nn.Parameter(w), nn.Parameter(b)
+    y = F.conv2d(tx, tw, tb, (s, s), p)
+    yr, col = X.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), p)
+    assert X.rel_err(y.eval, yr) <= TOL
+    g = rs.randn(*yr.shape).astype(np.float32)
+    y.backward(gradients=g)
+    dx, dw, db = X.conv2d_bwd(g.astype(np.float64), x.shape, w.astype(np.float64), col, (s, s), p)
+    assert X.rel_err(tx.grad.eval, dx) <= TOL
+    assert X.rel_err(tw.grad.eval, dw) <= TOL
+    assert X.rel_err(tb.grad.eval.reshape(-1), db) <= TOL
+
+
+@pytest.mark.parametrize("n,c,h,k,s,p", [(32, 64, 28, 3, 2, 1), (256, 8, 27, 2, 2, 0), (4, 64, 112, 3, 2, 1)])
+def test_maxpool_vs_oracle(n, c, h, k, s, p):
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200.nn import functional as F
+    rs = np.random.RandomState(n + c + h)
+    x = np.maximum(rs.randn(n, c, h, h), 0).astype(np.float32)   # post-ReLU: ~50 % exact zeros -> ties
+    tx = xs.tensor(x, requires_grad=True)
+    y = F.max_pool2d(tx, k, s, p)
+    yr, am = X.max_pool2d_fwd(x, k, s, p)
+    assert np.array_equal(y.eval, yr)
+    assert np.array_equal(np.asarray(y.cache["pool_argmax"]), am)
+    g = rs.randn(*yr.shape).astype(np.float32)
+    y.backward(gradients=g)
+    assert X.rel_err(tx.grad.eval, X.max_pool2d_bwd(g, am, x.shape, k, s, p)) <= 1e-6
+
+
+def test_bn_large_vs_oracle():
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    rs = np.random.RandomState(3)
+    x = (rs.randn(32, 64, 28, 28) * 2 + 1).astype(np.float32)
+    gm, bt = (rs.rand(64) + 0.5).astype(np.float32), rs.randn(64).astype(np.float32)
+    tx, tg, tb = xs.tensor(x, requires_grad=True), nn.Parameter(gm), nn.Parameter(bt)
+    mm, mv = xs.zeros(64), xs.ones(64)
+    y = F.batch_norm(tx, tg, tb, mm, mv, 1, True, 1e-6, 0.99)
+    yr, xhat, sv, mm1, mv1 = X.batch_norm_fwd(x.astype(np.float64), gm, bt, np.zeros(64), np.ones(64), 1, 1e-6, 0.99)
+    assert X.rel_err(y.eval, yr) <= TOL
+    assert X.rel_err(mm.eval, mm1) <= TOL and X.rel_err(mv.eval, mv1) <= TOL
+    g = rs.randn(*x.shape).astype(np.float32)
+    y.backward(gradients=g)
+    dx, dg, db = X.batch_norm_bwd(g.astype(np.float64), xhat, sv, gm, 1)
+    assert X.rel_err(tx.grad.eval, dx) <= TOL
+    assert X.rel_err(tg.grad.eval, dg) <= TOL and X.rel_err(tb.grad.eval, db) <= TOL
+
+
+def test_no_silent_fallback_for_tensor_core_mode():
+    """Asking for a math mode whose kernel is not built must raise, never fall back."""
+    import xshinnosuke_b200 as xs
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.core.device import rt
+    a = xs.tensor(np.ones((4, 4), dtype=np.float32))
+    try:
+        lib.xsb_gemm(a.arr.ptr, a.arr.ptr, a.arr.ptr, None, 4, 4, 4, 0, 0, 0, 7, None, 0, rt.stream())
+    except RuntimeError:
+        return
+    # mode 7 does not exist: reaching here means a silent fallback
+    raise AssertionError("unknown math mode was accepted")

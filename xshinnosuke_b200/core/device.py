@@ -1,0 +1,279 @@
+"""Device plumbing under the Tensor: runtime singleton (device, stream, scratch) and DevArray,
+the owning handle of one fp32 / int64 buffer in HBM.
+
+Data layout in HBM: every 4-D array is stored channels-last ([N,H,W,C]; filters
+[OC,KH,KW,C]) while its *logical* shape stays the reference's NCHW / [OC,C,KH,KW]
+(xs/core/base.py:69-75: `.eval` is the universal NCHW read/write port). All other ranks are plain
+row-major. PyTorch is used only as the caching device allocator, for streams and for host<->device
+copies; every computation goes through libxsb200.
+"""
+import os
+
+import numpy as np
+
+from .._lib import MATH_FP32, MATH_TF32, lib
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+class Runtime:
+    """One process drives one GPU (LOCAL_RANK) from one host thread."""
+
+    WS_SMALL_FLOATS = 4 << 20     # BN / colsum partials + ticket counters (zero-initialised once)
+    WS_BIG_FLOATS = 48 << 20      # split-K partials of the FP32 implicit GEMM
+
+    def __init__(self):
+        self.ready = False
+        self.device = None
+        self.math_mode = MATH_FP32
+        self._ws_small = None
+        self._ws_big = None
+        self.launches = 0          # kernel-launching C-ABI calls issued (bench.py reports it)
+
+    def ensure(self):
+        if self.ready:
+            return self
+        t = torch()
+        if not t.cuda.is_available():
+            raise RuntimeError("xshinnosuke_b200 needs a CUDA device (sm_100a): there is no CPU fallback")
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        t.cuda.set_device(dev)
+        lib.xsb_init(dev)
+        self.device = t.device("cuda", dev)
+        self.ready = True
+        return self
+
+    def stream(self):
+        return torch().cuda.current_stream().cuda_stream
+
+    def empty(self, n, dtype="float32"):
+        t = torch()
+        return t.empty(int(n), dtype=t.float32 if dtype == "float32" else t.int64 if dtype == "int64" else t.uint8,
+                       device=self.device)
+
+    @property
+    def ws_small(self):
+        if self._ws_small is None:
+            self._ws_small = torch().zeros(self.WS_SMALL_FLOATS, dtype=torch().float32, device=self.device)
+        return self._ws_small
+
+    @property
+    def ws_big(self):
+        if self._ws_big is None:
+            self._ws_big = torch().empty(self.WS_BIG_FLOATS, dtype=torch().float32, device=self.device)
+        return self._ws_big
+
+    def synchronize(self):
+        torch().cuda.current_stream().synchronize()
+
+
+rt = Runtime()
+
+
+def set_math_mode(mode):
+    """'fp32' (CUDA-core FFMA, <=1e-5 vs the reference) or 'tf32' (tcgen05 tensor cores, <=2e-3)."""
+    m = {"fp32": MATH_FP32, "tf32": MATH_TF32, MATH_FP32: MATH_FP32, MATH_TF32: MATH_TF32}[mode]
+    rt.math_mode = m
+
+
+def get_math_mode():
+    return "fp32" if rt.math_mode == MATH_FP32 else "tf32"
+
+
+def _prod(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+class DevArray:
+    """A device buffer + logical shape. `cl` marks a 4-D array physically stored channels-last.
+
+    `pending_zero`: the contents are logically zero but have not been written. A kernel that
+    accumulates into the array asks `take_acc()` -- 0 ("=", and the flag clears) the first time,
+    1 ("+=") afterwards -- which is how `zero_grad` costs no memset and no read-modify-write
+    (the reference allocates and fills zeros: xs/utils/common.py:29-32, xs/core/base.py:312-316).
+    """
+    __slots__ = ("buf", "shape", "dtype", "cl", "_pz", "_root")
+
+    def __init__(self, buf, shape, dtype="float32", cl=None, pending_zero=False, _share=None):
+        self.buf = buf
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = dtype
+        self.cl = (len(self.shape) == 4 and dtype == "float32") if cl is None else cl
+        if _share is None:
+            self._pz = [bool(pending_zero)]   # one cell shared by an array and all its prefix views
+            self._root = None
+        else:
+            self._pz = _share._pz
+            self._root = _share if _share._root is None else _share._root
+
+    @property
+    def pending_zero(self):
+        return self._pz[0]
+
+    @pending_zero.setter
+    def pending_zero(self, v):
+        self._pz[0] = bool(v)
+
+    def _materialize_zero(self):
+        root = self if self._root is None else self._root
+        root.buf.zero_()
+        self._pz[0] = False
+
+    # ---- construction
+    @staticmethod
+    def empty(shape, dtype="float32", pending_zero=False):
+        rt.ensure()
+        shape = tuple(int(s) for s in shape)
+        return DevArray(rt.empty(max(_prod(shape), 1), dtype), shape, dtype, pending_zero=pending_zero)
+
+    @staticmethod
+    def zeros(shape, dtype="float32"):
+        a = DevArray.empty(shape, dtype)
+        a.buf.zero_()
+        return a
+
+    @staticmethod
+    def full(shape, value, dtype="float32"):
+        a = DevArray.empty(shape, dtype)
+        a.buf.fill_(value)
+        return a
+
+    @staticmethod
+    def from_numpy(a):
+        rt.ensure()
+        a = np.asarray(a)
+        if a.dtype.kind in "iu":
+            dtype, host = "int64", np.ascontiguousarray(a, dtype=np.int64)
+        else:
+            dtype, host = "float32", np.ascontiguousarray(a, dtype=np.float32)
+        shape = host.shape if host.ndim else (1,)  # 0-d scalars behave as shape (1,) (xs/core/base.py:82-84)
+        t = torch()
+        dev = t.from_numpy(host.reshape(-1)).to(rt.device)
+        out = DevArray(dev, shape, dtype)
+        if out.cl and out.size > 0:
+            n, c, h, w = out.shape
+            if c > 1 and h * w > 1:
+                dst = rt.empty(out.size)
+                lib.xsb_nchw_to_nhwc(dev.data_ptr(), dst.data_ptr(), n, c, h, w, 0, rt.stream())
+                rt.launches += 1
+                out.buf = dst
+        return out
+
+    # ---- properties
+    @property
+    def size(self):
+        return _prod(self.shape)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def ptr(self):
+        """Pointer for a kernel that will READ (or read-modify-write) the contents."""
+        if self.pending_zero:
+            self._materialize_zero()
+        return self.buf.data_ptr()
+
+    @property
+    def wptr(self):
+        """Pointer for a kernel that fully OVERWRITES the contents."""
+        self.pending_zero = False
+        return self.buf.data_ptr()
+
+    def take_acc(self):
+        """-> accumulate flag for a kernel that adds into this array (see class doc)."""
+        if self.pending_zero:
+            self.pending_zero = False
+            return 0
+        return 1
+
+    def peek_ptr(self):
+        return self.buf.data_ptr()
+
+    @property
+    def phys_shape(self):
+        if self.cl:
+            n, c, h, w = self.shape
+            return (n, h, w, c)
+        return self.shape
+
+    # ---- host transfer
+    def to_numpy(self):
+        rt.ensure()
+        if self.pending_zero:
+            return np.zeros(self.shape, dtype=np.float32 if self.dtype == "float32" else np.int64)
+        n = self.size
+        src = self.buf[:n] if self.buf.numel() != n else self.buf
+        if self.cl and n > 0:
+            nn_, c, h, w = self.shape
+            if c > 1 and h * w > 1:
+                tmp = rt.empty(n)
+                lib.xsb_nhwc_to_nchw(src.data_ptr(), tmp.data_ptr(), nn_, c, h, w, 0, rt.stream())
+                rt.launches += 1
+                src = tmp
+        return src.cpu().numpy().reshape(self.shape)
+
+    def assign_numpy(self, a):
+        """Overwrite the contents from a host array of the same logical shape (keeps the buffer:
+        parameter storage may be a view into the flat optimizer buffer)."""
+        new = DevArray.from_numpy(np.broadcast_to(np.asarray(a), self.shape))
+        if new.dtype != self.dtype:
+            raise TypeError(f"cannot assign {new.dtype} data to a {self.dtype} tensor")
+        self.buf[: max(self.size, 1)].copy_(new.buf[: max(self.size, 1)])
+        self.pending_zero = False
+
+    # ---- views / copies
+    def prefix(self, n):
+        """First n entries along axis 0 (contiguous in both layouts)."""
+        if n == self.shape[0]:
+            return self
+        per = self.size // self.shape[0] if self.shape[0] else 0
+        return DevArray(self.buf[: max(n * per, 1)], (n,) + self.shape[1:], self.dtype, self.cl, _share=self)
+
+    def clone(self):
+        if self.pending_zero:
+            return DevArray.empty(self.shape, self.dtype, pending_zero=True)
+        return DevArray(self.buf.clone(), self.shape, self.dtype, self.cl)
+
+    def logical_rowmajor(self):
+        """-> a DevArray whose physical order equals the logical (NCHW) row-major order."""
+        if not self.cl:
+            return self
+        n, c, h, w = self.shape
+        if c == 1 or h * w == 1:
+            return DevArray(self.buf, self.shape, self.dtype, cl=False, _share=self)
+        dst = rt.empty(self.size)
+        lib.xsb_nhwc_to_nchw(self.ptr, dst.data_ptr(), n, c, h, w, 0, rt.stream())
+        rt.launches += 1
+        return DevArray(dst, self.shape, self.dtype, cl=False)
+
+    def as_cl(self):
+        """4-D row-major (NCHW) -> channels-last physical order; no-op for everything else."""
+        if self.cl or len(self.shape) != 4 or self.dtype != "float32":
+            return self
+        n, c, h, w = self.shape
+        if c == 1 or h * w == 1:
+            return DevArray(self.buf, self.shape, self.dtype, cl=True, _share=self)
+        dst = rt.empty(self.size)
+        lib.xsb_nchw_to_nhwc(self.ptr, dst.data_ptr(), n, c, h, w, 0, rt.stream())
+        rt.launches += 1
+        return DevArray(dst, self.shape, self.dtype, cl=True)
+
+    def reshaped(self, shape):
+        """Reinterpret a row-major (non channels-last) buffer with a new logical shape (zero copy)."""
+        assert not self.cl
+        shape = tuple(int(s) for s in shape)
+        assert _prod(shape) == self.size, (shape, self.shape)
+        return DevArray(self.buf, shape, self.dtype, cl=False, _share=self)

@@ -1,0 +1,552 @@
+// BatchNorm (training branch) forward + backward and per-column sums, on row-major [R, C] fp32
+// (channels-last activations: R = N*H*W, C = channels; a Dense activation [N, F]: R = N, C = F).
+// Roofline: HBM. Algorithmic bytes: fwd 3e*n (x read for statistics, x read + y write
+// for the apply), bwd 5e*n (dy, x read for the two sums; dy, x read + dx write for the apply).
+//
+// Reference semantics: xs/nn/functional.py:676-740 -- batch mean and BIASED variance (np.mean/np.var,
+// i.e. a two-pass variance) over every axis but the channel axis, xhat = (x - mean)/sqrt(var + eps),
+// y = gamma*xhat + beta, running = momentum*running + (1 - momentum)*batch (biased variance, Q4).
+// xs/nn/grad_fn.py:379-411 -- dgamma += sum(dy*xhat), dbeta += sum(dy),
+// dx += (M*dxhat - sum(dxhat) - xhat*sum(dxhat*xhat)) / (M*sqrt(var + eps)), dxhat = dy*gamma.
+//
+// Variance numerics: one pass over x, but NOT E[x^2]-E[x]^2. Every thread accumulates sum(x-K) and
+// sum((x-K)^2) around a pivot K (its first element), converts to (count, mean, M2) and all partials are
+// combined with Chan's pairwise update -- as well conditioned as np.var's two passes at 1/2 the traffic.
+// The backward recomputes xhat from the retained input x and the saved mean / invstd instead of
+// caching a full xhat tensor (the reference caches xhat + sqrtvar).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRowUnroll = 8;
+constexpr int kMaxRowBlocks = 2 * 148;
+constexpr int kCounterSlots = 64;  // ws[0..63]: one "blocks done" ticket counter per column chunk
+
+struct Geom {
+    int V;        // channels per thread (4 or 1)
+    int CV;       // C / V
+    int LX, LY;   // thread tile: LX vector-columns x LY rows, LX*LY <= 256
+    int chunks;   // column chunks of LX vector-columns (grid.y)
+    int nb;       // row blocks (grid.x)
+    int rows_per_block;
+};
+
+static Geom make_geom(int64_t R, int C, bool vec4) {
+    Geom g;
+    g.V = vec4 ? 4 : 1;
+    g.CV = C / g.V;
+    g.LX = g.CV < kThreads ? g.CV : kThreads;
+    g.LY = kThreads / g.LX;
+    g.chunks = (g.CV + g.LX - 1) / g.LX;
+    int64_t nb = ceil_div64(R, (int64_t)g.LY * kRowUnroll);
+    if (nb > kMaxRowBlocks) nb = kMaxRowBlocks;
+    if (nb < 1) nb = 1;
+    g.rows_per_block = (int)ceil_div64(R, nb);
+    g.nb = (int)ceil_div64(R, g.rows_per_block);
+    return g;
+}
+
+template <int V>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[V]) {
+    if (V == 4) {
+        const float4 q = ldg_stream(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+struct Moments {  // count, mean, sum of squared deviations
+    float n, mean, m2;
+};
+__device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
+    if (b.n == 0.f) return a;
+    if (a.n == 0.f) return b;
+    Moments r;
+    r.n = a.n + b.n;
+    const float d = b.mean - a.mean;
+    const float fb = b.n / r.n;
+    r.mean = a.mean + d * fb;
+    r.m2 = a.m2 + b.m2 + d * d * a.n * fb;
+    return r;
+}
+
+// ------------------------------------------------------------------ forward statistics
+// grid (nb, chunks). ws layout (floats): [kCounterSlots counters][nb][C] mean | [nb][C] m2
+// (per-block row counts are re-derived from the row partition)
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+bn_stats_k(const float* __restrict__ x, int64_t R, int C, int LX, int LY, int rows_per_block, float* ws,
+           float* __restrict__ save_mean, float* __restrict__ save_invstd, float* running_mean, float* running_var,
+           float eps, float momentum) {
+    __shared__ float s_mean[kThreads * V];
+    __shared__ float s_m2[kThreads * V];
+    __shared__ float s_n[kThreads];
+    __shared__ unsigned s_ticket;
+
+    const int tid = threadIdx.x;
+    const int tx = tid % LX, ty = tid / LX;
+    const int CV = C / V;
+    const int cv = blockIdx.y * LX + tx;
+    const bool active = (ty < LY) && (cv < CV);
+    const int nb = gridDim.x;
+    unsigned* counters = reinterpret_cast<unsigned*>(ws);
+    float* p_mean = ws + kCounterSlots;
+    float* p_m2 = p_mean + (int64_t)nb * C;
+
+    float K[V], s1[V], s2[V];
+    float cnt = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { K[i] = 0.f; s1[i] = 0.f; s2[i] = 0.f; }
+    if (active) {
+        const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+        int64_t r_end = r_begin + rows_per_block;
+        if (r_end > R) r_end = R;
+        const float* base = x + (int64_t)cv * V;
+        int64_t r = r_begin + ty;
+        if (r < r_end) load_vec<V>(base + r * C, K);  // pivot = first element of this thread
+        for (; r + (int64_t)(kRowUnroll - 1) * LY < r_end; r += (int64_t)kRowUnroll * LY) {
+            float v[kRowUnroll][V];
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) load_vec<V>(base + (r + (int64_t)u * LY) * C, v[u]);
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float d = v[u][i] - K[i];
+                    s1[i] += d;
+                    s2[i] = fmaf(d, d, s2[i]);
+                }
+            cnt += (float)kRowUnroll;
+        }
+        for (; r < r_end; r += LY) {
+            float v[V];
+            load_vec<V>(base + r * C, v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float d = v[i] - K[i];
+                s1[i] += d;
+                s2[i] = fmaf(d, d, s2[i]);
+            }
+            cnt += 1.f;
+        }
+    }
+    // per-thread (n, mean, M2)
+    s_n[tid] = cnt;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float inv = cnt > 0.f ? 1.f / cnt : 0.f;
+        s_mean[tid * V + i] = K[i] + s1[i] * inv;
+        s_m2[tid * V + i] = fmaxf(s2[i] - s1[i] * s1[i] * inv, 0.f);
+    }
+    __syncthreads();
+    // tree over ty (rows of the thread tile)
+    int span = 1;
+    while (span < LY) span <<= 1;
+    for (int st = span >> 1; st > 0; st >>= 1) {
+        if (active && ty < st && ty + st < LY) {
+            const int o = tid + st * LX;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                Moments a{s_n[tid], s_mean[tid * V + i], s_m2[tid * V + i]};
+                Moments b{s_n[o], s_mean[o * V + i], s_m2[o * V + i]};
+                const Moments m = merge(a, b);
+                s_mean[tid * V + i] = m.mean;
+                s_m2[tid * V + i] = m.m2;
+                if (i == V - 1) s_n[tid] = m.n;
+            }
+        }
+        __syncthreads();
+    }
+    if (active && ty == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            p_mean[(int64_t)blockIdx.x * C + cv * V + i] = s_mean[tid * V + i];
+            p_m2[(int64_t)blockIdx.x * C + cv * V + i] = s_m2[tid * V + i];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&counters[blockIdx.y], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(nb - 1)) return;
+    __threadfence();
+    // ---- last block of this column chunk: combine the nb partials per channel (fixed order)
+    {
+        Moments acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = Moments{0.f, 0.f, 0.f};
+        if (active) {
+            for (int b = ty; b < nb; b += LY) {
+                const int64_t rb = (int64_t)b * rows_per_block;
+                int64_t re = rb + rows_per_block;
+                if (re > R) re = R;
+                const float nrows = (float)(re - rb);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    Moments pb{nrows, __ldcg(&p_mean[(int64_t)b * C + cv * V + i]),
+                               __ldcg(&p_m2[(int64_t)b * C + cv * V + i])};
+                    acc[i] = merge(acc[i], pb);
+                }
+            }
+        }
+        __syncthreads();
+        s_n[tid] = active ? acc[0].n : 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            s_mean[tid * V + i] = acc[i].mean;
+            s_m2[tid * V + i] = acc[i].m2;
+        }
+        __syncthreads();
+        for (int st = span >> 1; st > 0; st >>= 1) {
+            if (active && ty < st && ty + st < LY) {
+                const int o = tid + st * LX;
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    Moments a{s_n[tid], s_mean[tid * V + i], s_m2[tid * V + i]};
+                    Moments b{s_n[o], s_mean[o * V + i], s_m2[o * V + i]};
+                    const Moments m = merge(a, b);
+                    s_mean[tid * V + i] = m.mean;
+                    s_m2[tid * V + i] = m.m2;
+                    if (i == V - 1) s_n[tid] = m.n;
+                }
+            }
+            __syncthreads();
+        }
+        if (active && ty == 0) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const int c = cv * V + i;
+                const float mean = s_mean[tid * V + i];
+                const float var = s_m2[tid * V + i] / (float)R;
+                save_mean[c] = mean;
+                save_invstd[c] = 1.0f / sqrtf(var + eps);
+                if (running_mean) running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * mean;
+                if (running_var) running_var[c] = momentum * running_var[c] + (1.f - momentum) * var;
+            }
+        }
+        if (tid == 0) counters[blockIdx.y] = 0u;  // self-cleaning for the next launch
+    }
+}
+
+// ------------------------------------------------------------------ forward apply: y = gamma*(x-mean)*invstd + beta
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_k(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
+           const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+           int64_t nvec, int CV, int cv_mask) {
+    constexpr int U = 4;
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    float v[U][V];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < nvec) load_vec<V>(x + i * V, v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < nvec) {
+            const int c = (cv_mask >= 0 ? (int)((unsigned)i & (unsigned)cv_mask) : (int)(i % CV)) * V;
+            float o[V];
+#pragma unroll
+            for (int q = 0; q < V; ++q)
+                o[q] = fmaf((v[j][q] - __ldg(mean + c + q)) * __ldg(invstd + c + q), __ldg(gamma + c + q),
+                            __ldg(beta + c + q));
+            if (V == 4)
+                stg_stream(reinterpret_cast<float4*>(y + i * V), make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]));
+            else
+                y[i] = o[0];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward sums (and plain column sums)
+// kXhat: also accumulate sum(dy * xhat). ws: [counters][nb][C] s_dy | [nb][C] s_dyxhat
+// finalize writes dgamma/dbeta (+)= and coef[0..C)=sum_dy/M, coef[C..2C)=sum_dyxhat/M, coef[2C..3C)=gamma*invstd
+template <int V, bool kXhat>
+__global__ void __launch_bounds__(kThreads)
+col_sums_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+           const float* __restrict__ invstd, const float* __restrict__ gamma, int64_t R, int C, int LX, int LY,
+           int rows_per_block, float* ws, float* dgamma, float* dbeta, float* coef, int acc_gamma, int acc_beta) {
+    __shared__ float s_a[kThreads * V];
+    __shared__ float s_b[kThreads * V];
+    __shared__ unsigned s_ticket;
+    const int tid = threadIdx.x;
+    const int tx = tid % LX, ty = tid / LX;
+    const int CV = C / V;
+    const int cv = blockIdx.y * LX + tx;
+    const bool active = (ty < LY) && (cv < CV);
+    const int nb = gridDim.x;
+    unsigned* counters = reinterpret_cast<unsigned*>(ws);
+    float* p_a = ws + kCounterSlots;
+    float* p_b = p_a + (int64_t)nb * C;
+
+    float sa[V], sb[V], mu[V], is[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sa[i] = 0.f; sb[i] = 0.f; mu[i] = 0.f; is[i] = 0.f; }
+    if (active) {
+        if (kXhat) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { mu[i] = mean[cv * V + i]; is[i] = invstd[cv * V + i]; }
+        }
+        const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+        int64_t r_end = r_begin + rows_per_block;
+        if (r_end > R) r_end = R;
+        const int64_t coff = (int64_t)cv * V;
+        int64_t r = r_begin + ty;
+        constexpr int U = kXhat ? 4 : 8;
+        for (; r + (int64_t)(U - 1) * LY < r_end; r += (int64_t)U * LY) {
+            float g[U][V], xv[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                load_vec<V>(dy + (r + (int64_t)u * LY) * C + coff, g[u]);
+                if (kXhat) load_vec<V>(x + (r + (int64_t)u * LY) * C + coff, xv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    sa[i] += g[u][i];
+                    if (kXhat) sb[i] = fmaf(g[u][i], (xv[u][i] - mu[i]) * is[i], sb[i]);
+                }
+        }
+        for (; r < r_end; r += LY) {
+            float g[V], xv[V];
+            load_vec<V>(dy + r * C + coff, g);
+            if (kXhat) load_vec<V>(x + r * C + coff, xv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                sa[i] += g[i];
+                if (kXhat) sb[i] = fmaf(g[i], (xv[i] - mu[i]) * is[i], sb[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) { s_a[tid * V + i] = sa[i]; s_b[tid * V + i] = sb[i]; }
+    __syncthreads();
+    int span = 1;
+    while (span < LY) span <<= 1;
+    for (int st = span >> 1; st > 0; st >>= 1) {
+        if (active && ty < st && ty + st < LY) {
+            const int o = tid + st * LX;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                s_a[tid * V + i] += s_a[o * V + i];
+                if (kXhat) s_b[tid * V + i] += s_b[o * V + i];
+            }
+        }
+        __syncthreads();
+    }
+    if (active && ty == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            p_a[(int64_t)blockIdx.x * C + cv * V + i] = s_a[tid * V + i];
+            if (kXhat) p_b[(int64_t)blockIdx.x * C + cv * V + i] = s_b[tid * V + i];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&counters[blockIdx.y], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(nb - 1)) return;
+    __threadfence();
+    {
+        double da[V], db[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) { da[i] = 0.0; db[i] = 0.0; }
+        if (active) {
+            for (int b = ty; b < nb; b += LY) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    da[i] += (double)__ldcg(&p_a[(int64_t)b * C + cv * V + i]);
+                    if (kXhat) db[i] += (double)__ldcg(&p_b[(int64_t)b * C + cv * V + i]);
+                }
+            }
+        }
+        __syncthreads();
+        // cross-ty combine of <= LY partial sums in fp32
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            s_a[tid * V + i] = (float)da[i];
+            s_b[tid * V + i] = (float)db[i];
+        }
+        __syncthreads();
+        for (int st = span >> 1; st > 0; st >>= 1) {
+            if (active && ty < st && ty + st < LY) {
+                const int o = tid + st * LX;
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    s_a[tid * V + i] += s_a[o * V + i];
+                    if (kXhat) s_b[tid * V + i] += s_b[o * V + i];
+                }
+            }
+            __syncthreads();
+        }
+        if (active && ty == 0) {
+            const float invM = 1.0f / (float)R;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const int c = cv * V + i;
+                const float sdy = s_a[tid * V + i];
+                if (dbeta) dbeta[c] = acc_beta ? dbeta[c] + sdy : sdy;
+                if (kXhat) {
+                    const float sdyx = s_b[tid * V + i];
+                    if (dgamma) dgamma[c] = acc_gamma ? dgamma[c] + sdyx : sdyx;
+                    if (coef) {
+                        coef[c] = sdy * invM;
+                        coef[C + c] = sdyx * invM;
+                        coef[2 * C + c] = gamma[c] * invstd[c];
+                    }
+                }
+            }
+        }
+        if (tid == 0) counters[blockIdx.y] = 0u;
+    }
+}
+
+// ------------------------------------------------------------------ backward apply
+// dx (+)= gamma*invstd * (dy - sum_dy/M - xhat * sum_dyxhat/M)
+template <int V, bool kAcc>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_k(const float* __restrict__ dy, const float* __restrict__ x, float* dx, const float* __restrict__ mean,
+               const float* __restrict__ invstd, const float* __restrict__ coef, int64_t nvec, int CV, int C,
+               int cv_mask) {
+    constexpr int U = 4;
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    float g[U][V], xv[U][V];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < nvec) {
+            load_vec<V>(dy + i * V, g[j]);
+            load_vec<V>(x + i * V, xv[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < nvec) {
+            const int c = (cv_mask >= 0 ? (int)((unsigned)i & (unsigned)cv_mask) : (int)(i % CV)) * V;
+            float o[V];
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const float xhat = (xv[j][q] - __ldg(mean + c + q)) * __ldg(invstd + c + q);
+                o[q] = __ldg(coef + 2 * C + c + q) * (g[j][q] - __ldg(coef + c + q) - xhat * __ldg(coef + C + c + q));
+            }
+            if (V == 4) {
+                float4* p = reinterpret_cast<float4*>(dx + i * V);
+                float4 r = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+                if (kAcc) {
+                    const float4 d = *p;
+                    r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+                }
+                stg_stream(p, r);
+            } else {
+                dx[i] = kAcc ? dx[i] + o[0] : o[0];
+            }
+        }
+    }
+}
+
+inline bool use_vec4(int C, const void* a, const void* b = nullptr, const void* c = nullptr) {
+    return (C % 4 == 0) && aligned16(a) && (!b || aligned16(b)) && (!c || aligned16(c));
+}
+
+}  // namespace
+
+extern "C" {
+
+// Number of floats the `ws` scratch buffer must hold for a [R, C] problem. The buffer must be
+// zero-initialised once (the ticket counters at its head are self-cleaning afterwards).
+int64_t xsb_bn_workspace_floats(int64_t R, int C) {
+    (void)R;
+    return kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks + 3 * (int64_t)C;
+}
+
+// Training-mode forward. x,y [R,C]; gamma,beta,running_*,save_* [C]. running_* nullable.
+int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float* y, float* save_mean, float* save_invstd, int64_t R, int C, float eps, float momentum,
+                     float* ws, void* stream) {
+    XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
+    cudaStream_t s = xsb_stream(stream);
+    const bool v4 = use_vec4(C, x, y);
+    const Geom g = make_geom(R, C, v4);
+    XSB_CHECK_ARG(g.chunks <= kCounterSlots, "bn: C=%d too large", C);
+    dim3 grid(g.nb, g.chunks);
+    if (v4)
+        bn_stats_k<4><<<grid, kThreads, 0, s>>>(x, R, C, g.LX, g.LY, g.rows_per_block, ws, save_mean, save_invstd,
+                                                running_mean, running_var, eps, momentum);
+    else
+        bn_stats_k<1><<<grid, kThreads, 0, s>>>(x, R, C, g.LX, g.LY, g.rows_per_block, ws, save_mean, save_invstd,
+                                                running_mean, running_var, eps, momentum);
+    XSB_LAUNCH_CHECK();
+    const int64_t nvec = R * g.CV;
+    const int cv_mask = (g.CV & (g.CV - 1)) == 0 ? g.CV - 1 : -1;
+    const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
+    if (v4)
+        bn_apply_k<4><<<blocks, kThreads, 0, s>>>(x, y, save_mean, save_invstd, gamma, beta, nvec, g.CV, cv_mask);
+    else
+        bn_apply_k<1><<<blocks, kThreads, 0, s>>>(x, y, save_mean, save_invstd, gamma, beta, nvec, g.CV, cv_mask);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// Backward. dx nullable (input needs no grad); dgamma/dbeta nullable. acc_* : 1 = "+=", 0 = "=".
+int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+               float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
+               float* ws, void* stream) {
+    XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
+    cudaStream_t s = xsb_stream(stream);
+    const bool v4 = use_vec4(C, dy, x, dx);
+    const Geom g = make_geom(R, C, v4);
+    XSB_CHECK_ARG(g.chunks <= kCounterSlots, "bn: C=%d too large", C);
+    float* coef = ws + kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks;
+    dim3 grid(g.nb, g.chunks);
+    if (v4)
+        col_sums_k<4, true><<<grid, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, gamma, R, C, g.LX, g.LY,
+                                                      g.rows_per_block, ws, dgamma, dbeta, coef, acc_dgamma, acc_dbeta);
+    else
+        col_sums_k<1, true><<<grid, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, gamma, R, C, g.LX, g.LY,
+                                                      g.rows_per_block, ws, dgamma, dbeta, coef, acc_dgamma, acc_dbeta);
+    XSB_LAUNCH_CHECK();
+    if (dx) {
+        const int64_t nvec = R * g.CV;
+        const int cv_mask = (g.CV & (g.CV - 1)) == 0 ? g.CV - 1 : -1;
+        const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
+        if (v4) {
+            if (acc_dx)
+                bn_bwd_apply_k<4, true><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+            else
+                bn_bwd_apply_k<4, false><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+        } else {
+            if (acc_dx)
+                bn_bwd_apply_k<1, true><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+            else
+                bn_bwd_apply_k<1, false><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+        }
+        XSB_LAUNCH_CHECK();
+    }
+    return XSB_OK;
+}
+
+// out[c] (+)= sum_r x[r, c]   (bias gradients: conv db over N*OH*OW rows, Dense db over N rows)
+int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, float* ws, void* stream) {
+    XSB_CHECK_ARG(R > 0 && C > 0, "colsum: empty input");
+    cudaStream_t s = xsb_stream(stream);
+    const bool v4 = use_vec4(C, x);
+    const Geom g = make_geom(R, C, v4);
+    XSB_CHECK_ARG(g.chunks <= kCounterSlots, "colsum: C=%d too large", C);
+    dim3 grid(g.nb, g.chunks);
+    if (v4)
+        col_sums_k<4, false><<<grid, kThreads, 0, s>>>(x, nullptr, nullptr, nullptr, nullptr, R, C, g.LX, g.LY,
+                                                       g.rows_per_block, ws, nullptr, out, nullptr, 0, accumulate);
+    else
+        col_sums_k<1, false><<<grid, kThreads, 0, s>>>(x, nullptr, nullptr, nullptr, nullptr, R, C, g.LX, g.LY,
+                                                       g.rows_per_block, ws, nullptr, out, nullptr, 0, accumulate);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+}  // extern "C"

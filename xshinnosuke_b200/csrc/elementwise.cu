@@ -1,0 +1,360 @@
+// Bandwidth kernels: ReLU fwd/bwd (+bit mask for the in-place protocol), add, accumulate, fill,
+// NCHW<->NHWC layout transposes, small axis reductions.
+// Roofline: HBM. Algorithmic bytes (fp32): relu fwd 2e*n (+n/8 mask), bwd 3e*n, add 3e*n.
+// Reference semantics: xs/nn/td_functional.py:59-60 (relu = maximum(0, x)),
+// xs/nn/grad_fn.py:146-157 (mask is x < 0: gradient passes at x == 0), xs/nn/functional.py:6-21 (add).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;  // float4 per thread -> 16 KB per CTA in flight
+
+__device__ __forceinline__ float relu1(float v) { return fmaxf(v, 0.0f); }
+
+// ---- ReLU forward, vector path: n % 8 == 0, 16B aligned ---------------------------------------
+template <bool kMask>
+__global__ void __launch_bounds__(kThreads) relu_fwd_vec(const float4* x, float4* y,
+                                                         uint8_t* __restrict__ mask, int64_t n4) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    float4 v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        v[j] = (i < n4) ? ldg_stream_rw(x + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (kMask) {
+            // bit e of the mask <=> x[e] < 0 (gradient blocked). Two lanes share one byte.
+            unsigned nib = (v[j].x < 0.f ? 1u : 0u) | (v[j].y < 0.f ? 2u : 0u) | (v[j].z < 0.f ? 4u : 0u) |
+                           (v[j].w < 0.f ? 8u : 0u);
+            const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
+            if ((threadIdx.x & 1) == 0 && i < n4) mask[i >> 1] = (uint8_t)(nib | (hi << 4));
+        }
+        if (i < n4) {
+            float4 r = make_float4(relu1(v[j].x), relu1(v[j].y), relu1(v[j].z), relu1(v[j].w));
+            stg_stream(y + i, r);
+        }
+    }
+}
+
+// scalar path: one thread per mask byte (8 elements); any n, any alignment
+__global__ void relu_fwd_scalar(const float* x, float* y, uint8_t* __restrict__ mask,
+                                int64_t n) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e0 = b * 8;
+    if (e0 >= n) return;
+    unsigned bits = 0;
+    for (int j = 0; j < 8 && e0 + j < n; ++j) {
+        const float v = x[e0 + j];
+        if (v < 0.f) bits |= 1u << j;
+        y[e0 + j] = relu1(v);
+    }
+    if (mask) mask[b] = (uint8_t)bits;
+}
+
+// ---- ReLU backward from the retained input: dx (+)= dy * [x >= 0] ----------------------------
+template <bool kAcc>
+__global__ void __launch_bounds__(kThreads) relu_bwd_vec(const float4* __restrict__ dy, const float4* __restrict__ x,
+                                                         float4* dx, int64_t n4) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    float4 g[kUnroll], v[kUnroll], a[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) {
+            g[j] = ldg_stream(dy + i);
+            v[j] = ldg_stream(x + i);
+            if (kAcc) a[j] = dx[i];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) {
+            float4 r;
+            r.x = v[j].x < 0.f ? 0.f : g[j].x;
+            r.y = v[j].y < 0.f ? 0.f : g[j].y;
+            r.z = v[j].z < 0.f ? 0.f : g[j].z;
+            r.w = v[j].w < 0.f ? 0.f : g[j].w;
+            if (kAcc) { r.x += a[j].x; r.y += a[j].y; r.z += a[j].z; r.w += a[j].w; }
+            stg_stream(dx + i, r);
+        }
+    }
+}
+
+__global__ void relu_bwd_scalar(const float* __restrict__ dy, const float* __restrict__ x, float* dx, int64_t n,
+                                int acc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float r = x[i] < 0.f ? 0.f : dy[i];
+    dx[i] = acc ? dx[i] + r : r;
+}
+
+// ---- ReLU backward from the bit mask (in-place protocol; dx may alias dy) --------------------
+template <bool kAcc>
+__global__ void __launch_bounds__(kThreads) relu_bwd_mask_vec(const float4* dy, const uint8_t* __restrict__ mask,
+                                                              float4* dx, int64_t n4) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) {
+            const float4 g = dy[i];
+            const unsigned m = (mask[i >> 1] >> ((i & 1) * 4)) & 0xFu;
+            float4 r;
+            r.x = (m & 1u) ? 0.f : g.x;
+            r.y = (m & 2u) ? 0.f : g.y;
+            r.z = (m & 4u) ? 0.f : g.z;
+            r.w = (m & 8u) ? 0.f : g.w;
+            if (kAcc) {
+                const float4 a = dx[i];
+                r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+            }
+            dx[i] = r;
+        }
+    }
+}
+
+__global__ void relu_bwd_mask_scalar(const float* dy, const uint8_t* __restrict__ mask, float* dx, int64_t n,
+                                     int acc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float r = ((mask[i >> 3] >> (i & 7)) & 1u) ? 0.f : dy[i];
+    dx[i] = acc ? dx[i] + r : r;
+}
+
+// ---- y = a + b ; dst += src ; fill -----------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) add_vec(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                    float4* __restrict__ y, int64_t n4) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    float4 u[kUnroll], v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) { u[j] = ldg_stream(a + i); v[j] = ldg_stream(b + i); }
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) stg_stream(y + i, make_float4(u[j].x + v[j].x, u[j].y + v[j].y, u[j].z + v[j].z, u[j].w + v[j].w));
+    }
+}
+__global__ void add_scalar(const float* a, const float* b, float* y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a[i] + b[i];
+}
+
+__global__ void __launch_bounds__(kThreads) axpy_vec(float4* dst, const float4* __restrict__ src, float alpha,
+                                                     int64_t n4) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) {
+            float4 d = dst[i];
+            const float4 s = ldg_stream(src + i);
+            d.x += alpha * s.x; d.y += alpha * s.y; d.z += alpha * s.z; d.w += alpha * s.w;
+            dst[i] = d;
+        }
+    }
+}
+__global__ void axpy_scalar(float* dst, const float* src, float alpha, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += alpha * src[i];
+}
+
+__global__ void fill_k(float* dst, float v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = v;
+}
+
+// ---- layout: per image transpose [rows, cols] -> [cols, rows] through a padded smem tile -----
+// nchw->nhwc: rows = C, cols = H*W ; nhwc->nchw: rows = H*W, cols = C.
+template <bool kAcc>
+__global__ void transpose_batched(const float* __restrict__ src, float* dst, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int64_t img = (int64_t)blockIdx.z * rows * cols;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[img + (int64_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            float* p = dst + img + (int64_t)c * rows + r;
+            *p = kAcc ? *p + tile[threadIdx.x][j] : tile[threadIdx.x][j];
+        }
+    }
+}
+
+// ---- y[o,i] = scale * sum_r x[o,r,i] ; dx[o,r,i] (+)= scale * dy[o,i] -------------------------
+__global__ void reduce_axis_k(const float* __restrict__ x, float* __restrict__ y, int64_t outer, int64_t red,
+                              int64_t inner, float scale) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= outer * inner) return;
+    const int64_t o = t / inner, i = t % inner;
+    const float* p = x + o * red * inner + i;
+    double acc = 0.0;
+    for (int64_t r = 0; r < red; ++r) acc += (double)p[r * inner];
+    y[t] = (float)(acc * (double)scale);
+}
+__global__ void broadcast_axis_k(const float* __restrict__ dy, float* dx, int64_t outer, int64_t red, int64_t inner,
+                                 float scale, int acc) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= outer * red * inner) return;
+    const int64_t i = t % inner, o = t / (red * inner);
+    const float v = scale * dy[o * inner + i];
+    dx[t] = acc ? dx[t] + v : v;
+}
+
+inline bool vec_ok(int64_t n, const void* a, const void* b = nullptr, const void* c = nullptr) {
+    return (n % 8 == 0) && aligned16(a) && (!b || aligned16(b)) && (!c || aligned16(c));
+}
+inline unsigned vec_blocks(int64_t n4) { return (unsigned)ceil_div64(n4, (int64_t)kThreads * kUnroll); }
+
+}  // namespace
+
+extern "C" {
+
+// y = max(0, x). y may alias x. mask (nullable): ceil(n/8) bytes, bit e set <=> x[e] < 0.
+int xsb_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (vec_ok(n, x, y)) {
+        const int64_t n4 = n / 4;
+        if (mask)
+            relu_fwd_vec<true><<<vec_blocks(n4), kThreads, 0, s>>>((const float4*)x, (float4*)y, mask, n4);
+        else
+            relu_fwd_vec<false><<<vec_blocks(n4), kThreads, 0, s>>>((const float4*)x, (float4*)y, nullptr, n4);
+    } else {
+        const int64_t nb = ceil_div64(n, 8);
+        relu_fwd_scalar<<<(unsigned)ceil_div64(nb, 256), 256, 0, s>>>(x, y, mask, n);
+    }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// dx (+)= dy * [x >= 0]   (x = the tensor ReLU was applied to)
+int xsb_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, int accumulate, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (vec_ok(n, dy, x, dx)) {
+        const int64_t n4 = n / 4;
+        if (accumulate)
+            relu_bwd_vec<true><<<vec_blocks(n4), kThreads, 0, s>>>((const float4*)dy, (const float4*)x, (float4*)dx, n4);
+        else
+            relu_bwd_vec<false><<<vec_blocks(n4), kThreads, 0, s>>>((const float4*)dy, (const float4*)x, (float4*)dx, n4);
+    } else {
+        relu_bwd_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(dy, x, dx, n, accumulate);
+    }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// dx (+)= dy * [mask bit clear]; dx may alias dy (in-place ReLU backward masks outputs.grad in place)
+int xsb_relu_bwd_mask(const float* dy, const uint8_t* mask, float* dx, int64_t n, int accumulate, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (vec_ok(n, dy, dx)) {
+        const int64_t n4 = n / 4;
+        if (accumulate)
+            relu_bwd_mask_vec<true><<<vec_blocks(n4), kThreads, 0, s>>>((const float4*)dy, mask, (float4*)dx, n4);
+        else
+            relu_bwd_mask_vec<false><<<vec_blocks(n4), kThreads, 0, s>>>((const float4*)dy, mask, (float4*)dx, n4);
+    } else {
+        relu_bwd_mask_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(dy, mask, dx, n, accumulate);
+    }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_add(const float* a, const float* b, float* y, int64_t n, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (vec_ok(n, a, b, y))
+        add_vec<<<vec_blocks(n / 4), kThreads, 0, s>>>((const float4*)a, (const float4*)b, (float4*)y, n / 4);
+    else
+        add_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(a, b, y, n);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// dst += alpha * src
+int xsb_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (vec_ok(n, dst, src))
+        axpy_vec<<<vec_blocks(n / 4), kThreads, 0, s>>>((float4*)dst, (const float4*)src, alpha, n / 4);
+    else
+        axpy_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(dst, src, alpha, n);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_fill(float* dst, float value, int64_t n, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (value == 0.0f) {
+        XSB_CUDA(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(float), s));
+        return XSB_OK;
+    }
+    const unsigned blocks = (unsigned)(ceil_div64(n, 256) < 148 * 8 ? ceil_div64(n, 256) : 148 * 8);
+    fill_k<<<blocks, 256, 0, s>>>(dst, value, n);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// Logical NCHW (host/API order) -> device channels-last. dst (+)= if accumulate.
+int xsb_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int accumulate, void* stream) {
+    const int rows = C, cols = H * W;
+    if (N <= 0 || rows <= 0 || cols <= 0) return XSB_OK;
+    XSB_CHECK_ARG(N <= 65535, "batch %d exceeds grid.z", N);
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, N), block(32, 8);
+    if (accumulate)
+        transpose_batched<true><<<grid, block, 0, xsb_stream(stream)>>>(src, dst, rows, cols);
+    else
+        transpose_batched<false><<<grid, block, 0, xsb_stream(stream)>>>(src, dst, rows, cols);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int accumulate, void* stream) {
+    const int rows = H * W, cols = C;
+    if (N <= 0 || rows <= 0 || cols <= 0) return XSB_OK;
+    XSB_CHECK_ARG(N <= 65535, "batch %d exceeds grid.z", N);
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, N), block(32, 8);
+    if (accumulate)
+        transpose_batched<true><<<grid, block, 0, xsb_stream(stream)>>>(src, dst, rows, cols);
+    else
+        transpose_batched<false><<<grid, block, 0, xsb_stream(stream)>>>(src, dst, rows, cols);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// y[outer, inner] = scale * sum over the middle axis of x[outer, red, inner]
+int xsb_reduce_axis(const float* x, float* y, int64_t outer, int64_t red, int64_t inner, float scale, void* stream) {
+    const int64_t n = outer * inner;
+    if (n <= 0) return XSB_OK;
+    reduce_axis_k<<<(unsigned)ceil_div64(n, 128), 128, 0, xsb_stream(stream)>>>(x, y, outer, red, inner, scale);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// dx[outer, red, inner] (+)= scale * dy[outer, inner]
+int xsb_broadcast_axis(const float* dy, float* dx, int64_t outer, int64_t red, int64_t inner, float scale,
+                       int accumulate, void* stream) {
+    const int64_t n = outer * red * inner;
+    if (n <= 0) return XSB_OK;
+    broadcast_axis_k<<<(unsigned)ceil_div64(n, 256), 256, 0, xsb_stream(stream)>>>(dy, dx, outer, red, inner, scale,
+                                                                                  accumulate);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+}  // extern "C"

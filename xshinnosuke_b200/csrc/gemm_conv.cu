@@ -1,0 +1,109 @@
+// Dense GEMM and conv2d forward / dgrad / wgrad entry points.
+// math_mode XSB_MATH_FP32 (0): CUDA-core FFMA implicit GEMM (igemm_ffma.cuh) -- fp32 in, fp32 FMA accumulate.
+// math_mode XSB_MATH_TF32 (1): tcgen05 tensor-core implicit GEMM (conv_tc.cu / gemm_tc.cu) where the shape is
+//   supported by those kernels; the entry point reports XSB_ERR_UNSUPPORTED otherwise (no silent fallback).
+//
+// Layouts (device): activations channels-last [N,H,W,C]; filters [OC,KH,KW,C]; Dense weight [in,out] row-major
+// (XS stores Dense kernels un-transposed, xs/layers/linear.py:32). API-level NCHW <-> channels-last conversion
+// is done by xsb_nchw_to_nhwc / xsb_nhwc_to_nchw at the Tensor boundary, not here.
+//
+// Reference arithmetic: xs/nn/functional.py:405-442 (conv2d = im2col . W^T + b), xs/nn/grad_fn.py:186-203
+// (dW = dY^T . col, db = sum dY, dX = col2im(dY . W)), xs/nn/functional.py:81-120 + grad_fn.py:73-99 (Dense).
+// FLOPs: 2*N*OH*OW*C*KH*KW*OC for each of fwd / dgrad / wgrad.
+#include "igemm_ffma.cuh"
+
+using namespace igemm;
+
+// implemented in conv_tc.cu (tcgen05). Return XSB_ERR_UNSUPPORTED when the shape is outside their envelope.
+int xsb_tc_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
+                int transB, int accumulate, float* ws, int64_t ws_floats, cudaStream_t s);
+int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
+                    int64_t ws_floats, cudaStream_t s);
+int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
+                      int64_t ws_floats, cudaStream_t s);
+int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
+                      int64_t ws_floats, cudaStream_t s);
+
+namespace {
+
+bool fill_geom(ConvGeom& g, int N, int H, int W, int C, int OC, int KH, int KW, int sh, int sw, int pad) {
+    g.N = N; g.H = H; g.W = W; g.C = C; g.OC = OC; g.KH = KH; g.KW = KW; g.sh = sh; g.sw = sw; g.pad = pad;
+    g.OH = (H - KH + 2 * pad) / sh + 1;  // xs/nn/functional.py:415-416
+    g.OW = (W - KW + 2 * pad) / sw + 1;
+    return N > 0 && C > 0 && OC > 0 && KH > 0 && KW > 0 && sh > 0 && sw > 0 && pad >= 0 && g.OH > 0 && g.OW > 0 &&
+           (int64_t)N * H * W < (int64_t)1 << 31 && (int64_t)N * g.OH * g.OW < (int64_t)1 << 31 &&
+           (int64_t)KH * KW * C < (int64_t)1 << 31;
+}
+
+}  // namespace
+
+extern "C" {
+
+// C[M,N] (+)= op(A) . op(B) (+ bias[N]); row-major. transA: A stored [K,M]; transB: B stored [N,K].
+int xsb_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
+             int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, void* stream) {
+    cudaStream_t s = xsb_stream(stream);
+    if (math_mode != 0) return xsb_tc_gemm(A, B, C, bias, M, N, K, transA, transB, accumulate, ws, ws_floats, s);
+    const bool split_ok = true;
+    if (!transA && !transB) {
+        MatK la{A, K, M, K, K % 4 == 0 && aligned16(A)};
+        MatR lb{B, N, N, K, N % 4 == 0 && aligned16(B)};
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+    } else if (!transA && transB) {
+        MatK la{A, K, M, K, K % 4 == 0 && aligned16(A)};
+        MatK lb{B, K, N, K, K % 4 == 0 && aligned16(B)};
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+    } else if (transA && !transB) {
+        MatR la{A, M, M, K, M % 4 == 0 && aligned16(A)};
+        MatR lb{B, N, N, K, N % 4 == 0 && aligned16(B)};
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+    } else {
+        MatR la{A, M, M, K, M % 4 == 0 && aligned16(A)};
+        MatK lb{B, K, N, K, K % 4 == 0 && aligned16(B)};
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+    }
+}
+
+// y[N,OH,OW,OC] = conv(x[N,H,W,C], w[OC,KH,KW,C]) (+ bias[OC])
+int xsb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int C, int OC,
+                   int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws, int64_t ws_floats,
+                   void* stream) {
+    ConvGeom g;
+    XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_fwd: bad geometry");
+    cudaStream_t s = xsb_stream(stream);
+    if (math_mode != 0) return xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s);
+    const int P = N * g.OH * g.OW, J = KH * KW * C;
+    PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
+    MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};
+    return launch(la, lb, y, OC, bias, P, OC, J, 0, true, ws, ws_floats, s);
+}
+
+// dx[N,H,W,C] (+)= sum_{kh,kw,oc} dy[n,(h+p-kh)/sh,(w+p-kw)/sw,oc] * w[oc,kh,kw,c]
+int xsb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int C, int OC, int KH, int KW,
+                     int sh, int sw, int pad, int accumulate, int math_mode, float* ws, int64_t ws_floats,
+                     void* stream) {
+    ConvGeom g;
+    XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_dgrad: bad geometry");
+    cudaStream_t s = xsb_stream(stream);
+    if (math_mode != 0) return xsb_tc_conv_dgrad(dy, w, dx, g, accumulate, ws, ws_floats, s);
+    const int P = N * H * W, J = KH * KW * OC;
+    DgradA la{dy, g, P, J, OC % 4 == 0 && aligned16(dy)};
+    DgradB lb{w, g, J, C % 4 == 0 && aligned16(w)};
+    return launch(la, lb, dx, C, nullptr, P, C, J, accumulate, true, ws, ws_floats, s);
+}
+
+// dw[OC,KH,KW,C] (+)= sum_{n,oh,ow} dy[n,oh,ow,oc] * x[n,oh*sh-p+kh,ow*sw-p+kw,c]
+int xsb_conv2d_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int C, int OC, int KH, int KW,
+                     int sh, int sw, int pad, int accumulate, int math_mode, float* ws, int64_t ws_floats,
+                     void* stream) {
+    ConvGeom g;
+    XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_wgrad: bad geometry");
+    cudaStream_t s = xsb_stream(stream);
+    if (math_mode != 0) return xsb_tc_conv_wgrad(dy, x, dw, g, accumulate, ws, ws_floats, s);
+    const int P = N * g.OH * g.OW, J = KH * KW * C;
+    MatR la{dy, OC, OC, P, OC % 4 == 0 && aligned16(dy)};  // A[m=oc][k=pixel] = dy[pixel*OC + oc]
+    PatchB lb{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
+    return launch(la, lb, dw, J, nullptr, OC, J, P, accumulate, true, ws, ws_floats, s);
+}
+
+}  // extern "C"

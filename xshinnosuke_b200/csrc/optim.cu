@@ -1,0 +1,126 @@
+// Fused multi-tensor optimizer step over ONE flat parameter buffer (all parameters of the model live
+// contiguously, gradients in a parallel flat buffer in the same order).
+// Roofline: HBM. Algorithmic bytes: SGD 3e*P (p, g read; p write), Adam 7e*P (p, g, m, v read; p, m, v write).
+// Reference: xs/optim/sgd.py:5-9 (p -= lr*g, weight_decay never applied, Q8);
+// xs/optim/adam.py:13-30 (v = b1 v + (1-b1) g; m = b2 m + (1-b2) g^2;
+//   p -= lr * (v/(1-b1^t)) / (sqrt(m/(1-b2^t)) + eps); v is the FIRST moment, m the second).
+// grad_scale folds the data-parallel 1/world averaging of the all-reduced gradient sum into the update.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+__global__ void __launch_bounds__(kThreads)
+sgd_vec(float4* p, const float4* __restrict__ g, int64_t n4, float step) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    float4 pv[kUnroll], gv[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) { pv[j] = p[i]; gv[j] = ldg_stream(g + i); }
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) {
+            pv[j].x -= step * gv[j].x; pv[j].y -= step * gv[j].y; pv[j].z -= step * gv[j].z; pv[j].w -= step * gv[j].w;
+            p[i] = pv[j];
+        }
+    }
+}
+__global__ void sgd_scalar(float* p, const float* __restrict__ g, int64_t n, float step) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] -= step * g[i];
+}
+
+__device__ __forceinline__ float adam1(float& p, float g, float& v, float& m, float b1, float b2, float lr,
+                                       float inv_c1, float inv_c2, float eps) {
+    v = b1 * v + (1.f - b1) * g;
+    m = b2 * m + (1.f - b2) * g * g;
+    p -= lr * ((v * inv_c1) / (sqrtf(m * inv_c2) + eps));
+    return p;
+}
+
+// `step` is a device-resident counter (already incremented for this update) so the kernel can be
+// replayed from a CUDA graph with a changing bias correction.
+__global__ void __launch_bounds__(kThreads)
+adam_vec(float4* p, const float4* __restrict__ g, float4* v, float4* m, int64_t n4, float lr, float b1, float b2,
+         float eps, float gscale, const int* __restrict__ step) {
+    __shared__ float s_c[2];
+    if (threadIdx.x == 0) {
+        const double t = (double)step[0];
+        s_c[0] = (float)(1.0 / (1.0 - pow((double)b1, t)));
+        s_c[1] = (float)(1.0 / (1.0 - pow((double)b2, t)));
+    }
+    __syncthreads();
+    const float ic1 = s_c[0], ic2 = s_c[1];
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * 2) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) {
+            float4 pv = p[i], vv = v[i], mv = m[i];
+            float4 gv = ldg_stream(g + i);
+            gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
+            adam1(pv.x, gv.x, vv.x, mv.x, b1, b2, lr, ic1, ic2, eps);
+            adam1(pv.y, gv.y, vv.y, mv.y, b1, b2, lr, ic1, ic2, eps);
+            adam1(pv.z, gv.z, vv.z, mv.z, b1, b2, lr, ic1, ic2, eps);
+            adam1(pv.w, gv.w, vv.w, mv.w, b1, b2, lr, ic1, ic2, eps);
+            p[i] = pv; v[i] = vv; m[i] = mv;
+        }
+    }
+}
+__global__ void adam_scalar(float* p, const float* __restrict__ g, float* v, float* m, int64_t n, float lr, float b1,
+                            float b2, float eps, float gscale, const int* __restrict__ step) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double t = (double)step[0];
+    const float ic1 = (float)(1.0 / (1.0 - pow((double)b1, t)));
+    const float ic2 = (float)(1.0 / (1.0 - pow((double)b2, t)));
+    adam1(p[i], g[i] * gscale, v[i], m[i], b1, b2, lr, ic1, ic2, eps);
+}
+
+__global__ void counter_inc_k(int* c) { c[0] += 1; }
+
+}  // namespace
+
+extern "C" {
+
+// p[i] -= lr * grad_scale * g[i] over the whole flat buffer (n floats)
+int xsb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    const float step = lr * grad_scale;
+    if (n % 4 == 0 && aligned16(p) && aligned16(g))
+        sgd_vec<<<(unsigned)ceil_div64(n / 4, (int64_t)kThreads * kUnroll), kThreads, 0, s>>>((float4*)p,
+                                                                                             (const float4*)g, n / 4, step);
+    else
+        sgd_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(p, g, n, step);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// `step_dev`: device int holding t (1-based) for THIS update; see xsb_counter_inc.
+int xsb_adam_step(float* p, const float* g, float* v, float* m, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float grad_scale, const int* step_dev, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (n % 4 == 0 && aligned16(p) && aligned16(g) && aligned16(v) && aligned16(m))
+        adam_vec<<<(unsigned)ceil_div64(n / 4, (int64_t)kThreads * 2), kThreads, 0, s>>>(
+            (float4*)p, (const float4*)g, (float4*)v, (float4*)m, n / 4, lr, beta1, beta2, eps, grad_scale, step_dev);
+    else
+        adam_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(p, g, v, m, n, lr, beta1, beta2, eps, grad_scale,
+                                                                 step_dev);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_counter_inc(int* counter_dev, void* stream) {
+    counter_inc_k<<<1, 1, 0, xsb_stream(stream)>>>(counter_dev);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+}  // extern "C"

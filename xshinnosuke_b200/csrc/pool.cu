@@ -1,0 +1,235 @@
+// max_pool2d (with argmax) and avg_pool2d, forward + backward, on channels-last [N,H,W,C] fp32.
+// Roofline: HBM. Algorithmic bytes: fwd 4*(NHWC + N*OH*OW*C) + 1*N*OH*OW*C,
+// bwd 4*(N*OH*OW*C + NHWC) + 1*N*OH*OW*C.
+//
+// Reference semantics (xs/nn/functional.py:445-491, xs/nn/grad_fn.py:206-235):
+//  * the window is taken on a ZERO-padded input (not -inf), OH = (H + 2p - k)//s + 1;
+//  * argmax is the index ky*k+kx of the FIRST maximum of the k*k window (np.argmax), stored flat in
+//    (n, oh, ow, c) order -- exactly the channels-last order used here, so the u8 array this kernel
+//    writes is the reference's int64 `pool_argmax` element for element;
+//  * backward scatters dY to that slot and overlap-adds (col2im); slots that fall in the padding
+//    are cropped away. Here: each input pixel GATHERS from the <= ceil(k/s)^2 windows covering it
+//    (no atomics, deterministic, supports accumulate).
+#include "common.cuh"
+
+namespace {
+
+// V = channels per thread (4 -> float4, 1 -> scalar). Grids are (ceil(W*CV/256), rows, N): no 64-bit div.
+template <int V>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W,
+              int C, int OH, int OW, int k, int sh, int sw, int pad) {
+    const unsigned CV = C / V;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)OW * CV) return;
+    const int cv = (int)(t % CV);
+    const int ow = (int)(t / CV);
+    const int oh = blockIdx.y;
+    const int n = blockIdx.z;
+    const int h0 = oh * sh - pad, w0 = ow * sw - pad;
+    float best[V];
+    int arg[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best[i] = 0.f; arg[i] = 0; }
+    bool first = true;
+    for (int ky = 0; ky < k; ++ky) {
+        const int h = h0 + ky;
+        for (int kx = 0; kx < k; ++kx) {
+            const int w = w0 + kx;
+            float v[V];
+            if (h >= 0 && h < H && w >= 0 && w < W) {
+                const float* p = x + (((int64_t)n * H + h) * W + w) * C + (int64_t)cv * V;
+                if (V == 4) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                    v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w;
+                } else {
+                    v[0] = __ldg(p);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = 0.f;  // zero padding takes part in the max
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                if (first || v[i] > best[i]) { best[i] = v[i]; arg[i] = ky * k + kx; }
+            }
+            first = false;
+        }
+    }
+    const int64_t o = (((int64_t)n * OH + oh) * OW + ow) * C + (int64_t)cv * V;
+    if (V == 4) {
+        *reinterpret_cast<float4*>(y + o) = make_float4(best[0], best[1 % V], best[2 % V], best[3 % V]);
+        if (amax)
+            *reinterpret_cast<uchar4*>(amax + o) =
+                make_uchar4((unsigned char)arg[0], (unsigned char)arg[1 % V], (unsigned char)arg[2 % V],
+                            (unsigned char)arg[3 % V]);
+    } else {
+        y[o] = best[0];
+        if (amax) amax[o] = (uint8_t)arg[0];
+    }
+}
+
+template <int V, bool kAcc>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_k(const float* __restrict__ dy, const uint8_t* __restrict__ amax, float* dx, int N, int H, int W, int C,
+              int OH, int OW, int k, int sh, int sw, int pad) {
+    const unsigned CV = C / V;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)W * CV) return;
+    const int cv = (int)(t % CV);
+    const int w = (int)(t / CV);
+    const int h = blockIdx.y;
+    const int n = blockIdx.z;
+    // windows oh with oh*sh - pad <= h <= oh*sh - pad + k - 1
+    const int hp = h + pad, wp = w + pad;
+    int oh_lo = hp - k + 1;
+    oh_lo = oh_lo <= 0 ? 0 : (oh_lo + sh - 1) / sh;
+    int oh_hi = hp / sh;
+    if (oh_hi > OH - 1) oh_hi = OH - 1;
+    int ow_lo = wp - k + 1;
+    ow_lo = ow_lo <= 0 ? 0 : (ow_lo + sw - 1) / sw;
+    int ow_hi = wp / sw;
+    if (ow_hi > OW - 1) ow_hi = OW - 1;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+            const int slot = (hp - oh * sh) * k + (wp - ow * sw);
+            const int64_t o = (((int64_t)n * OH + oh) * OW + ow) * C + (int64_t)cv * V;
+            if (V == 4) {
+                const uchar4 a = __ldg(reinterpret_cast<const uchar4*>(amax + o));
+                const float4 g = __ldg(reinterpret_cast<const float4*>(dy + o));
+                if (a.x == slot) acc[0] += g.x;
+                if (a.y == slot) acc[1 % V] += g.y;
+                if (a.z == slot) acc[2 % V] += g.z;
+                if (a.w == slot) acc[3 % V] += g.w;
+            } else {
+                if (__ldg(amax + o) == slot) acc[0] += __ldg(dy + o);
+            }
+        }
+    }
+    const int64_t xi = (((int64_t)n * H + h) * W + w) * C + (int64_t)cv * V;
+    if (V == 4) {
+        float4 out = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+        if (kAcc) {
+            const float4 d = *reinterpret_cast<const float4*>(dx + xi);
+            out.x += d.x; out.y += d.y; out.z += d.z; out.w += d.w;
+        }
+        *reinterpret_cast<float4*>(dx + xi) = out;
+    } else {
+        dx[xi] = kAcc ? dx[xi] + acc[0] : acc[0];
+    }
+}
+
+// avg pool (padding == 0 only: the reference's padded variant is broken)
+__global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int OH,
+                              int OW, int k, int sh, int sw) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)OW * C) return;
+    const int c = (int)(t % (unsigned)C);
+    const int ow = (int)(t / (unsigned)C);
+    const int oh = blockIdx.y;
+    const int n = blockIdx.z;
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx)
+            acc += __ldg(x + (((int64_t)n * H + oh * sh + ky) * W + ow * sw + kx) * C + c);
+    y[(((int64_t)n * OH + oh) * OW + ow) * C + c] = acc / (float)(k * k);
+}
+
+__global__ void avgpool_bwd_k(const float* __restrict__ dy, float* dx, int N, int H, int W, int C, int OH, int OW,
+                              int k, int sh, int sw, int acc_flag) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)W * C) return;
+    const int c = (int)(t % (unsigned)C);
+    const int w = (int)(t / (unsigned)C);
+    const int h = blockIdx.y;
+    const int n = blockIdx.z;
+    int oh_lo = h - k + 1;
+    oh_lo = oh_lo <= 0 ? 0 : (oh_lo + sh - 1) / sh;
+    int oh_hi = h / sh;
+    if (oh_hi > OH - 1) oh_hi = OH - 1;
+    int ow_lo = w - k + 1;
+    ow_lo = ow_lo <= 0 ? 0 : (ow_lo + sw - 1) / sw;
+    int ow_hi = w / sw;
+    if (ow_hi > OW - 1) ow_hi = OW - 1;
+    float acc = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) acc += __ldg(dy + (((int64_t)n * OH + oh) * OW + ow) * C + c);
+    acc /= (float)(k * k);
+    float* p = dx + (((int64_t)n * H + h) * W + w) * C + c;
+    *p = acc_flag ? *p + acc : acc;
+}
+
+}  // namespace
+
+extern "C" {
+
+// x [N,H,W,C] -> y [N,OH,OW,C], argmax u8 [N,OH,OW,C] (nullable). OH = (H + 2*pad - k)/sh + 1.
+int xsb_maxpool2d_fwd(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int k, int sh, int sw,
+                      int pad, void* stream) {
+    XSB_CHECK_ARG(k >= 1 && k <= 15 && sh >= 1 && sw >= 1 && pad >= 0, "maxpool: bad k/stride/pad %d %d %d %d", k, sh,
+                  sw, pad);
+    const int OH = (H + 2 * pad - k) / sh + 1, OW = (W + 2 * pad - k) / sw + 1;
+    XSB_CHECK_ARG(OH > 0 && OW > 0, "maxpool: empty output");
+    cudaStream_t s = xsb_stream(stream);
+    const bool v4 = (C % 4 == 0) && aligned16(x) && aligned16(y) && (!argmax || ((uintptr_t)argmax & 3u) == 0);
+    XSB_CHECK_ARG(N <= 65535 && OH <= 65535, "maxpool: N/OH exceed grid limits");
+    if (v4) {
+        dim3 grid((unsigned)ceil_div64((int64_t)OW * (C / 4), 256), OH, N);
+        maxpool_fwd_k<4><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
+    } else {
+        dim3 grid((unsigned)ceil_div64((int64_t)OW * C, 256), OH, N);
+        maxpool_fwd_k<1><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
+    }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_maxpool2d_bwd(const float* dy, const uint8_t* argmax, float* dx, int N, int H, int W, int C, int k, int sh,
+                      int sw, int pad, int accumulate, void* stream) {
+    const int OH = (H + 2 * pad - k) / sh + 1, OW = (W + 2 * pad - k) / sw + 1;
+    XSB_CHECK_ARG(OH > 0 && OW > 0, "maxpool: empty output");
+    cudaStream_t s = xsb_stream(stream);
+    const bool v4 = (C % 4 == 0) && aligned16(dy) && aligned16(dx) && (((uintptr_t)argmax & 3u) == 0);
+    XSB_CHECK_ARG(N <= 65535 && H <= 65535, "maxpool: N/H exceed grid limits");
+    if (v4) {
+        dim3 g((unsigned)ceil_div64((int64_t)W * (C / 4), 256), H, N);
+        if (accumulate)
+            maxpool_bwd_k<4, true><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, sh, sw, pad);
+        else
+            maxpool_bwd_k<4, false><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, sh, sw, pad);
+    } else {
+        dim3 g((unsigned)ceil_div64((int64_t)W * C, 256), H, N);
+        if (accumulate)
+            maxpool_bwd_k<1, true><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, sh, sw, pad);
+        else
+            maxpool_bwd_k<1, false><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, sh, sw, pad);
+    }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_avgpool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int sh, int sw, void* stream) {
+    const int OH = (H - k) / sh + 1, OW = (W - k) / sw + 1;
+    XSB_CHECK_ARG(OH > 0 && OW > 0, "avgpool: empty output");
+    XSB_CHECK_ARG(N <= 65535 && OH <= 65535, "avgpool: N/OH exceed grid limits");
+    dim3 grid((unsigned)ceil_div64((int64_t)OW * C, 256), OH, N);
+    avgpool_fwd_k<<<grid, 256, 0, xsb_stream(stream)>>>(x, y, N, H, W, C, OH, OW, k, sh, sw);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_avgpool2d_bwd(const float* dy, float* dx, int N, int H, int W, int C, int k, int sh, int sw, int accumulate,
+                      void* stream) {
+    const int OH = (H - k) / sh + 1, OW = (W - k) / sw + 1;
+    XSB_CHECK_ARG(OH > 0 && OW > 0, "avgpool: empty output");
+    XSB_CHECK_ARG(N <= 65535 && H <= 65535, "avgpool: N/H exceed grid limits");
+    dim3 grid((unsigned)ceil_div64((int64_t)W * C, 256), H, N);
+    avgpool_bwd_k<<<grid, 256, 0, xsb_stream(stream)>>>(dy, dx, N, H, W, C, OH, OW, k, sh, sw, accumulate);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+"""Functional ops (mirror of the hot-path subset of xs/nn/functional.py).
+
+Same signatures, defaults and side effects as the reference: each op (i) computes -- here by one or
+two libxsb200 kernel launches on the current CUDA stream, (ii) wires the dynamic graph
+(`add_in_bounds` / `add_out_bounds`) when `out.is_dynamic`, (iii) stashes what its backward needs in
+`out.cache`, (iv) sets `out.grad_fn` and gives grad-requiring operands a zeroed grad
+(`initialize_ops_grad`). `out=` is honoured (the static-graph front end passes preallocated buffers).
+Ops outside the hot path named in SURVEY.md section 8a are not provided.
+"""
+import numpy as np
+
+from ..core import state as GLOBAL
+from ..core.device import DevArray, rt
+from ..core.tensor import Parameter, Tensor
+from ..utils.common import initialize_ops_grad, pair
+from .._lib import lib
+from .grad_fn import (AddBackward, AddmmBackward, Avgpool2DBackward, BatchNormBackward, Conv2DBackward,
+                      CrossEntropyLossBackward, FlattenBackward, Maxpool2DBackward, MeanBackward, MMBackward,
+                      MSELossBackward, ReLUBackward, SumBackward, ViewBackward)
+
+
+def _mark_inputs(t):
+    if GLOBAL.INPUTS is None:
+        GLOBAL.INPUTS = t
+
+
+def _out_arr(out, shape, dtype="float32"):
+    """Resolve the destination DevArray: a fresh one, or the (active prefix of the) preallocated `out`."""
+    if out is None or out._arr is None:
+        arr = DevArray.empty(shape, dtype)
+        if out is None:
+            return Tensor(arr), arr
+        out._arr = arr
+        return out, arr
+    arr = out.arr
+    if tuple(arr.shape) != tuple(shape):
+        raise ValueError(f"out has shape {arr.shape}, op produces {tuple(shape)}")
+    return out, arr
+
+
+def _wire(out, operands, requires_grad, grad_fn, cache=None, grad_ops=None):
+    out.requires_grad = bool(requires_grad)
+    if out.is_dynamic:
+        out.add_in_bounds(*operands)
+        for o in operands:
+            if o is not None:
+                o.add_out_bounds(out)
+    else:
+        # static (preallocated) output: its closure must see THIS step's operands -- the backward
+        # kernels read the live input tensor where the reference reads a cached copy (col / xhat)
+        out._in_bounds = list(operands)
+    if GLOBAL.COMPUTE_GRAD and out.requires_grad:
+        if cache:
+            out.cache.update(cache)
+        out.grad_fn = grad_fn
+        ops = operands if grad_ops is None else grad_ops
+        initialize_ops_grad(*ops)
+        for o in ops:
+            if isinstance(o, Parameter) and o.requires_grad:
+                o.pending_uses += 1
+    return out
+
+
+class DeviceArgmax:
+    """`cache['pool_argmax']`: the max-pool arg-max kept on the device as one byte per output
+    (k*k <= 255). np.asarray(...) yields the reference's representation -- int64, flat, (n,oh,ow,c)
+    order (xs/nn/functional.py:475)."""
+
+    def __init__(self, dev, count):
+        self.dev, self.count = dev, count
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.dev[: self.count].cpu().numpy().astype(np.int64)
+        return a if dtype is None else a.astype(dtype)
+
+    @property
+    def size(self):
+        return self.count
+
+
+# ---------------------------------------------------------------------------------------------- math
+def add(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:6-21 (same-shape operands: the residual add)."""
+    _mark_inputs(lhs)
+    a, b = lhs.arr, rhs.arr
+    if tuple(a.shape) != tuple(b.shape):
+        raise NotImplementedError(f"add: broadcasting {a.shape} + {b.shape} is outside the hot path")
+    if a.cl != b.cl:
+        b = b.as_cl() if a.cl else b.logical_rowmajor()
+    out, y = _out_arr(out, a.shape)
+    y.cl = a.cl
+    lib.xsb_add(a.ptr, b.ptr, y.wptr, y.size, rt.stream())
+    rt.launches += 1
+    return _wire(out, (lhs, rhs), lhs.requires_grad or rhs.requires_grad, AddBackward)
+
+
+def _gemm_fwd(x, w, bias, y):
+    m, k = x.shape
+    n = w.shape[-1]
+    lib.xsb_gemm(x.ptr, w.ptr, y.wptr, bias.ptr if bias is not None else None, m, n, k, 0, 0, 0, rt.math_mode,
+                 rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream())
+    rt.launches += 1
+
+
+def _as_matrix(t):
+    a = t.arr
+    if a.ndim != 2:
+        raise NotImplementedError(f"matrix operand must be 2-D, got {a.shape}")
+    return a
+
+
+def mm(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:81-96: out = lhs . rhs."""
+    _mark_inputs(lhs)
+    x, w = _as_matrix(lhs), _as_matrix(rhs)
+    out, y = _out_arr(out, (x.shape[0], w.shape[-1]))
+    _gemm_fwd(x, w, None, y)
+    return _wire(out, (lhs, rhs), lhs.requires_grad or rhs.requires_grad, MMBackward)
+
+
+def addmm(b: Tensor, x1: Tensor, x2: Tensor, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:99-120: out = x1 . x2 + b (Dense; x2 is [in, out], b is [1, out])."""
+    _mark_inputs(x1)
+    x, w = _as_matrix(x1), _as_matrix(x2)
+    if b.arr.size != w.shape[-1]:
+        raise ValueError("bias size mismatch")
+    out, y = _out_arr(out, (x.shape[0], w.shape[-1]))
+    _gemm_fwd(x, w, b.arr, y)
+    return _wire(out, (x1, x2, b), x1.requires_grad or x2.requires_grad or b.requires_grad, AddmmBackward,
+                 grad_ops=(b, x1, x2))
+
+
+def _reduce(x, axis, keepdims, op):
+    _mark_inputs(x)
+    a = x.arr.logical_rowmajor()
+    shape = a.shape
+    if axis is None:
+        outer, red, inner = 1, a.size, 1
+        oshape = (1,) * len(shape) if keepdims else (1,)
+    else:
+        axis = axis % len(shape)
+        outer = int(np.prod(shape[:axis], dtype=np.int64))
+        red = shape[axis]
+        inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+        oshape = shape[:axis] + ((1,) if keepdims else ()) + shape[axis + 1:]
+        if not oshape:
+            oshape = (1,)
+    y = DevArray.empty(oshape)
+    y.cl = False
+    lib.xsb_reduce_axis(a.ptr, y.wptr, outer, red, inner, 1.0 / red if op == "mean" else 1.0, rt.stream())
+    rt.launches += 1
+    out = Tensor(y)
+    return _wire(out, (x,), x.requires_grad, MeanBackward if op == "mean" else SumBackward,
+                 cache={"axis": axis, "ori": (outer, red, inner), "op": op})
+
+
+def mean(x: Tensor, axis: int = None, keepdims: bool = False, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:244-260."""
+    return _reduce(x, axis, keepdims, "mean")
+
+
+def sum(x: Tensor, axis: int = None, keepdims: bool = False, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:224-241."""
+    return _reduce(x, axis, keepdims, "sum")
+
+
+# ---------------------------------------------------------------------------------------------- activations
+def relu(inputs: Tensor, inplace: bool = False, out: Tensor = None, _mask=None) -> Tensor:
+    """xs/nn/functional.py:297-313. `_mask` (private): device byte buffer that receives the x<0 bit
+    mask in the same pass -- used by layers.ReLU(inplace=True)."""
+    _mark_inputs(inputs)
+    x = inputs.arr
+    mptr = _mask.data_ptr() if _mask is not None else None
+    if inplace:
+        lib.xsb_relu_fwd(x.ptr, x.peek_ptr(), mptr, x.size, rt.stream())
+        rt.launches += 1
+        return inputs
+    out, y = _out_arr(out, x.shape)
+    y.cl = x.cl
+    lib.xsb_relu_fwd(x.ptr, y.wptr, mptr, x.size, rt.stream())
+    rt.launches += 1
+    return _wire(out, (inputs,), inputs.requires_grad, ReLUBackward)
+
+
+def softmax(inputs: Tensor, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:348-357 (host-side helper; the training path uses the fused cross_entropy)."""
+    z = inputs.eval.astype(np.float64)
+    e = np.exp(z - z.max(axis=-1, keepdims=True))
+    res = Tensor((e / e.sum(axis=-1, keepdims=True)).astype(np.float32))
+    res.requires_grad = inputs.requires_grad
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- shape
+def flatten(inputs: Tensor, start: int = 1, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:370-384. The result is in the reference's NCHW feature order: the
+    channels-last activation is transposed back once here (zero-copy when H*W == 1)."""
+    _mark_inputs(inputs)
+    a = inputs.arr.logical_rowmajor()
+    shape = tuple(a.shape[:start]) + (int(np.prod(a.shape[start:], dtype=np.int64)),)
+    flat = a.reshaped(shape)
+    if out is None:
+        out = Tensor(flat)
+    else:
+        dst = out.arr
+        if dst is None:
+            out._arr = flat
+        else:
+            dst.buf[: flat.size].copy_(flat.buf[: flat.size])
+            dst.pending_zero = False
+    return _wire(out, (inputs,), inputs.requires_grad, FlattenBackward)
+
+
+def view(inputs: Tensor, shape, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:814-828."""
+    _mark_inputs(inputs)
+    a = inputs.arr.logical_rowmajor()
+    shape = tuple(int(s) for s in shape)
+    if -1 in shape:
+        known = -int(np.prod(shape, dtype=np.int64))
+        shape = tuple(a.size // known if s == -1 else s for s in shape)
+    v = a.reshaped(shape)
+    if out is None:
+        out = Tensor(v)
+    else:
+        dst = out.arr
+        if dst is None:
+            out._arr = v
+        else:
+            dst.buf[: v.size].copy_(v.as_cl().buf[: v.size] if dst.cl else v.buf[: v.size])
+            dst.pending_zero = False
+    return _wire(out, (inputs,), inputs.requires_grad, ViewBackward)
+
+
+# ---------------------------------------------------------------------------------------------- conv / pool
+def conv2d(inputs: Tensor, weight: Tensor, bias: Tensor = None, stride=(1, 1), padding: int = 0,
+           out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:405-442. Implicit GEMM over channels-last data (xsb_conv2d_fwd);
+    OH = (H - kh + 2p)//s + 1. Bias is fused into the kernel epilogue."""
+    _mark_inputs(inputs)
+    x = inputs.arr.as_cl()
+    w = weight.arr.as_cl()
+    n, c, h, wd = x.shape
+    oc, wc, kh, kw = w.shape
+    if wc != c:
+        raise ValueError(f"conv2d: input has {c} channels, weight expects {wc}")
+    sh, sw = pair(stride)
+    oh = (h - kh + 2 * padding) // sh + 1
+    ow = (wd - kw + 2 * padding) // sw + 1
+    out, y = _out_arr(out, (n, oc, oh, ow))
+    y.cl = True
+    lib.xsb_conv2d_fwd(x.ptr, w.ptr, bias.arr.ptr if bias is not None else None, y.wptr, n, h, wd, c, oc, kh, kw,
+                       sh, sw, padding, rt.math_mode, rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream())
+    rt.launches += 1
+    rg = inputs.requires_grad or weight.requires_grad or bool(bias is not None and bias.requires_grad)
+    return _wire(out, (inputs, weight, bias), rg, Conv2DBackward, cache={"stride": (sh, sw), "padding": padding})
+
+
+def max_pool2d(inputs: Tensor, kernel_size: int = 2, stride=None, padding: int = 0, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:445-491. Always the reference's im2col/argmax semantics (Q1): zero padding,
+    first max wins, `cache['pool_argmax']` in (n,oh,ow,c) order."""
+    _mark_inputs(inputs)
+    if stride is None:
+        stride = (kernel_size, kernel_size)
+    sh, sw = pair(stride)
+    k = int(kernel_size)
+    x = inputs.arr.as_cl()
+    n, c, h, w = x.shape
+    oh = (h + 2 * padding - k) // sh + 1
+    ow = (w + 2 * padding - k) // sw + 1
+    out, y = _out_arr(out, (n, c, oh, ow))
+    y.cl = True
+    need_grad = GLOBAL.COMPUTE_GRAD and inputs.requires_grad
+    amax = rt.empty(max(y.size, 1), "uint8") if need_grad else None
+    lib.xsb_maxpool2d_fwd(x.ptr, y.wptr, amax.data_ptr() if amax is not None else None, n, h, w, c, k, sh, sw,
+                          padding, rt.stream())
+    rt.launches += 1
+    cache = {"mode": "im2col", "stride": (sh, sw), "padding": padding, "kernel_size": k}
+    if need_grad:
+        cache["pool_argmax"] = DeviceArgmax(amax, y.size)
+    return _wire(out, (inputs,), inputs.requires_grad, Maxpool2DBackward, cache=cache)
+
+
+def avg_pool2d(inputs: Tensor, kernel_size: int, stride=None, padding: int = 0, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:539-583 (padding must be 0: the reference's padded branch double-counts it)."""
+    _mark_inputs(inputs)
+    if padding != 0:
+        raise NotImplementedError("avg_pool2d with padding != 0 is broken in the reference (functional.py:551-553)")
+    if stride is None:
+        stride = (kernel_size, kernel_size)
+    sh, sw = pair(stride)
+    k = int(kernel_size)
+    x = inputs.arr.as_cl()
+    n, c, h, w = x.shape
+    oh = (h - k) // sh + 1
+    ow = (w - k) // sw + 1
+    if oh <= 0 or ow <= 0:
+        raise ValueError(f"avg_pool2d: {h}x{w} input is smaller than the {k}x{k} window")
+    out, y = _out_arr(out, (n, c, oh, ow))
+    y.cl = True
+    lib.xsb_avgpool2d_fwd(x.ptr, y.wptr, n, h, w, c, k, sh, sw, rt.stream())
+    rt.launches += 1
+    return _wire(out, (inputs,), inputs.requires_grad, Avgpool2DBackward,
+                 cache={"mode": "im2col", "stride": (sh, sw), "padding": 0, "kernel_size": k})
+
+
+# ---------------------------------------------------------------------------------------------- normalisation
+def batch_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, moving_mean: Tensor, moving_variance: Tensor,
+               axis: int = 1, training: bool = True, epsilon: float = 1e-5, momentum: float = 0.9,
+               out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:676-740, training branch (the only one the reference ever reaches, Q5)."""
+    _mark_inputs(inputs)
+    x = inputs.arr
+    if x.ndim == 4 and axis == 1:
+        x = x.as_cl()
+    elif x.ndim == 2 and axis in (1, -1):
+        pass
+    else:
+        raise NotImplementedError(f"batch_norm over axis {axis} of a {x.ndim}-D tensor is outside the hot path")
+    if not training:
+        raise NotImplementedError("batch_norm eval branch: SURVEY.md 8f rank 4 (next)")
+    C = x.shape[1]
+    R = x.size // C
+    out, y = _out_arr(out, x.shape)
+    y.cl = x.cl
+    save_mean, save_invstd = DevArray.empty((C,)), DevArray.empty((C,))
+    lib.xsb_bn_train_fwd(x.ptr, gamma.arr.ptr, beta.arr.ptr, moving_mean.arr.ptr, moving_variance.arr.ptr, y.wptr,
+                         save_mean.wptr, save_invstd.wptr, R, C, float(epsilon), float(momentum),
+                         rt.ws_small.data_ptr(), rt.stream())
+    rt.launches += 2
+    rg = inputs.requires_grad or gamma.requires_grad or beta.requires_grad
+    axis_field = tuple(i for i in range(x.ndim) if i != (axis % x.ndim))
+    return _wire(out, (inputs, gamma, beta), rg, BatchNormBackward,
+                 cache={"axis_field": axis_field, "save_mean": save_mean, "save_invstd": save_invstd})
+
+
+# ---------------------------------------------------------------------------------------------- losses
+def _loss_out(out, reduction):
+    if reduction not in ("mean", "sum"):
+        raise TypeError("unknown type for reduction" if reduction != "none" else "reduction='none' is outside the hot path")
+    return _out_arr(out, (1,))
+
+
+def mse_loss(x1: Tensor, x2: Tensor, reduction: str = "mean", out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:843-873: 'mean' = sum((a-b)^2) / 2 / numel (Q9)."""
+    assert x1.shape == x2.shape
+    _mark_inputs(x1)
+    a = x1.arr
+    b = x2.arr
+    if a.cl != b.cl:
+        b = b.as_cl() if a.cl else b.logical_rowmajor()
+    out, y = _loss_out(out, reduction)
+    lib.xsb_mse_fwd(a.ptr, b.ptr, y.wptr, a.size, 0 if reduction == "mean" else 1, rt.stream())
+    rt.launches += 1
+    return _wire(out, (x1, x2), x1.requires_grad or x2.requires_grad, MSELossBackward,
+                 cache={"reduction": reduction})
+
+
+def cross_entropy(x1: Tensor, x2: Tensor, reduction: str = "mean", out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:984-1010: softmax -> log -> NLL, fused in one kernel; the softmax is kept
+    in `x1.cache['softmax']` for the backward; the loss is marked leaf so `.item()` survives backward (Q14)."""
+    _mark_inputs(x1)
+    out, y = _loss_out(out, reduction)
+    x2.long_()
+    z = x1.arr.logical_rowmajor()
+    c = z.shape[-1]
+    rows = z.size // c
+    sm = x1.cache.get("softmax")
+    if sm is None or sm._arr is None or tuple(sm.arr.shape) != tuple(z.shape):
+        sm = Tensor(DevArray.empty(z.shape))
+        sm._arr.cl = False
+    x1.cache["softmax"] = sm
+    lib.xsb_softmax_xent_fwd(z.ptr, x2.arr.ptr, sm.arr.wptr, y.wptr, rows, c, 0 if reduction == "mean" else 1,
+                             rt.stream())
+    rt.launches += 1
+    if rows != z.shape[0] and reduction == "mean":
+        raise NotImplementedError("cross_entropy 'mean' over >2-D logits")
+    out.requires_grad = x1.requires_grad or x2.requires_grad
+    if out.is_dynamic:
+        out.add_in_bounds(x1, x2)
+        x1.add_out_bounds(out)
+        x2.add_out_bounds(out)
+        out.is_leaf = True
+    else:
+        out._in_bounds = [x1, x2]   # static loss buffer: this step's logits and labels
+    if GLOBAL.COMPUTE_GRAD and out.requires_grad:
+        out.cache["reduction"] = reduction
+        out.grad_fn = CrossEntropyLossBackward
+        initialize_ops_grad(x1, x2)
+    return out

@@ -1,0 +1,273 @@
+"""Backward closures `XxxBackward(outputs) -> None` (mirror of xs/nn/grad_fn.py).
+
+Contract kept from the reference: a closure reads `outputs.grad`, `outputs.in_bounds` and
+`outputs.cache`, and ACCUMULATES into `in_bound.grad` for every operand that requires grad.
+Each one is a thin launcher of libxsb200 kernels; "accumulate" is passed to the kernel as a flag
+(0 the first time a freshly zeroed gradient is written, 1 afterwards), so no zero-fill and no
+separate `+=` pass is ever run.
+"""
+from ..core.device import DevArray, rt
+from ..core.tensor import Parameter, Tensor
+from .._lib import lib
+
+
+def _done(t):
+    """Bookkeeping for the data-parallel engine: one pending use of a Parameter has produced its gradient."""
+    if isinstance(t, Parameter) and t.pending_uses > 0:
+        t.pending_uses -= 1
+
+
+def _grad_arr(t):
+    if t.grad is None:
+        t.zero_grad()
+    return t.grad.arr
+
+
+def _same_layout(src, like):
+    """src DevArray re-laid to match `like`'s physical order (both have equal logical shapes)."""
+    if src.cl == like.cl:
+        return src
+    return src.as_cl() if like.cl else src.logical_rowmajor()
+
+
+def accumulate_into(t, src):
+    """t.grad += src (src: DevArray of t's logical shape)."""
+    g = _grad_arr(t)
+    src = _same_layout(src, g)
+    if g.take_acc():
+        lib.xsb_axpy(g.peek_ptr(), src.ptr, 1.0, g.size, rt.stream())
+        rt.launches += 1
+    elif src.pending_zero:
+        g.buf[: g.size].zero_()
+    else:
+        g.buf[: g.size].copy_(src.buf[: g.size])   # first write: a plain device-to-device copy
+
+
+def accumulate_rowmajor_into(t, src_rm):
+    """t.grad += src where src is in LOGICAL row-major order and t may be channels-last."""
+    g = _grad_arr(t)
+    if g.cl:
+        n, c, h, w = g.shape
+        if c > 1 and h * w > 1:
+            lib.xsb_nchw_to_nhwc(src_rm.ptr, g.peek_ptr(), n, c, h, w, g.take_acc(), rt.stream())
+            rt.launches += 1
+            return
+    accumulate_into(t, DevArray(src_rm.buf, g.shape, g.dtype, cl=g.cl, _share=src_rm))
+
+
+# ------------------------------------------------------------------ elementwise
+def AddBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:6-16 (same-shape operands)."""
+    dy = outputs.grad.arr
+    for in_bound in outputs.in_bounds:
+        if in_bound.requires_grad:
+            accumulate_into(in_bound, dy)
+
+
+def ReLUBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:146-157. In-place form: mask outputs.grad in place with the bit mask
+    recorded by the forward, pop the producer's closure and run it; otherwise dX += dY*[x>=0]."""
+    if outputs.cache.get("inplace"):
+        mask = outputs.cache["mask"]
+        g = outputs.grad.arr
+        lib.xsb_relu_bwd_mask(g.ptr, mask.data_ptr(), g.peek_ptr(), g.size, 0, rt.stream())
+        rt.launches += 1
+        outputs.grad_fn = outputs.cache["grad_fn"].pop()
+        if outputs.grad_fn is not None:
+            outputs.grad_fn(outputs)
+    else:
+        inputs, = outputs.in_bounds
+        if inputs.requires_grad:
+            dy = outputs.grad.arr
+            g = _grad_arr(inputs)
+            x = _same_layout(inputs.arr, g)
+            dy = _same_layout(dy, g)
+            lib.xsb_relu_bwd(dy.ptr, x.ptr, g.peek_ptr(), g.size, g.take_acc(), rt.stream())
+            rt.launches += 1
+
+
+# ------------------------------------------------------------------ shape ops
+def FlattenBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:173-176: dX += reshape(dY) (dY is in NCHW feature order)."""
+    inputs, = outputs.in_bounds
+    if inputs.requires_grad:
+        accumulate_rowmajor_into(inputs, outputs.grad.arr.logical_rowmajor())
+
+
+ViewBackward = FlattenBackward  # xs/nn/grad_fn.py:497-500
+
+
+def MeanBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:128-137: dX += broadcast(dY) / (#reduced)."""
+    inputs, = outputs.in_bounds
+    if inputs.requires_grad:
+        outer, red, inner = outputs.cache["ori"]
+        scale = 1.0 / red if outputs.cache["op"] == "mean" else 1.0
+        tmp = DevArray.empty(inputs.shape)
+        tmp.cl = False
+        lib.xsb_broadcast_axis(outputs.grad.arr.logical_rowmajor().ptr, tmp.wptr, outer, red, inner, scale, 0,
+                               rt.stream())
+        rt.launches += 1
+        accumulate_rowmajor_into(inputs, tmp)
+
+
+SumBackward = MeanBackward
+
+
+# ------------------------------------------------------------------ Dense
+def _gemm(a, b, c_arr, bias, M, N, K, ta, tb, acc):
+    lib.xsb_gemm(a, b, c_arr, bias, M, N, K, ta, tb, acc, rt.math_mode, rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS,
+                 rt.stream())
+    rt.launches += 1
+
+
+def MMBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:73-83: dX += dY.W^T ; dW += X^T.dY."""
+    x, w = outputs.in_bounds
+    dy = outputs.grad.arr
+    m, n = dy.shape
+    k = x.shape[-1]
+    if x.requires_grad:
+        g = _grad_arr(x)
+        _gemm(dy.ptr, w.arr.ptr, g.peek_ptr(), None, m, k, n, 0, 1, g.take_acc())
+    if w.requires_grad:
+        g = _grad_arr(w)
+        _gemm(x.arr.ptr, dy.ptr, g.peek_ptr(), None, k, n, m, 1, 0, g.take_acc())
+        _done(w)
+
+
+def AddmmBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:86-99: db += sum_rows(dY) (dY itself when N == 1, Q12), then MMBackward."""
+    x1, x2, b = outputs.in_bounds
+    dy = outputs.grad.arr
+    m, n = dy.shape
+    if b.requires_grad:
+        g = _grad_arr(b)
+        lib.xsb_colsum(dy.ptr, g.peek_ptr(), m, n, g.take_acc(), rt.ws_small.data_ptr(), rt.stream())
+        rt.launches += 1
+        _done(b)
+    k = x1.shape[-1]
+    if x1.requires_grad:
+        g = _grad_arr(x1)
+        _gemm(dy.ptr, x2.arr.ptr, g.peek_ptr(), None, m, k, n, 0, 1, g.take_acc())
+    if x2.requires_grad:
+        g = _grad_arr(x2)
+        _gemm(x1.arr.ptr, dy.ptr, g.peek_ptr(), None, k, n, m, 1, 0, g.take_acc())
+        _done(x2)
+
+
+# ------------------------------------------------------------------ conv / pool / bn
+def Conv2DBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:186-203: dW += dY^T.col ; db += sum dY ; dX += col2im(dY.W) -- as three implicit
+    GEMM / reduction kernels over the channels-last tensors (no col buffer, no col2im scatter). The
+    reference's unconditional dcol GEMM (line 199) is skipped when the input needs no gradient."""
+    inputs, weight, bias = outputs.in_bounds
+    x = inputs.arr.as_cl()
+    dy = outputs.grad.arr.as_cl()
+    n, c, h, w = x.shape
+    oc, _, kh, kw = weight.shape
+    (sh, sw), pad = outputs.cache["stride"], outputs.cache["padding"]
+    ws, wsn, st = rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream()
+    if weight.requires_grad:
+        g = _grad_arr(weight)
+        lib.xsb_conv2d_wgrad(dy.ptr, x.ptr, g.peek_ptr(), n, h, w, c, oc, kh, kw, sh, sw, pad, g.take_acc(),
+                             rt.math_mode, ws, wsn, st)
+        rt.launches += 1
+        _done(weight)
+    if bias is not None and bias.requires_grad:
+        g = _grad_arr(bias)
+        lib.xsb_colsum(dy.ptr, g.peek_ptr(), dy.size // oc, oc, g.take_acc(), rt.ws_small.data_ptr(), st)
+        rt.launches += 1
+        _done(bias)
+    if inputs.requires_grad:
+        g = _grad_arr(inputs)
+        assert g.cl, "conv input gradient must be channels-last"
+        lib.xsb_conv2d_dgrad(dy.ptr, weight.arr.ptr, g.peek_ptr(), n, h, w, c, oc, kh, kw, sh, sw, pad, g.take_acc(),
+                             rt.math_mode, ws, wsn, st)
+        rt.launches += 1
+
+
+def Maxpool2DBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:206-235 (im2col branch; the 'reshape' branch is dead code, Q1)."""
+    inputs, = outputs.in_bounds
+    if inputs.requires_grad:
+        k = outputs.cache["kernel_size"]
+        sh, sw = outputs.cache["stride"]
+        pad = outputs.cache["padding"]
+        amax = outputs.cache["pool_argmax"].dev
+        n, c, h, w = inputs.shape
+        g = _grad_arr(inputs)
+        dy = outputs.grad.arr.as_cl()
+        lib.xsb_maxpool2d_bwd(dy.ptr, amax.data_ptr(), g.peek_ptr(), n, h, w, c, k, sh, sw, pad, g.take_acc(),
+                              rt.stream())
+        rt.launches += 1
+
+
+def Avgpool2DBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:284-309: dX += col2im(repeat(dY)/k^2)."""
+    inputs, = outputs.in_bounds
+    if inputs.requires_grad:
+        k = outputs.cache["kernel_size"]
+        sh, sw = outputs.cache["stride"]
+        n, c, h, w = inputs.shape
+        g = _grad_arr(inputs)
+        dy = outputs.grad.arr.as_cl()
+        lib.xsb_avgpool2d_bwd(dy.ptr, g.peek_ptr(), n, h, w, c, k, sh, sw, g.take_acc(), rt.stream())
+        rt.launches += 1
+
+
+def BatchNormBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:379-411. xhat is recomputed from the retained input and the saved
+    mean / invstd (the reference caches xhat and sqrtvar and destroys them here)."""
+    inputs, gamma, beta = outputs.in_bounds
+    dy = outputs.grad.arr
+    x = inputs.arr
+    if x.ndim == 4:
+        x, dy = x.as_cl(), dy.as_cl()
+    C = gamma.arr.size
+    R = x.size // C
+    gx = _grad_arr(inputs) if inputs.requires_grad else None
+    gg = _grad_arr(gamma) if gamma.requires_grad else None
+    gb = _grad_arr(beta) if beta.requires_grad else None
+    lib.xsb_bn_bwd(dy.ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
+                   gx.peek_ptr() if gx is not None else None, gg.peek_ptr() if gg is not None else None,
+                   gb.peek_ptr() if gb is not None else None, R, C,
+                   gx.take_acc() if gx is not None else 0, gg.take_acc() if gg is not None else 0,
+                   gb.take_acc() if gb is not None else 0, rt.ws_small.data_ptr(), rt.stream())
+    rt.launches += 2 if gx is not None else 1
+    _done(gamma)
+    _done(beta)
+
+
+# ------------------------------------------------------------------ losses
+def CrossEntropyLossBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:604-620: d logits += (softmax - onehot)/N * dLoss."""
+    logits, labels = outputs.in_bounds
+    if logits.requires_grad:
+        probs = logits.cache["softmax"].arr
+        n = logits.shape[0]
+        c = logits.shape[-1]
+        rows = probs.size // c
+        g = _grad_arr(logits)
+        red = 0 if outputs.cache["reduction"] == "mean" else 1
+        # 'mean' divides by shape[0] (grad_fn.py:614-616) even when logits have more leading axes
+        lib.xsb_softmax_xent_bwd(probs.ptr, labels.arr.ptr, outputs.grad.arr.ptr, g.peek_ptr(), rows, c, red,
+                                 g.take_acc(), rt.stream())
+        rt.launches += 1
+        if rows != n and red == 0:
+            raise NotImplementedError("cross_entropy 'mean' over >2-D logits")
+
+
+def MSELossBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:503-520: d pred += (pred-true)*dLoss (/numel for 'mean'); d true -= the same."""
+    y_pred, y_true = outputs.in_bounds
+    a, b = y_pred.arr, _same_layout(y_true.arr, y_pred.arr)
+    ga = _grad_arr(y_pred) if y_pred.requires_grad else None
+    gb = _grad_arr(y_true) if y_true.requires_grad else None
+    if ga is None and gb is None:
+        return
+    red = 0 if outputs.cache["reduction"] == "mean" else 1
+    lib.xsb_mse_bwd(a.ptr, b.ptr, outputs.grad.arr.ptr, ga.peek_ptr() if ga is not None else None,
+                    gb.peek_ptr() if gb is not None else None, a.size, red,
+                    ga.take_acc() if ga is not None else 0, gb.take_acc() if gb is not None else 0, rt.stream())
+    rt.launches += 1

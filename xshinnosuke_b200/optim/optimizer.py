@@ -1,0 +1,140 @@
+"""SGD / Adam as ONE fused kernel launch over a flat parameter buffer (mirror of xs/optim/optimizer.py:5-20,
+sgd.py:4-9, adam.py:4-30).
+
+On the first `zero_grad()` / `step()` the optimizer flattens its parameters (creation order, each
+tensor padded to a 64-float boundary) into one device buffer, rebinds every Parameter's storage to a
+view of it, and lays the gradients out in a parallel flat buffer. `zero_grad()` then costs nothing
+(gradients are flagged logically zero, see DevArray.pending_zero) and `step()` is a single
+128-bit-vectorised kernel (xsb_sgd_step / xsb_adam_step). The parameter collection may be a live set
+that is still empty at construction (tests/resnet/resnet18_dg.py:88 builds the optimizer before the
+first forward); it is re-flattened whenever it grows. `weight_decay` is accepted and ignored, like
+the reference (Q8). The data-parallel engine (parallel.py) all-reduces buckets of the flat gradient
+buffer and passes grad_scale = 1/world.
+"""
+from ..core.device import DevArray, rt, torch
+from ..core.tensor import Tensor
+from .._lib import lib
+
+ALIGN = 64  # floats; keeps every tensor 256-byte aligned inside the flat buffers (TMA-friendly)
+
+
+class FlatState:
+    """Flat parameter / gradient (/ moment) buffers and the per-tensor views into them."""
+
+    def __init__(self, params, n_extra=0):
+        self.params = list(params)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.total = off
+        t = torch()
+        self.flat_p = t.zeros(max(off, 1), dtype=t.float32, device=rt.device)
+        self.flat_g = t.zeros(max(off, 1), dtype=t.float32, device=rt.device)
+        self.extra = [t.zeros(max(off, 1), dtype=t.float32, device=rt.device) for _ in range(n_extra)]
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            old = p._arr
+            view = self.flat_p[o:o + n]
+            view.copy_(old.buf[:n]) if not old.pending_zero else view.zero_()
+            old.buf = view
+            old.pending_zero = False
+            gview = self.flat_g[o:o + n]
+            pending = True
+            if p._grad is not None and p._grad._arr is not None and not p._grad._arr.pending_zero:
+                gview.copy_(p._grad._arr.buf[:n])
+                pending = False
+            p._grad = Tensor(DevArray(gview, old.shape, "float32", cl=old.cl, pending_zero=pending))
+
+    def owns(self, params):
+        return len(params) == len(self.params) and all(a is b for a, b in zip(params, self.params))
+
+
+class Optimizer:
+    n_state = 0
+
+    def __init__(self, parameters=None, lr=0.01, weight_decay=0.0):
+        self._parameters = parameters if parameters is not None else []
+        self.lr = lr
+        self.weight_decay = weight_decay
+        self.iterations = 0
+        self.flat = None
+        self.grad_scale = 1.0        # set to 1/world by the data-parallel engine
+        self.before_step = None      # hook: wait for gradient all-reduces
+
+    def _ensure_flat(self):
+        rt.ensure()
+        params = [p for p in self._parameters if p is not None]
+        if self.flat is None or not self.flat.owns(params):
+            old = self.flat
+            self.flat = FlatState(params, self.n_state)
+            if old is not None:
+                self._migrate_state(old, self.flat)
+        return self.flat
+
+    def _migrate_state(self, old, new):
+        for k in range(self.n_state):
+            for p, o in zip(old.params, old.offsets):
+                if p in new.params:
+                    no = new.offsets[new.params.index(p)]
+                    new.extra[k][no:no + p.numel()].copy_(old.extra[k][o:o + p.numel()])
+
+    def zero_grad(self):
+        """xs/optim/optimizer.py:12-17 -- logical: each gradient view is flagged zero, no kernel runs."""
+        flat = self._ensure_flat()
+        for p in flat.params:
+            p._grad._arr.pending_zero = True
+
+    def _materialize_grads(self):
+        for p in self.flat.params:
+            if p._grad._arr.pending_zero:      # parameter received no gradient this step
+                p._grad._arr.buf.zero_()
+                p._grad._arr.pending_zero = False
+
+    def step(self):
+        self.iterations += 1
+
+
+class SGD(Optimizer):
+    """p -= lr * g (xs/optim/sgd.py:5-9)."""
+
+    def step(self):
+        flat = self._ensure_flat()
+        if self.before_step is not None:
+            self.before_step(self)
+        self._materialize_grads()
+        if flat.total:
+            lib.xsb_sgd_step(flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), flat.total, float(self.lr),
+                             float(self.grad_scale), rt.stream())
+            rt.launches += 1
+        super().step()
+
+
+class Adam(Optimizer):
+    """xs/optim/adam.py:4-30 (v = first moment, m = second moment, bias-corrected, eps outside the sqrt).
+    The step counter lives on the device so a CUDA-graph replay advances the bias correction."""
+    n_state = 2
+
+    def __init__(self, parameters=None, lr=0.001, weight_decay=0.0, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self._step_dev = None
+        super().__init__(parameters=parameters, lr=lr, weight_decay=weight_decay)
+
+    def step(self):
+        flat = self._ensure_flat()
+        if self._step_dev is None:
+            t = torch()
+            self._step_dev = t.zeros(1, dtype=t.int32, device=rt.device)
+        if self.before_step is not None:
+            self.before_step(self)
+        self._materialize_grads()
+        self.iterations += 1
+        st = rt.stream()
+        lib.xsb_counter_inc(self._step_dev.data_ptr(), st)
+        if flat.total:
+            lib.xsb_adam_step(flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), flat.extra[0].data_ptr(),
+                              flat.extra[1].data_ptr(), flat.total, float(self.lr), float(self.beta1),
+                              float(self.beta2), float(self.epsilon), float(self.grad_scale),
+                              self._step_dev.data_ptr(), st)
+        rt.launches += 2
