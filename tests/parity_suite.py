@@ -285,13 +285,20 @@ def resnet_steps(n, hw, steps=3, lr=0.1, optimizer="sgd"):
     return net, losses, logits0
 
 
-def check_resnet18(golden, tag, n, hw, tol_logits, tol_loss):
+def check_resnet18(golden, tag, n, hw, tol_logits, tol_loss, tail_rtol=None):
+    """Step 0 (logits, loss) is pinned tightly. Steps 1-2 follow an lr=0.1 trajectory (loss 6.6 -> 0.84 ->
+    0.02 at N=32) that is itself sensitive to 1-ulp fp32 perturbations: re-running the float64 ORACLE
+    with weights perturbed by 6e-8 relative noise gives 0.83825 / 0.018768 instead of 0.83641 / 0.020209
+    (measured), so at N=32 the tail is only held to `tail_rtol`."""
     c = golden.case(f"resnet18/{tag}")
     net, losses, logits0 = resnet_steps(n, hw)
     assert [sum(p.numel() for p in net.parameters()), len(net.parameters())] == c["nparams"].tolist()
     close(logits0, c["logits0"], tol_logits, f"resnet18/{tag}/logits0")
     np.testing.assert_allclose(losses[0], c["losses"][0], rtol=tol_loss)
-    np.testing.assert_allclose(losses, c["losses"], rtol=50 * tol_loss, atol=1e-3)
+    if tail_rtol is None:
+        np.testing.assert_allclose(losses, c["losses"], rtol=50 * tol_loss, atol=1e-3)
+    else:
+        np.testing.assert_allclose(losses, c["losses"], rtol=tail_rtol)
 
 
 def check_fit_configs(golden, tol):

@@ -101,9 +101,9 @@ class SGD(Optimizer):
 
     def step(self):
         flat = self._ensure_flat()
+        self._materialize_grads()
         if self.before_step is not None:
             self.before_step(self)
-        self._materialize_grads()
         if flat.total:
             lib.xsb_sgd_step(flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), flat.total, float(self.lr),
                              float(self.grad_scale), rt.stream())
@@ -126,9 +126,9 @@ class Adam(Optimizer):
         if self._step_dev is None:
             t = torch()
             self._step_dev = t.zeros(1, dtype=t.int32, device=rt.device)
+        self._materialize_grads()
         if self.before_step is not None:
             self.before_step(self)
-        self._materialize_grads()
         self.iterations += 1
         st = rt.stream()
         lib.xsb_counter_inc(self._step_dev.data_ptr(), st)

@@ -1,0 +1,151 @@
+"""Batch-sharded data parallelism for the xs training loop: one process per GPU, NCCL over NVLink.
+
+The reference has no distributed code at all; this is the B200-side addition the
+north_star asks for. Semantics: every rank is "the reference run on its own shard" (per-replica
+BatchNorm statistics, loss = mean over the local batch); parameter gradients are SUMMED across ranks
+and the fused optimizer kernel applies grad_scale = 1/world (so the update uses the average).
+
+Mechanics: parameter gradients already live in one flat fp32 buffer laid out in parameter-creation
+order (optim/optimizer.py). It is cut into buckets from the END (fc -> layer4 -> ... -> conv1: the order
+in which backward produces them). `core.autograd.backward` calls `after_node` after every closure;
+as soon as every parameter of the next bucket has received its gradient the bucket's all-reduce is
+issued on a dedicated communication stream, overlapping the remaining backward kernels. `step()`
+waits for the communication stream and runs the single fused update kernel.
+"""
+import os
+
+from .core import state as GLOBAL
+from .core.device import rt, torch
+
+
+def init_process_group(backend=None):
+    """Idempotent torch.distributed init from RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT."""
+    import torch.distributed as dist
+    if not dist.is_available():
+        raise RuntimeError("torch.distributed is not available")
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch().cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        kw = {}
+        if backend == "nccl":
+            rt.ensure()
+            kw["device_id"] = rt.device
+        dist.init_process_group(backend=backend, **kw)
+    return dist
+
+
+def plan_buckets(offsets, sizes, total, bucket_floats):
+    """Cut [0, total) into contiguous ranges, walking parameters from the last one backwards.
+    Returns a list of (start, stop, [param indices]) in launch order (last parameters first)."""
+    buckets, cur, stop = [], [], total
+    for i in range(len(offsets) - 1, -1, -1):
+        cur.append(i)
+        start = offsets[i]
+        if stop - start >= bucket_floats or i == 0:
+            buckets.append((start, stop, cur))
+            cur, stop = [], start
+    return buckets
+
+
+class DataParallel:
+    """Wrap a (model, optimizer) pair:
+
+        opt = xs.optim.SGD(net.parameters(), lr=0.1)
+        dp = DataParallel(net, opt)           # after torchrun / init_process_group
+        ... usual loop: opt.zero_grad(); loss = crit(net(x_shard), y_shard); loss.backward(); opt.step()
+    """
+
+    def __init__(self, model, optimizer, bucket_mb=8.0, overlap=True, broadcast_params=True):
+        self.dist = init_process_group()
+        self.world = self.dist.get_world_size()
+        self.rank = self.dist.get_rank()
+        self.model, self.opt = model, optimizer
+        self.bucket_floats = int(bucket_mb * (1 << 20) / 4)
+        self.overlap = overlap
+        self.broadcast_params = broadcast_params
+        self._flat = None
+        self._buckets = []
+        self._next = 0
+        self._comm = None
+        self.n_allreduce = 0
+        optimizer.grad_scale = 1.0 / self.world
+        optimizer.before_step = self._before_step
+        GLOBAL.AFTER_NODE_BACKWARD = self._after_node
+
+    # ---- plumbing
+    def _cuda(self):
+        return rt.device is not None and rt.device.type == "cuda"
+
+    def _comm_stream(self):
+        if self._comm is None and self._cuda():
+            self._comm = torch().cuda.Stream(device=rt.device)
+        return self._comm
+
+    def _sync_plan(self):
+        flat = self.opt.flat
+        if flat is self._flat:
+            return
+        first = self._flat is None
+        self._flat = flat
+        sizes = [p.numel() for p in flat.params]
+        self._buckets = plan_buckets(flat.offsets, sizes, flat.total, self.bucket_floats)
+        self._next = 0
+        if self.broadcast_params and flat.total:
+            # replicas start from rank 0's weights (identical seeds make this a no-op, but do not rely on it)
+            self.dist.broadcast(flat.flat_p, src=0)
+        del first
+
+    def _launch(self, b):
+        start, stop, _ = self._buckets[b]
+        if stop <= start:
+            return
+        view = self._flat.flat_g[start:stop]
+        if self._cuda():
+            comm = self._comm_stream()
+            comm.wait_stream(torch().cuda.current_stream())
+            with torch().cuda.stream(comm):
+                self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM)
+        else:
+            self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM)
+        self.n_allreduce += 1
+
+    def _bucket_ready(self, b):
+        params = self._flat.params
+        for i in self._buckets[b][2]:
+            p = params[i]
+            if p.pending_uses > 0 or p._grad._arr.pending_zero:
+                return False
+        return True
+
+    # ---- hooks
+    def _after_node(self, node):
+        if not self.overlap or self.world == 1 or self._flat is None or self.opt.flat is not self._flat:
+            return
+        while self._next < len(self._buckets) and self._bucket_ready(self._next):
+            self._launch(self._next)
+            self._next += 1
+
+    def _before_step(self, opt):
+        self._sync_plan()
+        if self.world > 1:
+            while self._next < len(self._buckets):
+                self._launch(self._next)
+                self._next += 1
+            if self._cuda():
+                torch().cuda.current_stream().wait_stream(self._comm_stream())
+        self._next = 0
+
+    def close(self):
+        if GLOBAL.AFTER_NODE_BACKWARD == self._after_node:
+            GLOBAL.AFTER_NODE_BACKWARD = None
+        self.opt.before_step = None
+        self.opt.grad_scale = 1.0
+
+
+def shard(array, rank, world):
+    """Contiguous batch shard `rank` of `world`."""
+    n = array.shape[0]
+    per = n // world
+    return array[rank * per:(rank + 1) * per]
