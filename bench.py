@@ -248,15 +248,11 @@ def run_ours(args, wl):
                 records.append((_n, a, s, e))
                 return r
             setattr(lib, n, wrapped)
-        import xshinnosuke_b200.nn.functional as F_
-        import xshinnosuke_b200.nn.grad_fn as G_
-        import xshinnosuke_b200.optim.optimizer as O_
         for _ in range(3):
             step_resident()
         torch.cuda.synchronize()
         for n, fn in originals.items():
             setattr(lib, n, fn)
-        del F_, G_, O_
         for n, a, s, e in records:
             kind, amount = opcost.cost(n, a)
             d = prof.setdefault(n, dict(ms=0.0, calls=0, amount=0.0, kind=kind))

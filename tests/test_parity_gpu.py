@@ -161,3 +161,65 @@ def test_no_silent_fallback_for_tensor_core_mode():
         return
     # mode 7 does not exist: reaching here means a silent fallback
     raise AssertionError("unknown math mode was accepted")
+
+
+# ------------------------------------------------------------------ tf32 tensor-core mode (tcgen05): <= 2e-3
+TOL_TC = 2e-3
+
+
+def _tc_stats():
+    import ctypes
+    from xshinnosuke_b200._lib import lib
+    buf = (ctypes.c_uint64 * 2)()
+    lib.xsb_tc_stats(ctypes.addressof(buf))
+    return buf[0], buf[1]
+
+
+@pytest.mark.parametrize("n,c,h,oc,k,s,p,n_tc", [
+    (4, 64, 14, 64, 3, 1, 1, 3), (8, 64, 28, 128, 3, 2, 1, 2), (8, 64, 28, 128, 1, 2, 0, 2), (4, 128, 14, 256, 3, 1, 1, 3),
+    (2, 256, 7, 512, 3, 1, 1, 3), (2, 64, 12, 64, 5, 1, 2, 3), (16, 64, 56, 64, 3, 1, 1, 3), (3, 32, 9, 64, 3, 1, 1, 2),
+    (2, 3, 20, 64, 7, 2, 3, 0)])
+def test_conv_tf32_tensor_cores(n, c, h, oc, k, s, p, n_tc):
+    """fwd / dgrad / wgrad on tcgen05 (kind::tf32) against the float64 oracle; `n_tc` = how many of the three
+    must have run on the tensor cores for this shape (stride-2 dgrad and C=3 run the fp32 FFMA kernel)."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    xs.set_math_mode("tf32")
+    try:
+        rs = np.random.RandomState(n * 1000 + c + h)
+        x = rs.randn(n, c, h, h).astype(np.float32)
+        w = (rs.randn(oc, c, k, k) * 0.1).astype(np.float32)
+        b = rs.randn(1, oc).astype(np.float32)
+        s0 = _tc_stats()
+        tx, tw, tb = xs.tensor(x, requires_grad=True), nn.Parameter(w), nn.Parameter(b)
+        y = F.conv2d(tx, tw, tb, (s, s), p)
+        yr, col = X.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), p)
+        assert X.rel_err(y.eval, yr) <= TOL_TC
+        g = rs.randn(*yr.shape).astype(np.float32)
+        y.backward(gradients=g)
+        s1 = _tc_stats()
+        dx, dw, db = X.conv2d_bwd(g.astype(np.float64), x.shape, w.astype(np.float64), col, (s, s), p)
+        assert X.rel_err(tx.grad.eval, dx) <= TOL_TC
+        assert X.rel_err(tw.grad.eval, dw) <= TOL_TC
+        assert X.rel_err(tb.grad.eval.reshape(-1), db) <= 1e-5
+        assert s1[0] - s0[0] == n_tc and (s1[0] - s0[0]) + (s1[1] - s0[1]) == 3
+    finally:
+        xs.set_math_mode("fp32")
+
+
+def test_resnet18_tf32_mode(golden):
+    """Whole ResNet-18 step in tf32 mode: logits of the first forward within 2e-3 of the reference."""
+    import xshinnosuke_b200 as xs
+    import parity_suite as S
+    xs.set_math_mode("tf32")
+    try:
+        c = golden.case("resnet18/n4_56")
+        net, losses, logits0 = S.resnet_steps(4, 56)
+        from oracle import xs_numpy as X
+        assert X.rel_err(logits0, c["logits0"]) <= 5e-3     # 20 tf32 convs + BN deep: per-op bound is 2e-3
+        assert abs(losses[0] - c["losses"][0]) / c["losses"][0] <= 5e-3
+        assert losses[2] < losses[0]
+    finally:
+        xs.set_math_mode("fp32")

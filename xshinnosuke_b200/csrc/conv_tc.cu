@@ -1,22 +1,599 @@
-// tcgen05 tensor-core path (placeholder until the kernels land): every entry reports UNSUPPORTED so that a
-// caller asking for XSB_MATH_TF32 fails loudly instead of silently running the FFMA path.
+// tcgen05 tensor-core implicit-GEMM convolution for sm_100a (XSB_MATH_TF32).
+//
+//  * operands stay fp32 in HBM (channels-last activations, [OC,KH,KW,C] filters) and are fed to
+//    `tcgen05.mma.cta_group::1.kind::tf32` directly: no conversion pass, no im2col buffer;
+//  * A tiles are fetched by TMA in IM2COL mode (cp.async.bulk.tensor.4d...im2col): one instruction
+//    gathers {32 channels x P pixels} for one filter tap, zero padding and the conv stride handled
+//    by the tensor map; B tiles by tiled 2-D TMA; both land in SWIZZLE_128B shared memory;
+//  * accumulators live in TMEM (fp32), read back with tcgen05.ld in the epilogue warps;
+//  * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 =
+//    epilogue; smem ring of STAGES stages guarded by full/empty mbarriers, tcgen05.commit frees stages.
+//
+//  fprop : D[pixel, oc]   = sum_{tap,c} patch[pixel,(tap,c)] * w[oc,(tap,c)]   A,B K-major
+//  dgrad : stride 1 only -- the same kernel on dY with the flipped/transposed filter wt[c,kh',kw',oc]
+//  wgrad : D[(tap,c), oc] = sum_pixel patch[pixel,(tap,c)] * dY[pixel,oc]      A,B MN-major, split-K
+//
+// Reference arithmetic: xs/nn/functional.py:405-442, xs/nn/grad_fn.py:186-203 (see gemm_conv.cu).
+// Shapes outside the envelope (C or OC not multiples of 32/64, strided dgrad) return
+// XSB_ERR_UNSUPPORTED from the xsb_tc_* probes and the caller runs the fp32 FFMA kernel instead.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "conv_geom.cuh"
 
+namespace tc {
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
+//   K-major : rows of 128 B (32 tf32 along K), 8-row groups SBO = 1024 B apart; K advance = +32 B.
+//   MN-major: rows of 128 B (32 elements along M/N) indexed by K, K groups SBO bytes apart,
+//             next 32-element M/N block LBO bytes away; K advance (8 rows) = +1024 B.
+//   32-bit MN-major operands (tf32) must use layout type 1 = SWIZZLE_128B_BASE32B ("for mn-major tf32
+//   operands, SW128_32B is the only available smem layout", CUTLASS sm100_common.inl): 32-byte chunks are
+//   swizzled inside each 128-byte row with a 4-row period, so K groups are 4 rows = 512 B (SBO) and the
+//   matching TMA mode is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = kLayoutSW128) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, M=128, N=n.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int BM = 128;
+constexpr int A_ROW_BYTES = 128;  // 32 fp32 = one SWIZZLE_128B row
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad
+struct FpropParams {
+    float* out;          // [M, ldo] row-major (channels-last output)
+    const float* bias;   // [OCtot] or null
+    int M, ldo;          // M = N*OH*OW output pixels, ldo = total output channels
+    int C, KH, KW, OH, OW, sh, sw, pad;
+    int accumulate;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int A_BYTES = BM * A_ROW_BYTES;
+    constexpr int B_BYTES = BN * A_ROW_BYTES;
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cblocks = p.C / 32;
+    const int num_kb = p.KH * p.KW * cblocks;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // first pixel of the tile -> window origin in the input image
+            const int hw = p.OH * p.OW;
+            const int n_img = m0 / hw, rem = m0 - n_img * hw;
+            const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+            const int w0 = ow0 * p.sw - p.pad, h0 = oh0 * p.sh - p.pad;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                tma_load_im2col(sA + s * A_BYTES, &tmA, &full[s], cb * 32, w0, h0, n_img, (uint16_t)kw, (uint16_t)kh);
+                tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], tap * p.C + cb * 32, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full[s], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), 16, 1024);
+                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 = 32 B) per 128-byte row
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        float* orow = p.out + (int64_t)m * p.ldo + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_wait_ld();
+            if (m < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    }
+                    float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
+                    if (p.accumulate) {
+                        const float4 o = *dst;
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                    *dst = v;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+struct WgradParams {
+    float* dw;           // [OC, KH*KW, C]
+    int P;               // N*OH*OW pixels (the reduction dimension)
+    int C, OC, KH, KW, OH, OW, sh, sw, pad;
+    int kb_per_split;    // pixel blocks per grid.z slice
+    int use_atomics;     // 1: red.add into dw (split-K or accumulate); 0: plain store
+};
+
+template <int BN, int BKP, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy, const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int BOX_BYTES = BKP * A_ROW_BYTES;       // one {32 elements x BKP pixels} box
+    constexpr int A_BYTES = 4 * BOX_BYTES;             // 128 rows of D = 4 boxes
+    constexpr int B_BYTES = (BN / 32) * BOX_BYTES;
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps = p.KH * p.KW;
+    const int r0 = blockIdx.x * BM;      // first row of D: rows are (tap, c)
+    const int n0 = blockIdx.y * BN;      // first output channel
+    const int total_kb = (p.P + BKP - 1) / BKP;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    int kb_end = kb_begin + p.kb_per_split;
+    if (kb_end > total_kb) kb_end = total_kb;
+    const int num_kb = kb_end - kb_begin;   // >= 1 by construction of the grid
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmDy);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int box_c[4], box_kh[4], box_kw[4], nvalid = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int mrow = r0 + i * 32;
+                const int tap = mrow / p.C;
+                box_c[i] = mrow - tap * p.C;
+                box_kh[i] = tap / p.KW;
+                box_kw[i] = tap - box_kh[i] * p.KW;
+                if (tap < taps) nvalid = i + 1;   // valid boxes are a prefix
+            }
+            const int hw = p.OH * p.OW;
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], nvalid * BOX_BYTES + B_BYTES);
+                const int p0 = (kb_begin + i) * BKP;
+                const int n_img = p0 / hw, rem = p0 - n_img * hw;
+                const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+                const int w0 = ow0 * p.sw - p.pad, h0 = oh0 * p.sh - p.pad;
+                for (int b = 0; b < nvalid; ++b)
+                    tma_load_im2col(sA + s * A_BYTES + b * BOX_BYTES, &tmX, &full[s], box_c[b], w0, h0, n_img,
+                                    (uint16_t)box_kw[b], (uint16_t)box_kh[b]);
+#pragma unroll
+                for (int b = 0; b < BN / 32; ++b)
+                    tma_load_2d(sB + s * B_BYTES + b * BOX_BYTES, &tmDy, &full[s], n0 + b * 32, p0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&full[s], (i / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
+                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
+#pragma unroll
+                for (int k = 0; k < BKP / 8; ++k)  // K = 8 pixels = two 4-row swizzle atoms = 1024 bytes
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (i | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int mrow = r0 + q * 32 + lane;
+        const int tap = mrow / p.C, c = mrow - tap * p.C;
+        const bool valid = tap < taps;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int oc = n0 + c0 + j;
+                    float* dst = p.dw + ((int64_t)oc * taps + tap) * p.C + c;   // lanes -> consecutive c: coalesced
+                    if (p.use_atomics)
+                        atomicAdd(dst, __uint_as_float(r[j]));
+                    else
+                        *dst = __uint_as_float(r[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+// wt[c, KH-1-kh, KW-1-kw, oc] = w[oc, kh, kw, c]: the filter of the equivalent forward conv on dY
+__global__ void flip_transpose_filter_k(const float* __restrict__ w, float* __restrict__ wt, int OC, int taps, int C) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z;
+    const int c0 = blockIdx.x * 32, oc0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int oc = oc0 + j, c = c0 + threadIdx.x;
+        if (oc < OC && c < C) tile[j][threadIdx.x] = w[((int64_t)oc * taps + tap) * C + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, oc = oc0 + threadIdx.x;
+        if (oc < OC && c < C) wt[((int64_t)c * taps + (taps - 1 - tap)) * OC + oc] = tile[threadIdx.x][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+static bool load_driver_entry_points() {
+    if (g_encode_tiled && g_encode_im2col) return true;
+    cudaDriverEntryPointQueryResult qr;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return false;
+    g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return false;
+    g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+    return true;
+}
+
+// 2-D fp32 row-major matrix [rows, cols] (cols contiguous), box {32 cols, box_rows}, SWIZZLE_128B
+static bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// im2col view of a channels-last activation [N,H,W,Cx]: box {32 channels, pixels_per_col output pixels};
+// window origins span [-pad, W+pad-KW] (step = conv stride), taps are given per load as {kw, kh} offsets.
+static bool make_map_im2col(CUtensorMap* m, const float* base, int N, int H, int W, int Cx, int KH, int KW, int sh,
+                            int sw, int pad, uint32_t pixels_per_col,
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cx * 4, (cuuint64_t)W * Cx * 4, (cuuint64_t)H * W * Cx * 4};
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (KW - 1), pad - (KH - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+    CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower,
+                                 upper, 32, pixels_per_col, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    // Same driver workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): for tensors smaller
+    // than 128 KiB drivers <= 13.1 set a descriptor bit that breaks im2col traversal.
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (uint64_t)N * H * W * Cx * 4 < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+    return true;
+}
+
+static uint64_t g_tc_launches = 0, g_ffma_fallbacks = 0;
+
+template <int BN, int STAGES>
+static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const FpropParams& p, int n_tiles, cudaStream_t s) {
+    constexpr int smem = STAGES * (BM * A_ROW_BYTES + BN * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        XSB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid((p.M + BM - 1) / BM, n_tiles);
+    conv_fprop_tc_k<BN, STAGES><<<grid, kThreads, smem, s>>>(a, b, p);
+    XSB_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return XSB_OK;
+}
+
+// D[M, OCx] (+)= conv of channels-last `in` [N,H,W,Cx] with filter `flt` [OCx, KH*KW*Cx] (+ bias)
+static int fprop_dispatch(const float* in, const float* flt, const float* bias, float* out, int N, int H, int W, int Cx,
+                          int OCx, int KH, int KW, int sh, int sw, int pad, int OH, int OW, int accumulate,
+                          cudaStream_t s) {
+    if (!load_driver_entry_points()) {
+        xsb_set_error("cuTensorMapEncode* entry points unavailable");
+        return XSB_ERR_CUDA;
+    }
+    const int BN = (OCx % 256 == 0) ? 256 : (OCx % 128 == 0) ? 128 : 64;
+    CUtensorMap ta, tb;
+    if (!make_map_im2col(&ta, in, N, H, W, Cx, KH, KW, sh, sw, pad, BM) ||
+        !make_map_2d(&tb, flt, (uint64_t)OCx, (uint64_t)KH * KW * Cx, (uint32_t)BN)) {
+        xsb_set_error("cuTensorMapEncode failed (fprop N=%d H=%d W=%d C=%d OC=%d k=%dx%d s=%d p=%d)", N, H, W, Cx, OCx, KH,
+                      KW, sh, pad);
+        return XSB_ERR_CUDA;
+    }
+    FpropParams p{out, bias, N * OH * OW, OCx, Cx, KH, KW, OH, OW, sh, sw, pad, accumulate};
+    if (BN == 256) return launch_fprop<256, 4>(ta, tb, p, OCx / 256, s);
+    if (BN == 128) return launch_fprop<128, 6>(ta, tb, p, OCx / 128, s);
+    return launch_fprop<64, 8>(ta, tb, p, OCx / 64, s);
+}
+
+template <int BN, int BKP, int STAGES>
+static int launch_wgrad(const CUtensorMap& x, const CUtensorMap& dy, const WgradParams& p, dim3 grid, cudaStream_t s) {
+    constexpr int smem = STAGES * ((4 + BN / 32) * BKP * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_k<BN, BKP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    conv_wgrad_tc_k<BN, BKP, STAGES><<<grid, kThreads, smem, s>>>(x, dy, p);
+    XSB_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return XSB_OK;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------ entry points
+// Envelope of the tensor-core kernels; everything else is answered with XSB_ERR_UNSUPPORTED and the
+// caller (gemm_conv.cu) runs the fp32 FFMA kernel, counting the event in xsb_tc_stats.
+static bool fprop_ok(int Cx, int OCx, const void* a, const void* b, const void* c) {
+    return Cx % 32 == 0 && OCx % 64 == 0 && aligned16(a) && aligned16(b) && aligned16(c);
+}
+
 int xsb_tc_gemm(const float*, const float*, float*, const float*, int, int, int, int, int, int, float*, int64_t,
                 cudaStream_t) {
-    xsb_set_error("tcgen05 GEMM not built yet");
-    return XSB_ERR_UNSUPPORTED;
+    return XSB_ERR_UNSUPPORTED;   // Dense layers of the hot path are < 1 % of the FLOPs: FFMA kernel
 }
-int xsb_tc_conv_fwd(const float*, const float*, const float*, float*, const ConvGeom&, float*, int64_t, cudaStream_t) {
-    xsb_set_error("tcgen05 conv fwd not built yet");
-    return XSB_ERR_UNSUPPORTED;
+
+int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
+                    int64_t ws_floats, cudaStream_t s) {
+    (void)ws; (void)ws_floats;
+    if (!fprop_ok(g.C, g.OC, x, w, y) || g.KW > 255 || g.KH > 255) return XSB_ERR_UNSUPPORTED;
+    return fprop_dispatch(x, w, bias, y, g.N, g.H, g.W, g.C, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.OH, g.OW, 0, s);
 }
-int xsb_tc_conv_dgrad(const float*, const float*, float*, const ConvGeom&, int, float*, int64_t, cudaStream_t) {
-    xsb_set_error("tcgen05 conv dgrad not built yet");
-    return XSB_ERR_UNSUPPORTED;
+
+int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
+                      int64_t ws_floats, cudaStream_t s) {
+    // stride-1 only: dX = conv(dY, flip/transpose(w)) with pad' = K-1-pad
+    if (g.sh != 1 || g.sw != 1 || g.pad > g.KH - 1 || g.pad > g.KW - 1) return XSB_ERR_UNSUPPORTED;
+    if (!fprop_ok(g.OC, g.C, dy, w, dx)) return XSB_ERR_UNSUPPORTED;
+    if (g.KH != g.KW) return XSB_ERR_UNSUPPORTED;
+    const int64_t wn = (int64_t)g.OC * g.KH * g.KW * g.C;
+    if (!ws || ws_floats < wn) return XSB_ERR_UNSUPPORTED;
+    const int taps = g.KH * g.KW;
+    dim3 grid((g.C + 31) / 32, (g.OC + 31) / 32, taps), block(32, 8);
+    flip_transpose_filter_k<<<grid, block, 0, s>>>(w, ws, g.OC, taps, g.C);
+    XSB_LAUNCH_CHECK();
+    return fprop_dispatch(dy, ws, nullptr, dx, g.N, g.OH, g.OW, g.OC, g.C, g.KH, g.KW, 1, 1, g.KH - 1 - g.pad, g.H, g.W,
+                          accumulate, s);
 }
-int xsb_tc_conv_wgrad(const float*, const float*, float*, const ConvGeom&, int, float*, int64_t, cudaStream_t) {
-    xsb_set_error("tcgen05 conv wgrad not built yet");
-    return XSB_ERR_UNSUPPORTED;
+
+int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
+                      int64_t ws_floats, cudaStream_t s) {
+    (void)ws; (void)ws_floats;
+    if (g.C % 32 != 0 || g.OC % 64 != 0 || !aligned16(dy) || !aligned16(x) || !aligned16(dw)) return XSB_ERR_UNSUPPORTED;
+    if (!load_driver_entry_points()) {
+        xsb_set_error("cuTensorMapEncode* entry points unavailable");
+        return XSB_ERR_CUDA;
+    }
+    const int P = g.N * g.OH * g.OW;
+    const int BN = (g.OC % 256 == 0) ? 256 : (g.OC % 128 == 0) ? 128 : 64;
+    const int BKP = BN == 256 ? 32 : 64;
+    CUtensorMap tx, tdy;
+    if (!make_map_im2col(&tx, x, g.N, g.H, g.W, g.C, g.KH, g.KW, g.sh, g.sw, g.pad, (uint32_t)BKP,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map_2d(&tdy, dy, (uint64_t)P, (uint64_t)g.OC, (uint32_t)BKP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
+        xsb_set_error("cuTensorMapEncode failed (wgrad)");
+        return XSB_ERR_CUDA;
+    }
+    const int rows = g.KH * g.KW * g.C;
+    const int m_tiles = (rows + BM - 1) / BM, n_tiles = g.OC / BN;
+    const int total_kb = (P + BKP - 1) / BKP;
+    int splits = (2 * xsb_sm_count_cached() + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+    if (splits > total_kb / 4) splits = total_kb / 4;
+    if (splits < 1) splits = 1;
+    int kb_per = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kb_per - 1) / kb_per;
+    const int use_atomics = (splits > 1 || accumulate) ? 1 : 0;
+    if (use_atomics && !accumulate) XSB_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.OC * rows * sizeof(float), s));
+    WgradParams p{dw, P, g.C, g.OC, g.KH, g.KW, g.OH, g.OW, g.sh, g.sw, g.pad, kb_per, use_atomics};
+    dim3 grid(m_tiles, n_tiles, splits);
+    if (BN == 256) return launch_wgrad<256, 32, 4>(tx, tdy, p, grid, s);
+    if (BN == 128) return launch_wgrad<128, 64, 3>(tx, tdy, p, grid, s);
+    return launch_wgrad<64, 64, 4>(tx, tdy, p, grid, s);
 }
+
+extern "C" {
+// counters: [0] tensor-core kernel launches, [1] GEMM-shaped calls that ran the fp32 FFMA kernel in TF32 mode
+int xsb_tc_stats(uint64_t* out2) {
+    out2[0] = tc::g_tc_launches;
+    out2[1] = tc::g_ffma_fallbacks;
+    return XSB_OK;
+}
+}
+void xsb_tc_note_ffma() { ++tc::g_ffma_fallbacks; }

@@ -23,6 +23,22 @@ int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom
                       int64_t ws_floats, cudaStream_t s);
 int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
                       int64_t ws_floats, cudaStream_t s);
+void xsb_tc_note_ffma();
+
+// TF32 mode: run the tensor-core kernel when the shape is inside its envelope; XSB_ERR_UNSUPPORTED means
+// "not my shape" and the fp32 FFMA kernel (a strictly more accurate CUDA kernel of this library) takes the
+// call, counted in xsb_tc_stats. Any other math_mode value is an error.
+#define XSB_TRY_TC(call)                                                     \
+    do {                                                                     \
+        if (math_mode == 1) {                                                \
+            const int rc__ = (call);                                         \
+            if (rc__ != XSB_ERR_UNSUPPORTED) return rc__;                    \
+            xsb_tc_note_ffma();                                              \
+        } else if (math_mode != 0) {                                         \
+            xsb_set_error("unknown math_mode %d", math_mode);                \
+            return XSB_ERR_ARG;                                              \
+        }                                                                    \
+    } while (0)
 
 namespace {
 
@@ -43,7 +59,7 @@ extern "C" {
 int xsb_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
              int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, void* stream) {
     cudaStream_t s = xsb_stream(stream);
-    if (math_mode != 0) return xsb_tc_gemm(A, B, C, bias, M, N, K, transA, transB, accumulate, ws, ws_floats, s);
+    XSB_TRY_TC(xsb_tc_gemm(A, B, C, bias, M, N, K, transA, transB, accumulate, ws, ws_floats, s));
     const bool split_ok = true;
     if (!transA && !transB) {
         MatK la{A, K, M, K, K % 4 == 0 && aligned16(A)};
@@ -71,7 +87,7 @@ int xsb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
     ConvGeom g;
     XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_fwd: bad geometry");
     cudaStream_t s = xsb_stream(stream);
-    if (math_mode != 0) return xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s);
+    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s));
     const int P = N * g.OH * g.OW, J = KH * KW * C;
     PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
     MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};
@@ -85,7 +101,7 @@ int xsb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, i
     ConvGeom g;
     XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_dgrad: bad geometry");
     cudaStream_t s = xsb_stream(stream);
-    if (math_mode != 0) return xsb_tc_conv_dgrad(dy, w, dx, g, accumulate, ws, ws_floats, s);
+    XSB_TRY_TC(xsb_tc_conv_dgrad(dy, w, dx, g, accumulate, ws, ws_floats, s));
     const int P = N * H * W, J = KH * KW * OC;
     DgradA la{dy, g, P, J, OC % 4 == 0 && aligned16(dy)};
     DgradB lb{w, g, J, C % 4 == 0 && aligned16(w)};
@@ -99,7 +115,7 @@ int xsb_conv2d_wgrad(const float* dy, const float* x, float* dw, int N, int H, i
     ConvGeom g;
     XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_wgrad: bad geometry");
     cudaStream_t s = xsb_stream(stream);
-    if (math_mode != 0) return xsb_tc_conv_wgrad(dy, x, dw, g, accumulate, ws, ws_floats, s);
+    XSB_TRY_TC(xsb_tc_conv_wgrad(dy, x, dw, g, accumulate, ws, ws_floats, s));
     const int P = N * g.OH * g.OW, J = KH * KW * C;
     MatR la{dy, OC, OC, P, OC % 4 == 0 && aligned16(dy)};  // A[m=oc][k=pixel] = dy[pixel*OC + oc]
     PatchB lb{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
