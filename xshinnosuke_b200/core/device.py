@@ -28,7 +28,7 @@ class Runtime:
     """One process drives one GPU (LOCAL_RANK) from one host thread."""
 
     WS_SMALL_FLOATS = 4 << 20     # BN / colsum partials + ticket counters (zero-initialised once)
-    WS_BIG_FLOATS = 48 << 20      # split-K partials of the FP32 implicit GEMM
+    WS_BIG_FLOATS = 80 << 20      # split-K partials (FP32 implicit GEMM); flipped filter + zero-inserted dY (tcgen05 dgrad)
 
     def __init__(self):
         self.ready = False

@@ -57,6 +57,17 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[V]) {
     }
 }
 
+// per-channel parameters: small, re-read by every thread -> keep them on the cached (L1) path, 128-bit wide
+template <int V>
+__device__ __forceinline__ void load_param(const float* p, float (&v)[V]) {
+    if (V == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
 struct Moments {  // count, mean, sum of squared deviations
     float n, mean, m2;
 };
@@ -249,11 +260,13 @@ bn_apply_k(const float* __restrict__ x, float* __restrict__ y, const float* __re
         const int64_t i = base + (int64_t)j * kThreads;
         if (i < nvec) {
             const int c = (cv_mask >= 0 ? (int)((unsigned)i & (unsigned)cv_mask) : (int)(i % CV)) * V;
-            float o[V];
+            float o[V], pm[V], pi[V], pg[V], pb[V];
+            load_param<V>(mean + c, pm);
+            load_param<V>(invstd + c, pi);
+            load_param<V>(gamma + c, pg);
+            load_param<V>(beta + c, pb);
 #pragma unroll
-            for (int q = 0; q < V; ++q)
-                o[q] = fmaf((v[j][q] - __ldg(mean + c + q)) * __ldg(invstd + c + q), __ldg(gamma + c + q),
-                            __ldg(beta + c + q));
+            for (int q = 0; q < V; ++q) o[q] = fmaf((v[j][q] - pm[q]) * pi[q], pg[q], pb[q]);
             if (V == 4)
                 stg_stream(reinterpret_cast<float4*>(y + i * V), make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]));
             else
@@ -429,11 +442,16 @@ bn_bwd_apply_k(const float* __restrict__ dy, const float* __restrict__ x, float*
         const int64_t i = base + (int64_t)j * kThreads;
         if (i < nvec) {
             const int c = (cv_mask >= 0 ? (int)((unsigned)i & (unsigned)cv_mask) : (int)(i % CV)) * V;
-            float o[V];
+            float o[V], pm[V], pi[V], k1[V], k2[V], kg[V];
+            load_param<V>(mean + c, pm);
+            load_param<V>(invstd + c, pi);
+            load_param<V>(coef + c, k1);
+            load_param<V>(coef + C + c, k2);
+            load_param<V>(coef + 2 * C + c, kg);
 #pragma unroll
             for (int q = 0; q < V; ++q) {
-                const float xhat = (xv[j][q] - __ldg(mean + c + q)) * __ldg(invstd + c + q);
-                o[q] = __ldg(coef + 2 * C + c + q) * (g[j][q] - __ldg(coef + c + q) - xhat * __ldg(coef + C + c + q));
+                const float xhat = (xv[j][q] - pm[q]) * pi[q];
+                o[q] = kg[q] * (g[j][q] - k1[q] - xhat * k2[q]);
             }
             if (V == 4) {
                 float4* p = reinterpret_cast<float4*>(dx + i * V);

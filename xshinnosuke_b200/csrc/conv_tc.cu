@@ -10,7 +10,8 @@
 //    epilogue; smem ring of STAGES stages guarded by full/empty mbarriers, tcgen05.commit frees stages.
 //
 //  fprop : D[pixel, oc]   = sum_{tap,c} patch[pixel,(tap,c)] * w[oc,(tap,c)]   A,B K-major
-//  dgrad : stride 1 only -- the same kernel on dY with the flipped/transposed filter wt[c,kh',kw',oc]
+//  dgrad : the same kernel on dY (zero-inserted for strided convs) with the flipped/transposed filter
+//          wt[c,kh',kw',oc], pad' = K-1-pad
 //  wgrad : D[(tap,c), oc] = sum_pixel patch[pixel,(tap,c)] * dY[pixel,oc]      A,B MN-major, split-K
 //
 // Reference arithmetic: xs/nn/functional.py:405-442, xs/nn/grad_fn.py:186-203 (see gemm_conv.cu).
@@ -410,6 +411,21 @@ __global__ void flip_transpose_filter_k(const float* __restrict__ w, float* __re
     }
 }
 
+// up[n, oh*sh, ow*sw, :] = dy[n, oh, ow, :] (up is pre-zeroed): the zero-insertion that turns a strided
+// dgrad into a stride-1 convolution of the up-sampled dY with the flipped filter.
+__global__ void zero_insert_k(const float4* __restrict__ dy, float4* __restrict__ up, int OH, int OW, int C4, int Hu,
+                              int Wu, int sh, int sw, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int c = (int)(t % C4);
+    int64_t r = t / C4;
+    const int ow = (int)(r % OW);
+    r /= OW;
+    const int oh = (int)(r % OH);
+    const int n = (int)(r / OH);
+    up[(((int64_t)n * Hu + (int64_t)oh * sh) * Wu + (int64_t)ow * sw) * C4 + c] = dy[t];
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
 static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
@@ -443,11 +459,12 @@ static bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64
 // window origins span [-pad, W+pad-KW] (step = conv stride), taps are given per load as {kw, kh} offsets.
 static bool make_map_im2col(CUtensorMap* m, const float* base, int N, int H, int W, int Cx, int KH, int KW, int sh,
                             int sw, int pad, uint32_t pixels_per_col,
-                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int extra_w = 0, int extra_h = 0) {
     cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)Cx * 4, (cuuint64_t)W * Cx * 4, (cuuint64_t)H * W * Cx * 4};
     int lower[2] = {-pad, -pad};
-    int upper[2] = {pad - (KW - 1), pad - (KH - 1)};
+    // extra_*: additional window origins past the symmetric-padding range (their taps read the zero OOB fill)
+    int upper[2] = {pad - (KW - 1) + extra_w, pad - (KH - 1) + extra_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
     CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower,
                                  upper, 32, pixels_per_col, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -481,14 +498,14 @@ static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const FpropP
 // D[M, OCx] (+)= conv of channels-last `in` [N,H,W,Cx] with filter `flt` [OCx, KH*KW*Cx] (+ bias)
 static int fprop_dispatch(const float* in, const float* flt, const float* bias, float* out, int N, int H, int W, int Cx,
                           int OCx, int KH, int KW, int sh, int sw, int pad, int OH, int OW, int accumulate,
-                          cudaStream_t s) {
+                          cudaStream_t s, int extra_w = 0, int extra_h = 0) {
     if (!load_driver_entry_points()) {
         xsb_set_error("cuTensorMapEncode* entry points unavailable");
         return XSB_ERR_CUDA;
     }
     const int BN = (OCx % 256 == 0) ? 256 : (OCx % 128 == 0) ? 128 : 64;
     CUtensorMap ta, tb;
-    if (!make_map_im2col(&ta, in, N, H, W, Cx, KH, KW, sh, sw, pad, BM) ||
+    if (!make_map_im2col(&ta, in, N, H, W, Cx, KH, KW, sh, sw, pad, BM, CU_TENSOR_MAP_SWIZZLE_128B, extra_w, extra_h) ||
         !make_map_2d(&tb, flt, (uint64_t)OCx, (uint64_t)KH * KW * Cx, (uint32_t)BN)) {
         xsb_set_error("cuTensorMapEncode failed (fprop N=%d H=%d W=%d C=%d OC=%d k=%dx%d s=%d p=%d)", N, H, W, Cx, OCx, KH,
                       KW, sh, pad);
@@ -539,18 +556,36 @@ int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y,
 
 int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
                       int64_t ws_floats, cudaStream_t s) {
-    // stride-1 only: dX = conv(dY, flip/transpose(w)) with pad' = K-1-pad
-    if (g.sh != 1 || g.sw != 1 || g.pad > g.KH - 1 || g.pad > g.KW - 1) return XSB_ERR_UNSUPPORTED;
+    // dX = conv_stride1(dY (zero-inserted when the forward conv was strided), flip/transpose(w)), pad' = K-1-pad
+    if (g.pad > g.KH - 1 || g.pad > g.KW - 1 || g.KH != g.KW) return XSB_ERR_UNSUPPORTED;
     if (!fprop_ok(g.OC, g.C, dy, w, dx)) return XSB_ERR_UNSUPPORTED;
-    if (g.KH != g.KW) return XSB_ERR_UNSUPPORTED;
     const int64_t wn = (int64_t)g.OC * g.KH * g.KW * g.C;
-    if (!ws || ws_floats < wn) return XSB_ERR_UNSUPPORTED;
+    const bool strided = g.sh != 1 || g.sw != 1;
+    const int Hu = (g.OH - 1) * g.sh + 1, Wu = (g.OW - 1) * g.sw + 1;
+    const int64_t un = strided ? (int64_t)g.N * Hu * Wu * g.OC : 0;
+    const int64_t wn_al = (wn + 255) / 256 * 256;
+    if (!ws || ws_floats < wn_al + un) return XSB_ERR_UNSUPPORTED;
     const int taps = g.KH * g.KW;
     dim3 grid((g.C + 31) / 32, (g.OC + 31) / 32, taps), block(32, 8);
     flip_transpose_filter_k<<<grid, block, 0, s>>>(w, ws, g.OC, taps, g.C);
     XSB_LAUNCH_CHECK();
-    return fprop_dispatch(dy, ws, nullptr, dx, g.N, g.OH, g.OW, g.OC, g.C, g.KH, g.KW, 1, 1, g.KH - 1 - g.pad, g.H, g.W,
-                          accumulate, s);
+    const int padp = g.KH - 1 - g.pad;
+    const float* src = dy;
+    if (strided) {
+        float* up = ws + wn_al;
+        XSB_CUDA(cudaMemsetAsync(up, 0, (size_t)un * sizeof(float), s));
+        const int64_t total = (int64_t)g.N * g.OH * g.OW * (g.OC / 4);
+        zero_insert_k<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(dy),
+                                                                      reinterpret_cast<float4*>(up), g.OH, g.OW,
+                                                                      g.OC / 4, Hu, Wu, g.sh, g.sw, total);
+        XSB_LAUNCH_CHECK();
+        src = up;
+    }
+    // rows/cols of dX past the last forward window get no gradient: extend the im2col box so they are produced (as 0)
+    const int extra_h = g.H - (Hu + 2 * padp - g.KH + 1), extra_w = g.W - (Wu + 2 * padp - g.KW + 1);
+    if (extra_h < 0 || extra_w < 0 || extra_h > 64 || extra_w > 64) return XSB_ERR_UNSUPPORTED;
+    return fprop_dispatch(src, ws, nullptr, dx, g.N, strided ? Hu : g.OH, strided ? Wu : g.OW, g.OC, g.C, g.KH, g.KW, 1, 1,
+                          padp, g.H, g.W, accumulate, s, extra_w, extra_h);
 }
 
 int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
