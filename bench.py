@@ -89,17 +89,23 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count()
+
+
 def run_reference(args, wl):
     """The reference's own algorithm (float64 im2col + np.dot + col2im, oracle/ port of xs/nn/functional.py,
     xs/nn/grad_fn.py, xs/optim) on the host cores, every BLAS thread it can use. Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle.resnet18 import ResNet18 as OracleNet, synthetic_batch
-    try:
-        from threadpoolctl import threadpool_info
-        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        cores = os.cpu_count()
+    cores = _use_all_host_threads()
     # bounded sample: a step on the full 224x224 batch is ~1.4 TFLOP of float64 -> time a 4-image slice instead
     n = wl["batch"] if wl["hw"] <= 64 else 4
     x, y = synthetic_batch(n, wl["hw"], wl["classes"], seed=0)
@@ -127,11 +133,7 @@ def run_reference(args, wl):
 
 def cpu_baseline_leg(wl, budget_s=20.0):
     from oracle.resnet18 import ResNet18 as OracleNet, synthetic_batch
-    try:
-        from threadpoolctl import threadpool_info
-        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        cores = os.cpu_count()
+    cores = _use_all_host_threads()
     n = wl["batch"] if wl["hw"] <= 64 else 2
     x, y = synthetic_batch(n, wl["hw"], wl["classes"], seed=0)
     net = OracleNet(num_classes=wl["classes"])
@@ -231,6 +233,10 @@ def run_ours(args, wl):
 
     # ---- per-kernel CUDA-event profile (3 extra steps, same stream) for the roofline of the dominant kernel
     prof = {}
+    if rank != 0 and dp is not None:
+        for _ in range(3):          # the profiled steps contain collectives: every rank must take part
+            step_resident()
+        torch.cuda.synchronize()
     if rank == 0:
         lib.load()
         names = [n for n in lib.protos if n.startswith("xsb_") and lib.protos[n][1] and
@@ -311,8 +317,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="r56", choices=sorted(WORKLOADS))
-    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--workload", default="r224", choices=sorted(WORKLOADS))
+    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--bucket-mb", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
