@@ -178,10 +178,12 @@ def _tc_stats():
 @pytest.mark.parametrize("n,c,h,oc,k,s,p,n_tc", [
     (4, 64, 14, 64, 3, 1, 1, 3), (8, 64, 28, 128, 3, 2, 1, 3), (8, 64, 28, 128, 1, 2, 0, 3), (4, 64, 15, 128, 3, 2, 1, 3), (4, 128, 14, 256, 3, 1, 1, 3),
     (2, 256, 7, 512, 3, 1, 1, 3), (2, 64, 12, 64, 5, 1, 2, 3), (16, 64, 56, 64, 3, 1, 1, 3), (3, 32, 9, 64, 3, 1, 1, 2),
-    (2, 3, 20, 64, 7, 2, 3, 0)])
+    (2, 3, 20, 64, 7, 2, 3, 2), (4, 3, 56, 64, 7, 2, 3, 2), (2, 1, 28, 64, 2, 1, 0, 2), (3, 3, 33, 128, 3, 1, 1, 2),
+    (2, 4, 19, 64, 5, 2, 2, 2), (2, 3, 20, 8, 3, 1, 1, 0)])
 def test_conv_tf32_tensor_cores(n, c, h, oc, k, s, p, n_tc):
     """fwd / dgrad / wgrad on tcgen05 (kind::tf32) against the float64 oracle; `n_tc` = how many of the three
-    must have run on the tensor cores for this shape (C=3 and channel counts off the 32/64 grid run the fp32 FFMA kernel)."""
+    must have run on the tensor cores for this shape (C <= 4 stems: fwd + wgrad via the padded-4-channel kernels,
+    their dgrad and channel counts off the 32/64 grid run the fp32 FFMA kernel)."""
     import xshinnosuke_b200 as xs
     from oracle import xs_numpy as X
     from xshinnosuke_b200 import nn

@@ -59,6 +59,22 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
                                                 int n, uint16_t off_w, uint16_t off_h) {
     asm volatile(
@@ -395,6 +411,268 @@ conv_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ stem (C <= 4)
+// First-layer convolutions have 1..4 input channels (K = KH*KW*C = 147 for the 7x7/2 ResNet stem): no 32-channel
+// k-block exists. The image is first copied into a zero-bordered 4-channel buffer xp[N,Hp,Wp,4]; then for a fixed
+// filter row kh the taps (kw, c) of one output pixel are 32 CONTIGUOUS floats starting at pixel
+// (oh*sh+kh, ow*sw) -- 8 pixels x 4 channels, columns kw >= KW / c >= C meet zero filter entries. A 5-D TILED tensor
+// map with overlapping strides {ow: sw*16 B, oh: sh*Wp*16 B, kh: Wp*16 B, n} exposes exactly those rows, so the
+// mainloop is the usual TMA -> tcgen05 pipeline with KH k-blocks of 32.
+constexpr int STEM_TW = 16, STEM_TH = 8;    // fprop tile: 16 x 8 output pixels = 128 rows of D
+constexpr int STEM_WTH = 4;                 // wgrad pixel block: 16 x 4 = 64 pixels (the K dimension)
+
+struct StemParams {
+    float* out;           // fprop: y [N,OH,OW,OC] ; wgrad: dw [OC,KH,KW,C]
+    const float* bias;
+    int N, OH, OW, OC, KH, KW, C;
+    int tiles_w, tiles_h;
+    int kb_per_split, use_atomics;
+};
+
+// xp[n, h+pad, w+pad, 0..3] = x[n,h,w,0..C-1] (zero elsewhere); every element of xp is written
+__global__ void stem_pad_c4_k(const float* __restrict__ x, float4* __restrict__ xp, int N, int H, int W, int C, int Hp,
+                              int Wp, int pad) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)N * Hp * Wp;
+    if (t >= total) return;
+    const int wp = (int)(t % Wp);
+    const int64_t r = t / Wp;
+    const int hp = (int)(r % Hp);
+    const int n = (int)(r / Hp);
+    const int h = hp - pad, w = wp - pad;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+        const float* src = x + (((int64_t)n * H + h) * W + w) * C;
+        for (int c = 0; c < C; ++c) v[c] = __ldg(src + c);
+    }
+    xp[t] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// wq[oc, kh, kw(8), c(4)] = w[oc, kh, kw, c] (zero for kw >= KW or c >= C)
+__global__ void stem_pack_filter_k(const float* __restrict__ w, float* __restrict__ wq, int OC, int KH, int KW, int C) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= OC * KH * 32) return;
+    const int j = t % 32, kh = (t / 32) % KH, oc = t / (32 * KH);
+    const int kw = j / 4, c = j % 4;
+    wq[t] = (kw < KW && c < C) ? w[((oc * KH + kh) * KW + kw) * C + c] : 0.f;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+stem_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StemParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int A_BYTES = BM * A_ROW_BYTES;
+    constexpr int B_BYTES = BN * A_ROW_BYTES;
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = p.KH;
+    const int t = blockIdx.x;
+    const int tw_i = t % p.tiles_w, th_i = (t / p.tiles_w) % p.tiles_h, n_img = t / (p.tiles_w * p.tiles_h);
+    const int n0 = blockIdx.y * BN;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], 0, tw_i * STEM_TW, th_i * STEM_TH, kb, n_img);
+                tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * 32, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full[s], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), 16, 1024);
+                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = q * 32 + lane;
+        const int oh = th_i * STEM_TH + row / STEM_TW, ow = tw_i * STEM_TW + row % STEM_TW;
+        const bool valid = oh < p.OH && ow < p.OW;
+        float* orow = p.out + (((int64_t)n_img * p.OH + oh) * p.OW + ow) * p.OC + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    }
+                    *reinterpret_cast<float4*>(orow + c0 + j) = v;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+// dwq[(kh, kw, c4), oc] = sum over pixel blocks of xp-rows^T . dY ; both operands MN-major (pixels = K)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+stem_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy, const StemParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int BKP = STEM_TW * STEM_WTH;            // 64 pixels per k-block
+    constexpr int BOX_BYTES = BKP * A_ROW_BYTES;
+    constexpr int A_BYTES = 4 * BOX_BYTES;
+    constexpr int B_BYTES = (BN / 32) * BOX_BYTES;
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kh0 = blockIdx.x * 4;                    // this CTA's 4 filter rows = 128 rows of D
+    const int n0 = blockIdx.y * BN;
+    const int blocks_per_img = p.tiles_w * p.tiles_h;  // tiles_h counts 4-row blocks here
+    const int total_kb = p.N * blocks_per_img;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    int kb_end = kb_begin + p.kb_per_split;
+    if (kb_end > total_kb) kb_end = total_kb;
+    const int num_kb = kb_end - kb_begin;
+    int nvalid = p.KH - kh0;
+    if (nvalid > 4) nvalid = 4;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmDy);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], nvalid * BOX_BYTES + B_BYTES);
+                const int kb = kb_begin + i;
+                const int n_img = kb / blocks_per_img, rem = kb - n_img * blocks_per_img;
+                const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+                for (int b = 0; b < nvalid; ++b)
+                    tma_load_5d(sA + s * A_BYTES + b * BOX_BYTES, &tmX, &full[s], 0, tw_i * STEM_TW, th_i * STEM_WTH,
+                                kh0 + b, n_img);
+#pragma unroll
+                for (int b = 0; b < BN / 32; ++b)
+                    tma_load_4d(sB + s * B_BYTES + b * BOX_BYTES, &tmDy, &full[s], n0 + b * 32, tw_i * STEM_TW,
+                                th_i * STEM_WTH, n_img);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&full[s], (i / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
+                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
+#pragma unroll
+                for (int k = 0; k < BKP / 8; ++k)
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (i | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = q * 32 + lane;
+        const int kh = kh0 + row / 32, j = row % 32, kw = j / 4, c = j % 4;
+        const bool valid = kh < p.KH && kw < p.KW && c < p.C;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int oc = n0 + c0 + jj;
+                    float* dst = p.out + (((int64_t)oc * p.KH + kh) * p.KW + kw) * p.C + c;
+                    if (p.use_atomics)
+                        atomicAdd(dst, __uint_as_float(r[jj]));
+                    else
+                        *dst = __uint_as_float(r[jj]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
 // wt[c, KH-1-kh, KW-1-kw, oc] = w[oc, kh, kw, c]: the filter of the equivalent forward conv on dY
 __global__ void flip_transpose_filter_k(const float* __restrict__ w, float* __restrict__ wt, int OC, int taps, int C) {
     __shared__ float tile[32][33];
@@ -531,7 +809,127 @@ static int launch_wgrad(const CUtensorMap& x, const CUtensorMap& dy, const Wgrad
     return XSB_OK;
 }
 
+// generic tiled map: dims/strides innermost first (strides in bytes for dims 1..rank-1), fp32
+static bool make_map_tiled(CUtensorMap* m, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                           const cuuint32_t* box, CUtensorMapSwizzle swz) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct StemPlan {
+    int Hp, Wp;
+    int64_t xp_floats, wq_floats;
+};
+static bool stem_ok(const ConvGeom& g) {
+    return g.C <= 4 && g.KW <= 8 && g.KH <= 64 && g.OC % 64 == 0 && g.sw * 16 % 16 == 0;
+}
+static StemPlan stem_plan(const ConvGeom& g) {
+    StemPlan p;
+    p.Hp = g.H + 2 * g.pad;
+    const int need_h = (g.OH - 1) * g.sh + g.KH;
+    if (p.Hp < need_h) p.Hp = need_h;
+    p.Wp = g.W + 2 * g.pad;
+    const int need_w = (g.OW - 1) * g.sw + 8;
+    if (p.Wp < need_w) p.Wp = need_w;
+    p.xp_floats = ((int64_t)g.N * p.Hp * p.Wp * 4 + 255) / 256 * 256;
+    p.wq_floats = ((int64_t)g.OC * g.KH * 32 + 255) / 256 * 256;
+    return p;
+}
+// the overlapping-window view of xp: {32 floats, OW, OH, KH, N}
+static bool stem_map_x(CUtensorMap* m, const float* xp, const ConvGeom& g, const StemPlan& pl, int box_w, int box_h,
+                       CUtensorMapSwizzle swz) {
+    cuuint64_t dims[5] = {32, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.KH, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {(cuuint64_t)g.sw * 16, (cuuint64_t)g.sh * pl.Wp * 16, (cuuint64_t)pl.Wp * 16,
+                             (cuuint64_t)pl.Hp * pl.Wp * 16};
+    cuuint32_t box[5] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+    return make_map_tiled(m, xp, 5, dims, strides, box, swz);
+}
+
+static int stem_prepare(const float* x, const ConvGeom& g, const StemPlan& pl, float* xp, cudaStream_t s) {
+    const int64_t total = (int64_t)g.N * pl.Hp * pl.Wp;
+    stem_pad_c4_k<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(x, reinterpret_cast<float4*>(xp), g.N, g.H, g.W, g.C,
+                                                                  pl.Hp, pl.Wp, g.pad);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+static int stem_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
+                    int64_t ws_floats, cudaStream_t s) {
+    const StemPlan pl = stem_plan(g);
+    if (!ws || ws_floats < pl.xp_floats + pl.wq_floats) return XSB_ERR_UNSUPPORTED;
+    if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
+    float* xp = ws;
+    float* wq = ws + pl.xp_floats;
+    CUtensorMap ta, tb;
+    if (!stem_map_x(&ta, xp, g, pl, STEM_TW, STEM_TH, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_map_2d(&tb, wq, (uint64_t)g.OC, (uint64_t)g.KH * 32, 64))
+        return XSB_ERR_UNSUPPORTED;   // driver rejected the overlapping-stride map: FFMA kernel takes the call
+    int rc = stem_prepare(x, g, pl, xp, s);
+    if (rc != XSB_OK) return rc;
+    stem_pack_filter_k<<<(g.OC * g.KH * 32 + 255) / 256, 256, 0, s>>>(w, wq, g.OC, g.KH, g.KW, g.C);
+    XSB_LAUNCH_CHECK();
+    StemParams p{y, bias, g.N, g.OH, g.OW, g.OC, g.KH, g.KW, g.C, (g.OW + STEM_TW - 1) / STEM_TW,
+                 (g.OH + STEM_TH - 1) / STEM_TH, 0, 0};
+    constexpr int STAGES = 4, BN = 64;
+    constexpr int smem = STAGES * (BM * A_ROW_BYTES + BN * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        XSB_CUDA(cudaFuncSetAttribute(stem_fprop_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(g.N * p.tiles_w * p.tiles_h, g.OC / BN);
+    stem_fprop_tc_k<BN, STAGES><<<grid, kThreads, smem, s>>>(ta, tb, p);
+    XSB_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return XSB_OK;
+}
+
+static int stem_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
+                      int64_t ws_floats, cudaStream_t s) {
+    const StemPlan pl = stem_plan(g);
+    if (!ws || ws_floats < pl.xp_floats) return XSB_ERR_UNSUPPORTED;
+    if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
+    float* xp = ws;
+    CUtensorMap tx, tdy;
+    cuuint64_t ddims[4] = {(cuuint64_t)g.OC, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+    cuuint64_t dstr[3] = {(cuuint64_t)g.OC * 4, (cuuint64_t)g.OW * g.OC * 4, (cuuint64_t)g.OH * g.OW * g.OC * 4};
+    cuuint32_t dbox[4] = {32, STEM_TW, STEM_WTH, 1};
+    if (!stem_map_x(&tx, xp, g, pl, STEM_TW, STEM_WTH, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map_tiled(&tdy, dy, 4, ddims, dstr, dbox, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return XSB_ERR_UNSUPPORTED;
+    int rc = stem_prepare(x, g, pl, xp, s);
+    if (rc != XSB_OK) return rc;
+    constexpr int STAGES = 4, BN = 64;
+    const int tiles_w = (g.OW + STEM_TW - 1) / STEM_TW, tiles_h = (g.OH + STEM_WTH - 1) / STEM_WTH;
+    const int total_kb = g.N * tiles_w * tiles_h;
+    const int m_tiles = (g.KH + 3) / 4, n_tiles = g.OC / BN;
+    int splits = (2 * xsb_sm_count_cached() + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+    if (splits > total_kb / 4) splits = total_kb / 4;
+    if (splits < 1) splits = 1;
+    const int kb_per = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kb_per - 1) / kb_per;
+    const int use_atomics = (splits > 1 || accumulate) ? 1 : 0;
+    if (use_atomics && !accumulate)
+        XSB_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.OC * g.KH * g.KW * g.C * sizeof(float), s));
+    StemParams p{dw, nullptr, g.N, g.OH, g.OW, g.OC, g.KH, g.KW, g.C, tiles_w, tiles_h, kb_per, use_atomics};
+    constexpr int smem = STAGES * ((4 + BN / 32) * STEM_TW * STEM_WTH * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        XSB_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(m_tiles, n_tiles, splits);
+    stem_wgrad_tc_k<BN, STAGES><<<grid, kThreads, smem, s>>>(tx, tdy, p);
+    XSB_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return XSB_OK;
+}
+
 }  // namespace tc
+
 
 using namespace tc;
 
@@ -549,7 +947,7 @@ int xsb_tc_gemm(const float*, const float*, float*, const float*, int, int, int,
 
 int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
                     int64_t ws_floats, cudaStream_t s) {
-    (void)ws; (void)ws_floats;
+    if (stem_ok(g) && aligned16(x) && aligned16(w) && aligned16(y)) return stem_fwd(x, w, bias, y, g, ws, ws_floats, s);
     if (!fprop_ok(g.C, g.OC, x, w, y) || g.KW > 255 || g.KH > 255) return XSB_ERR_UNSUPPORTED;
     return fprop_dispatch(x, w, bias, y, g.N, g.H, g.W, g.C, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.OH, g.OW, 0, s);
 }
@@ -590,7 +988,7 @@ int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom
 
 int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
                       int64_t ws_floats, cudaStream_t s) {
-    (void)ws; (void)ws_floats;
+    if (stem_ok(g) && aligned16(dy) && aligned16(x)) return stem_wgrad(dy, x, dw, g, accumulate, ws, ws_floats, s);
     if (g.C % 32 != 0 || g.OC % 64 != 0 || !aligned16(dy) || !aligned16(x) || !aligned16(dw)) return XSB_ERR_UNSUPPORTED;
     if (!load_driver_entry_points()) {
         xsb_set_error("cuTensorMapEncode* entry points unavailable");
