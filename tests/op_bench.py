@@ -1,0 +1,156 @@
+"""Op-level micro-benchmark through the C ABI (BASELINE.json configs[2]: conv2d / max_pool2d / BN / ReLU sweep).
+
+    python tests/op_bench.py [--ops conv,bn,...] [--shapes r224|r56] [--math tf32|fp32] [--iters 20] [--json out.json]
+
+Each op is timed with CUDA events over `iters` back-to-back launches after 3 warm-ups, on tensors larger than the
+126 MB L2 where the layer allows it (else noted "L2-resident"), and reported as algorithmic TFLOP/s or GB/s
+(utils/opcost.py) and as a fraction of the measured peaks in MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.dirname(HERE), HERE]
+
+import torch  # noqa: E402
+
+import xshinnosuke_b200 as xs  # noqa: E402
+from xshinnosuke_b200._lib import lib  # noqa: E402
+from xshinnosuke_b200.core.device import rt  # noqa: E402
+from xshinnosuke_b200.utils import opcost  # noqa: E402
+
+# (name, C, H, OC, k, s, p) of tests/resnet ResNet-18 at 224x224 / 56x56 input
+LAYERS = {
+    "r224": [("stem", 3, 224, 64, 7, 2, 3), ("layer1", 64, 56, 64, 3, 1, 1), ("layer2.0", 64, 56, 128, 3, 2, 1),
+             ("layer2", 128, 28, 128, 3, 1, 1), ("layer2.sc", 64, 56, 128, 1, 2, 0), ("layer3", 256, 14, 256, 3, 1, 1),
+             ("layer4", 512, 7, 512, 3, 1, 1)],
+    "r56": [("stem", 3, 56, 64, 7, 2, 3), ("layer1", 64, 14, 64, 3, 1, 1), ("layer2", 128, 7, 128, 3, 1, 1),
+            ("layer3", 256, 4, 256, 3, 1, 1), ("layer4", 512, 2, 512, 3, 1, 1)],
+}
+
+
+def dev(*shape, zero=False):
+    t = torch.zeros(*shape, device=rt.device) if zero else torch.randn(*shape, device=rt.device)
+    return t
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ops", default="conv_fwd,conv_dgrad,conv_wgrad,bn_fwd,bn_bwd,relu_fwd,relu_bwd,add,maxpool_fwd,"
+                                     "maxpool_bwd,colsum,sgd,adam")
+    ap.add_argument("--shapes", default="r224")
+    ap.add_argument("--math", default="tf32")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--layers", default="")
+    ap.add_argument("--json", default="")
+    a = ap.parse_args()
+    rt.ensure()
+    xs.set_math_mode(a.math)
+    peaks = json.load(open(os.path.join(os.path.dirname(HERE), "MEASURED_PEAKS.json"))) \
+        if os.path.exists(os.path.join(os.path.dirname(HERE), "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    N = a.batch or (128 if a.shapes == "r224" else 32)
+    ops = a.ops.split(",")
+    st = rt.stream()
+    ws, wsn, wss = rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.ws_small.data_ptr()
+    mode = rt.math_mode
+    rows = []
+
+    def report(op, layer, name, args, sec, note=""):
+        kind, amount = opcost.cost(name, args)
+        if kind == "flop":
+            ach, unit, peak = amount / sec / 1e12, "TFLOP/s", peaks["bf16_tflops"] / (2.0 if a.math == "tf32" else 1.0)
+            pk = "tf32 peak = measured bf16 burst / 2" if a.math == "tf32" else "measured bf16 burst"
+        else:
+            ach, unit, peak, pk = amount / sec / 1e9, "GB/s", peaks["hbm_gbs"], "measured HBM copy"
+        rows.append(dict(op=op, layer=layer, us=sec * 1e6, achieved=ach, unit=unit, frac=ach / peak, peak=peak,
+                         peak_kind=pk, note=note))
+        print(f"{op:12s} {layer:10s} {sec * 1e6:9.1f} us  {ach:9.1f} {unit:8s} {100 * ach / peak:5.1f}% of {pk} {note}", flush=True)
+
+    sel = [l for l in LAYERS[a.shapes] if not a.layers or l[0] in a.layers.split(",")]
+    for (lname, C, H, OC, k, s, p) in sel:
+        OH = (H - k + 2 * p) // s + 1
+        x, w, b = dev(N, H, H, C), dev(OC, k, k, C) * 0.1, dev(OC)
+        y, dy = dev(N, OH, OH, OC), dev(N, OH, OH, OC)
+        dx, dw = dev(N, H, H, C), dev(OC, k, k, C)
+        g = (N, H, H, C, OC, k, k, s, s, p)
+        if "conv_fwd" in ops:
+            args = (x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr()) + g + (mode, ws, wsn, st)
+            report("conv_fwd", lname, "xsb_conv2d_fwd", args, timed(lambda: lib.xsb_conv2d_fwd(*args), a.iters))
+        if "conv_dgrad" in ops and C >= 32:
+            args = (dy.data_ptr(), w.data_ptr(), dx.data_ptr()) + g + (0, mode, ws, wsn, st)
+            report("conv_dgrad", lname, "xsb_conv2d_dgrad", args, timed(lambda: lib.xsb_conv2d_dgrad(*args), a.iters))
+        if "conv_wgrad" in ops:
+            args = (dy.data_ptr(), x.data_ptr(), dw.data_ptr()) + g + (0, mode, ws, wsn, st)
+            report("conv_wgrad", lname, "xsb_conv2d_wgrad", args, timed(lambda: lib.xsb_conv2d_wgrad(*args), a.iters))
+        # bandwidth ops on the conv OUTPUT tensor [N,OH,OH,OC]
+        R, n = N * OH * OH, N * OH * OH * OC
+        note = "" if n * 4 > 126e6 else "(L2-resident)"
+        gam, bet, rm, rv, sm, si = dev(OC), dev(OC), dev(OC, zero=True), dev(OC) ** 2 + 1, dev(OC), dev(OC)
+        if "bn_fwd" in ops:
+            args = (y.data_ptr(), gam.data_ptr(), bet.data_ptr(), rm.data_ptr(), rv.data_ptr(), dy.data_ptr(), sm.data_ptr(),
+                    si.data_ptr(), R, OC, 1e-6, 0.99, wss, st)
+            report("bn_fwd", lname, "xsb_bn_train_fwd", args, timed(lambda: lib.xsb_bn_train_fwd(*args), a.iters), note)
+        if "bn_bwd" in ops:
+            dxo, dg, db = dev(N, OH, OH, OC), dev(OC), dev(OC)
+            args = (dy.data_ptr(), y.data_ptr(), gam.data_ptr(), sm.data_ptr(), si.data_ptr(), dxo.data_ptr(), dg.data_ptr(),
+                    db.data_ptr(), R, OC, 0, 0, 0, wss, st)
+            report("bn_bwd", lname, "xsb_bn_bwd", args, timed(lambda: lib.xsb_bn_bwd(*args), a.iters), note)
+        if "colsum" in ops:
+            args = (dy.data_ptr(), b.data_ptr(), R, OC, 0, wss, st)
+            report("colsum", lname, "xsb_colsum", args, timed(lambda: lib.xsb_colsum(*args), a.iters), note)
+        mask = torch.zeros((n + 7) // 8, dtype=torch.uint8, device=rt.device)
+        if "relu_fwd" in ops:
+            args = (y.data_ptr(), y.data_ptr(), mask.data_ptr(), n, st)
+            report("relu_fwd", lname, "xsb_relu_fwd", args, timed(lambda: lib.xsb_relu_fwd(*args), a.iters), note)
+        if "relu_bwd" in ops:
+            args = (dy.data_ptr(), mask.data_ptr(), dy.data_ptr(), n, 0, st)
+            report("relu_bwd", lname, "xsb_relu_bwd_mask", args, timed(lambda: lib.xsb_relu_bwd_mask(*args), a.iters), note)
+        if "add" in ops:
+            args = (y.data_ptr(), dy.data_ptr(), y.data_ptr(), n, st)
+            report("add", lname, "xsb_add", args, timed(lambda: lib.xsb_add(*args), a.iters), note)
+        if lname == "stem" and ("maxpool_fwd" in ops or "maxpool_bwd" in ops):
+            PH = (OH + 2 - 3) // 2 + 1
+            py, am = dev(N, PH, PH, OC), torch.zeros(N * PH * PH * OC, dtype=torch.uint8, device=rt.device)
+            yr = torch.relu(y)
+            args = (yr.data_ptr(), py.data_ptr(), am.data_ptr(), N, OH, OH, OC, 3, 2, 2, 1, st)
+            if "maxpool_fwd" in ops:
+                report("maxpool_fwd", lname, "xsb_maxpool2d_fwd", args, timed(lambda: lib.xsb_maxpool2d_fwd(*args), a.iters))
+            lib.xsb_maxpool2d_fwd(*args)
+            args2 = (py.data_ptr(), am.data_ptr(), dy.data_ptr(), N, OH, OH, OC, 3, 2, 2, 1, 0, st)
+            if "maxpool_bwd" in ops:
+                report("maxpool_bwd", lname, "xsb_maxpool2d_bwd", args2, timed(lambda: lib.xsb_maxpool2d_bwd(*args2), a.iters))
+        del x, w, y, dy, dx, dw
+        torch.cuda.empty_cache()
+    P = 11232612 // 64 * 64 + 64 * 82
+    fp, fg, fv, fm = dev(P), dev(P), dev(P, zero=True), dev(P, zero=True)
+    stp = torch.ones(1, dtype=torch.int32, device=rt.device)
+    if "sgd" in ops:
+        args = (fp.data_ptr(), fg.data_ptr(), P, 0.1, 1.0, st)
+        report("sgd", "flat", "xsb_sgd_step", args, timed(lambda: lib.xsb_sgd_step(*args), a.iters), "(90 MB: L2-resident)")
+    if "adam" in ops:
+        args = (fp.data_ptr(), fg.data_ptr(), fv.data_ptr(), fm.data_ptr(), P, 1e-3, 0.9, 0.999, 1e-8, 1.0, stp.data_ptr(), st)
+        report("adam", "flat", "xsb_adam_step", args, timed(lambda: lib.xsb_adam_step(*args), a.iters))
+    if a.json:
+        json.dump(dict(shapes=a.shapes, batch=N, math=a.math, iters=a.iters, rows=rows), open(a.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,7 +20,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kRowUnroll = 8;
-constexpr int kMaxRowBlocks = 2 * 148;
+constexpr int kMaxRowBlocks = 4 * 148;   // total CTAs (row blocks x column chunks): 4 per SM
+constexpr int kMaxLX = 32;
+constexpr int kRowsPerThread = 32;
+constexpr int kMergeBatch = 8;           // partials fetched per round trip in the last-block merge
 constexpr int kCounterSlots = 64;  // ws[0..63]: one "blocks done" ticket counter per column chunk
 
 struct Geom {
@@ -32,15 +35,20 @@ struct Geom {
     int rows_per_block;
 };
 
-static Geom make_geom(int64_t R, int C, bool vec4) {
+static Geom make_geom(int64_t R, int C, bool vec4, int max_blocks = kMaxRowBlocks) {
     Geom g;
     g.V = vec4 ? 4 : 1;
     g.CV = C / g.V;
-    g.LX = g.CV < kThreads ? g.CV : kThreads;
+    // <= 32 vector columns per block (a 512-byte row segment keeps every warp on full 128-byte lines) so that
+    // LY >= 8 row lanes share the final merge of the per-block partials; wide tensors spread over grid.y chunks
+    g.LX = g.CV < kMaxLX ? g.CV : kMaxLX;
     g.LY = kThreads / g.LX;
     g.chunks = (g.CV + g.LX - 1) / g.LX;
-    int64_t nb = ceil_div64(R, (int64_t)g.LY * kRowUnroll);
-    if (nb > kMaxRowBlocks) nb = kMaxRowBlocks;
+    // >= kRowsPerThread rows per thread: below that the serial merge of the per-block partials costs more than
+    // the extra CTAs win; above it up to max_blocks CTAs keep enough loads in flight for the big tensors
+    int64_t nb = R / ((int64_t)g.LY * kRowsPerThread);
+    const int64_t cap = max_blocks / g.chunks > 8 ? max_blocks / g.chunks : 8;
+    if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     g.rows_per_block = (int)ceil_div64(R, nb);
     g.nb = (int)ceil_div64(R, g.rows_per_block);
@@ -131,16 +139,23 @@ bn_stats_k(const float* __restrict__ x, int64_t R, int C, int LX, int LY, int ro
                 }
             cnt += (float)kRowUnroll;
         }
-        for (; r < r_end; r += LY) {
-            float v[V];
-            load_vec<V>(base + r * C, v);
+        {   // remainder (< kRowUnroll rows): issue every load before the first use
+            float v[kRowUnroll][V];
+            int m = 0;
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float d = v[i] - K[i];
-                s1[i] += d;
-                s2[i] = fmaf(d, d, s2[i]);
-            }
-            cnt += 1.f;
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (r + (int64_t)u * LY < r_end) { load_vec<V>(base + (r + (int64_t)u * LY) * C, v[u]); m = u + 1; }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+                if (u < m) {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const float d = v[u][i] - K[i];
+                        s1[i] += d;
+                        s2[i] = fmaf(d, d, s2[i]);
+                    }
+                    cnt += 1.f;
+                }
         }
     }
     // per-thread (n, mean, M2)
@@ -189,16 +204,30 @@ bn_stats_k(const float* __restrict__ x, int64_t R, int C, int LX, int LY, int ro
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = Moments{0.f, 0.f, 0.f};
         if (active) {
-            for (int b = ty; b < nb; b += LY) {
-                const int64_t rb = (int64_t)b * rows_per_block;
-                int64_t re = rb + rows_per_block;
-                if (re > R) re = R;
-                const float nrows = (float)(re - rb);
+            for (int b0 = ty; b0 < nb; b0 += LY * kMergeBatch) {
+                float pm[kMergeBatch][V], p2[kMergeBatch][V];
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    Moments pb{nrows, __ldcg(&p_mean[(int64_t)b * C + cv * V + i]),
-                               __ldcg(&p_m2[(int64_t)b * C + cv * V + i])};
-                    acc[i] = merge(acc[i], pb);
+                for (int u = 0; u < kMergeBatch; ++u) {      // independent loads first: one L2 round trip per batch
+                    const int b = b0 + u * LY;
+                    if (b < nb) {
+#pragma unroll
+                        for (int i = 0; i < V; ++i) {
+                            pm[u][i] = __ldcg(&p_mean[(int64_t)b * C + cv * V + i]);
+                            p2[u][i] = __ldcg(&p_m2[(int64_t)b * C + cv * V + i]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kMergeBatch; ++u) {
+                    const int b = b0 + u * LY;
+                    if (b < nb) {
+                        const int64_t rb = (int64_t)b * rows_per_block;
+                        int64_t re = rb + rows_per_block;
+                        if (re > R) re = R;
+                        const float nrows = (float)(re - rb);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[i] = merge(acc[i], Moments{nrows, pm[u][i], p2[u][i]});
+                    }
                 }
             }
         }
@@ -370,12 +399,24 @@ col_sums_k(const float* __restrict__ dy, const float* __restrict__ x, const floa
 #pragma unroll
         for (int i = 0; i < V; ++i) { da[i] = 0.0; db[i] = 0.0; }
         if (active) {
-            for (int b = ty; b < nb; b += LY) {
+            for (int b0 = ty; b0 < nb; b0 += LY * kMergeBatch) {
+                float pa[kMergeBatch][V], pb[kMergeBatch][V];
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    da[i] += (double)__ldcg(&p_a[(int64_t)b * C + cv * V + i]);
-                    if (kXhat) db[i] += (double)__ldcg(&p_b[(int64_t)b * C + cv * V + i]);
+                for (int u = 0; u < kMergeBatch; ++u) {
+                    const int b = b0 + u * LY;
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        pa[u][i] = b < nb ? __ldcg(&p_a[(int64_t)b * C + cv * V + i]) : 0.f;
+                        pb[u][i] = (kXhat && b < nb) ? __ldcg(&p_b[(int64_t)b * C + cv * V + i]) : 0.f;
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < kMergeBatch; ++u)
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        da[i] += (double)pa[u][i];
+                        if (kXhat) db[i] += (double)pb[u][i];
+                    }
             }
         }
         __syncthreads();
@@ -518,7 +559,7 @@ int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float*
     XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
     cudaStream_t s = xsb_stream(stream);
     const bool v4 = use_vec4(C, dy, x, dx);
-    const Geom g = make_geom(R, C, v4);
+    const Geom g = make_geom(R, C, v4, 2 * 148);   // two streamed arrays per thread: fewer, fatter CTAs measured faster
     XSB_CHECK_ARG(g.chunks <= kCounterSlots, "bn: C=%d too large", C);
     float* coef = ws + kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks;
     dim3 grid(g.nb, g.chunks);
