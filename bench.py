@@ -218,6 +218,19 @@ def run_ours(args, wl):
             ms = float(t.item())
         return ms
 
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    eager_step = step_resident
+    graphed = None
+    if use_graph:
+        # the whole step replayed as one CUDA graph (same kernels, no Python between launches)
+        graphed = xs.GraphedStep(eager_step, warmup=max(args.warmup, 3))
+        step_resident = graphed
+
+        def step_e2e():  # noqa: F811 -- host batch into the captured input buffers, replay, read the loss back
+            x_dev.eval = x_pin.numpy()
+            y_dev.arr.buf.copy_(y_pin, non_blocking=True)
+            return graphed().item()
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
@@ -235,7 +248,7 @@ def run_ours(args, wl):
     prof = {}
     if rank != 0 and dp is not None:
         for _ in range(3):          # the profiled steps contain collectives: every rank must take part
-            step_resident()
+            eager_step()
         torch.cuda.synchronize()
     if rank == 0:
         lib.load()
@@ -255,7 +268,7 @@ def run_ours(args, wl):
                 return r
             setattr(lib, n, wrapped)
         for _ in range(3):
-            step_resident()
+            eager_step()          # per-call events need the eager path (a graph replay is one opaque launch)
         torch.cuda.synchronize()
         for n, fn in originals.items():
             setattr(lib, n, fn)
@@ -299,7 +312,7 @@ def run_ours(args, wl):
                dtype=args.math, data="synthetic",
                config=dict(workload=wl["name"], global_batch=B * world, per_gpu_batch=B, image=f"3x{hw}x{hw}",
                            optimizer=wl["optimizer"], parallelism=f"dp{world}", params=nparams,
-                           math_mode=args.math,
+                           math_mode=args.math, cuda_graph=bool(use_graph),
                            l2="no flush: per-step working set (activations + 2x45 MB params/grads) exceeds the 126 MB L2",
                            vs_baseline_ref="README.md:37-38 XS dynamic graph on CuPy, 265 img/s, unspecified GPU"),
                clocks=clocks, gpu_launches=launches,
@@ -321,6 +334,8 @@ def main():
     ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--bucket-mb", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step as one CUDA graph (auto: single-GPU runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -225,3 +225,55 @@ def test_resnet18_tf32_mode(golden):
         assert losses[2] < losses[0]
     finally:
         xs.set_math_mode("fp32")
+
+
+@pytest.mark.parametrize("optimizer", ["sgd", "adam"])
+def test_cuda_graph_step_matches_eager(optimizer):
+    """a step replayed from a CUDA graph gives the same parameters and losses as the eager loop."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.layers import (AvgPooling2D, BatchNormalization, Conv2D, Dense, Flatten, MaxPooling2D, ReLU)
+
+    rs = np.random.RandomState(0)
+    xb = [rs.rand(8, 3, 20, 20).astype(np.float32) for _ in range(2)]
+    yb = [rs.randint(0, 10, (8,)) for _ in range(2)]
+
+    def build():
+        np.random.seed(3)
+        net = nn.Sequential(Conv2D(8, 7, stride=2, padding=3), BatchNormalization(), ReLU(True), MaxPooling2D(3, 2, 1),
+                            Conv2D(64, 3, padding=1), BatchNormalization(), ReLU(True), AvgPooling2D(2), Flatten(), Dense(10))
+        opt = xs.optim.SGD(net.parameters(), lr=0.05) if optimizer == "sgd" else xs.optim.Adam(net.parameters(), lr=0.01)
+        return net, opt
+
+    crit = nn.CrossEntropyLoss()
+    # eager: 2 warm-up steps on batch 0, then batches 0,1,0
+    net_e, opt_e = build()
+    losses_e = []
+    for i in (0, 0, 0, 1, 0):
+        opt_e.zero_grad()
+        loss = crit(net_e(xs.tensor(xb[i])), xs.tensor(yb[i]))
+        losses_e.append(loss.item())
+        loss.backward()
+        opt_e.step()
+    # graphed: same schedule, the last three steps are replays fed through the static input tensors
+    net_g, opt_g = build()
+    x_in, y_in = xs.tensor(xb[0]), xs.tensor(yb[0])
+
+    def step():
+        opt_g.zero_grad()
+        loss = crit(net_g(x_in), y_in)
+        loss.backward()
+        opt_g.step()
+        return loss
+
+    g = xs.GraphedStep(step, warmup=2)
+    losses_g = []
+    for i in (0, 1, 0):
+        x_in.eval = xb[i]
+        y_in.eval = yb[i]
+        losses_g.append(g().item())
+    assert g.launches_per_replay > 20
+    np.testing.assert_allclose(losses_g, losses_e[2:], rtol=1e-5)
+    for pe, pg in zip(net_e.parameters(), net_g.parameters()):
+        assert float(np.max(np.abs(pe.eval - pg.eval))) <= 1e-5 * max(float(np.max(np.abs(pe.eval))), 1e-2)

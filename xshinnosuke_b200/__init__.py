@@ -12,6 +12,7 @@ from .core.device import rt as runtime, set_math_mode, get_math_mode  # noqa: F4
 from .nn.initializers import manual_seed_all, randn, tensor, zeros, ones, rand, randint  # noqa: F401
 from .utils.toolkit import gradient_check, SummaryProfile  # noqa: F401
 from .utils.common import no_grad  # noqa: F401
+from .utils.graph import GraphedStep  # noqa: F401
 
 float32 = _np.dtype(_np.float32)
 float64 = _np.dtype(_np.float64)

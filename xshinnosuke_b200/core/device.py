@@ -157,6 +157,8 @@ class DevArray:
             dtype, host = "int64", np.ascontiguousarray(a, dtype=np.int64)
         else:
             dtype, host = "float32", np.ascontiguousarray(a, dtype=np.float32)
+        if not host.flags.writeable:
+            host = host.copy()   # torch.from_numpy refuses read-only arrays (e.g. views of an .npz)
         shape = host.shape if host.ndim else (1,)  # 0-d scalars behave as shape (1,) (xs/core/base.py:82-84)
         t = torch()
         dev = t.from_numpy(host.reshape(-1)).to(rt.device)

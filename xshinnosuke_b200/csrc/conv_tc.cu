@@ -19,6 +19,7 @@
 // XSB_ERR_UNSUPPORTED from the xsb_tc_* probes and the caller runs the fp32 FFMA kernel instead.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv_geom.cuh"
@@ -170,8 +171,8 @@ struct FpropParams {
     int accumulate;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int STAGES, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
 conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int A_BYTES = BM * A_ROW_BYTES;
@@ -758,16 +759,27 @@ static bool make_map_im2col(CUtensorMap* m, const float* base, int N, int H, int
 
 static uint64_t g_tc_launches = 0, g_ffma_fallbacks = 0;
 
-template <int BN, int STAGES>
+// XSB_TC_OCC=1|2 (env, read once): CTAs per SM for the fprop kernel. 2 (default) halves the smem ring of each CTA
+// so that one CTA's epilogue overlaps the other's mainloop.
+static int tc_occupancy() {
+    static int occ = 0;
+    if (occ == 0) {
+        const char* e = getenv("XSB_TC_OCC");
+        occ = (e && e[0] == '1') ? 1 : 2;
+    }
+    return occ;
+}
+
+template <int BN, int STAGES, int OCC>
 static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const FpropParams& p, int n_tiles, cudaStream_t s) {
     constexpr int smem = STAGES * (BM * A_ROW_BYTES + BN * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
-        XSB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        XSB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_k<BN, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid((p.M + BM - 1) / BM, n_tiles);
-    conv_fprop_tc_k<BN, STAGES><<<grid, kThreads, smem, s>>>(a, b, p);
+    conv_fprop_tc_k<BN, STAGES, OCC><<<grid, kThreads, smem, s>>>(a, b, p);
     XSB_LAUNCH_CHECK();
     ++g_tc_launches;
     return XSB_OK;
@@ -790,9 +802,16 @@ static int fprop_dispatch(const float* in, const float* flt, const float* bias, 
         return XSB_ERR_CUDA;
     }
     FpropParams p{out, bias, N * OH * OW, OCx, Cx, KH, KW, OH, OW, sh, sw, pad, accumulate};
-    if (BN == 256) return launch_fprop<256, 4>(ta, tb, p, OCx / 256, s);
-    if (BN == 128) return launch_fprop<128, 6>(ta, tb, p, OCx / 128, s);
-    return launch_fprop<64, 8>(ta, tb, p, OCx / 64, s);
+    if (tc_occupancy() == 1) {
+        if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, OCx / 256, s);
+        if (BN == 128) return launch_fprop<128, 6, 1>(ta, tb, p, OCx / 128, s);
+        return launch_fprop<64, 8, 1>(ta, tb, p, OCx / 64, s);
+    }
+    // measured on B200 (tests/op_bench.py, R224): 2 CTAs/SM is +45 % for BN=64 and +19 % for BN=128, but -25 % for
+    // BN=256 (only 2 stages fit) -> the widest tile keeps one CTA per SM with a 4-stage ring
+    if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, OCx / 256, s);
+    if (BN == 128) return launch_fprop<128, 3, 2>(ta, tb, p, OCx / 128, s);
+    return launch_fprop<64, 4, 2>(ta, tb, p, OCx / 64, s);
 }
 
 template <int BN, int BKP, int STAGES>
