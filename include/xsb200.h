@@ -82,6 +82,9 @@ int64_t xsb_bn_workspace_floats(int64_t R, int C);
 int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                      float* y, float* save_mean, float* save_invstd, int64_t R, int C, float eps, float momentum,
                      float* ws, void* stream);
+/* inference branch, xs/nn/functional.py:708-725 */
+int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const float* moving_mean,
+                    const float* moving_var, float* y, int64_t R, int C, float eps, float* ws, void* stream);
 int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                float* dx /* nullable */, float* dgamma /* nullable */, float* dbeta /* nullable */, int64_t R, int C,
                int acc_dx, int acc_dgamma, int acc_dbeta, float* ws, void* stream);
@@ -128,6 +131,10 @@ int xsb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale
 int xsb_adam_step(float* p, const float* g, float* v /* 1st moment */, float* m /* 2nd moment */, int64_t n, float lr,
                   float beta1, float beta2, float eps, float grad_scale, const int* step_dev, void* stream);
 int xsb_counter_inc(int* counter_dev, void* stream);
+/* Momentum (xs/optim/sgd.py:12-29), RMSprop (rmsprop.py:4-21), AdaGrad (adagrad.py:4-18), AdaDelta
+ * (adadelta.py:4-26) -- kind 0..3; s1/s2 = per-parameter state buffers (s2: AdaDelta's delta_x only). */
+int xsb_rule_step(int kind, float* p, const float* g, float* s1, float* s2, int64_t n, float lr, float rho, float eps,
+                  float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

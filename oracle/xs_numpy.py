@@ -16,7 +16,7 @@ __all__ = [
     "avg_pool2d_fwd", "avg_pool2d_bwd", "relu_fwd", "relu_bwd", "batch_norm_fwd",
     "batch_norm_bwd", "addmm_fwd", "addmm_bwd", "mm_bwd", "softmax", "cross_entropy_fwd",
     "cross_entropy_bwd", "mse_loss_fwd", "mse_loss_bwd", "sgd_step", "adam_step",
-    "conv_out_size", "pool_out_size", "rel_err",
+    "momentum_step", "rmsprop_step", "adagrad_step", "adadelta_step", "conv_out_size", "pool_out_size", "rel_err",
 ]
 
 
@@ -344,3 +344,43 @@ def adam_step(params, grads, state, lr=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-
         p -= lr * (vc / (np.sqrt(mc) + epsilon))
         state["v"][i] = v
         state["m"][i] = m
+
+
+def _state(state, key, params):
+    if key not in state:
+        state[key] = [np.zeros_like(p) for p in params]
+    return state[key]
+
+
+def momentum_step(params, grads, state, lr=0.01, rho=0.9):
+    """xs/optim/sgd.py:12-29: v = rho v + (1-rho) g ; p -= lr v."""
+    v = _state(state, "v", params)
+    for i, (p, g) in enumerate(zip(params, grads)):
+        v[i] = rho * v[i] + (1 - rho) * g
+        p -= lr * v[i]
+
+
+def rmsprop_step(params, grads, state, lr=0.001, rho=0.9, epsilon=1e-7):
+    """xs/optim/rmsprop.py:4-21: s = rho s + (1-rho) g^2 ; p -= lr g / sqrt(s + eps)."""
+    s = _state(state, "s", params)
+    for i, (p, g) in enumerate(zip(params, grads)):
+        s[i] = rho * s[i] + (1 - rho) * np.square(g)
+        p -= lr * g / np.sqrt(s[i] + epsilon)
+
+
+def adagrad_step(params, grads, state, lr=0.01, epsilon=1e-7):
+    """xs/optim/adagrad.py:4-18: s += g^2 ; p -= lr g / sqrt(s + eps)."""
+    s = _state(state, "s", params)
+    for i, (p, g) in enumerate(zip(params, grads)):
+        s[i] = s[i] + np.power(g, 2)
+        p -= lr * g / np.sqrt(s[i] + epsilon)
+
+
+def adadelta_step(params, grads, state, rho=0.95, epsilon=1e-7):
+    """xs/optim/adadelta.py:4-26 (lr is accepted by the reference but unused)."""
+    s, x = _state(state, "s", params), _state(state, "x", params)
+    for i, (p, g) in enumerate(zip(params, grads)):
+        s[i] = rho * s[i] + (1 - rho) * np.power(g, 2)
+        d = np.sqrt((x[i] + epsilon) / (s[i] + epsilon)) * g
+        p -= d
+        x[i] = rho * x[i] + (1 - rho) * np.power(d, 2)

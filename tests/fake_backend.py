@@ -235,6 +235,32 @@ class FakeLib:
     def _sgd_step(self, p, g, n, lr, gscale, s):
         f32(p, n)[...] = f32(p, n).astype(np.float64) - lr * gscale * f32(g, n).astype(np.float64)
 
+    def _rule_step(self, kind, p, g, s1, s2, n, lr, rho, eps, gscale, s):
+        P, G = [f32(p, n).astype(np.float64)], [f32(g, n).astype(np.float64) * gscale]
+        st = {"v": [f32(s1, n).astype(np.float64)], "s": [f32(s1, n).astype(np.float64)]}
+        if kind == 3:
+            st["x"] = [f32(s2, n).astype(np.float64)]
+        if kind == 0:
+            X.momentum_step(P, G, st, lr, rho)
+        elif kind == 1:
+            X.rmsprop_step(P, G, st, lr, rho, eps)
+        elif kind == 2:
+            X.adagrad_step(P, G, st, lr, eps)
+        else:
+            X.adadelta_step(P, G, st, rho, eps)
+        f32(p, n)[...] = P[0]
+        f32(s1, n)[...] = st["v"][0] if kind == 0 else st["s"][0]
+        if kind == 3:
+            f32(s2, n)[...] = st["x"][0]
+
+    def _bn_eval_fwd(self, x, gamma, beta, mm, mv, y, R, C, eps, ws, s):
+        xv = f32(x, R * C).reshape(R, C).astype(np.float64)
+        f32(y, R * C).reshape(R, C)[...] = (xv - f32(mm, C)) / np.sqrt(f32(mv, C).astype(np.float64) + eps) * f32(gamma, C) \
+            + f32(beta, C)
+
+    def _tc_stats(self, out):
+        pass
+
     def _counter_inc(self, c, s):
         i32(c, 1)[0] += 1
 

@@ -194,7 +194,14 @@ def gen_optim():
     shapes = [(5, 3, 3, 3), (1, 5), (7,), (20, 4)]
     p0 = [rs.randn(*s) for s in shapes]
     gs = [[rs.randn(*s) for s in shapes] for _ in range(4)]
-    for oname, ctor in [("sgd", lambda ps: xs.optim.SGD(ps, lr=0.1)), ("adam", lambda ps: xs.optim.Adam(ps, lr=0.01))]:
+    import xs.optim.sgd, xs.optim.rmsprop, xs.optim.adagrad, xs.optim.adadelta  # noqa: E401
+    for m in ("sgd", "rmsprop", "adagrad", "adadelta"):
+        sys.modules["xs.optim." + m].np = np      # same missing-import defect as adam.py
+    for oname, ctor in [("sgd", lambda ps: xs.optim.SGD(ps, lr=0.1)), ("adam", lambda ps: xs.optim.Adam(ps, lr=0.01)),
+                        ("momentum", lambda ps: xs.optim.Momentum(ps, lr=0.05)),
+                        ("rmsprop", lambda ps: xs.optim.RMSprop(ps, lr=0.01)),
+                        ("adagrad", lambda ps: xs.optim.AdaGrad(ps, lr=0.05)),
+                        ("adadelta", lambda ps: xs.optim.AdaDelta(ps))]:
         ps = [nn.Parameter(p.copy()) for p in p0]
         opt = ctor(ps)
         for step in range(4):

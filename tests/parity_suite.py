@@ -126,6 +126,19 @@ def check_bn(golden, tol):
         close(tb.grad.eval, c["dbeta"], tol, f"bn/{name}/dbeta")
 
 
+def check_bn_eval(tol):
+    """Inference branch (functional.py:708-725): normalise with the running statistics."""
+    rs = np.random.RandomState(11)
+    x = rs.randn(4, 8, 5, 5).astype(np.float32)
+    gm, bt = (rs.rand(8) + 0.5).astype(np.float32), rs.randn(8).astype(np.float32)
+    mm, mv = rs.randn(8).astype(np.float32), (rs.rand(8) + 0.5).astype(np.float32)
+    y = F.batch_norm(T(x), nn.Parameter(gm), nn.Parameter(bt), T(mm), T(mv), 1, False, 1e-5, 0.9)
+    ref = (x.astype(np.float64) - mm.reshape(1, -1, 1, 1)) / np.sqrt(mv.reshape(1, -1, 1, 1).astype(np.float64) + 1e-5) \
+        * gm.reshape(1, -1, 1, 1) + bt.reshape(1, -1, 1, 1)
+    close(y.eval, ref, tol, "bn eval")
+    assert y.grad_fn is None
+
+
 def check_dense_losses(golden, tol):
     for name in golden.names("addmm"):
         c = golden.case(f"addmm/{name}")
@@ -151,7 +164,11 @@ def check_dense_losses(golden, tol):
 def check_optimizers(golden, tol):
     init = golden.case("optim/init")
     n = len(init)
-    for name, ctor in (("sgd", lambda ps: xs.optim.SGD(ps, lr=0.1)), ("adam", lambda ps: xs.optim.Adam(ps, lr=0.01))):
+    for name, ctor in (("sgd", lambda ps: xs.optim.SGD(ps, lr=0.1)), ("adam", lambda ps: xs.optim.Adam(ps, lr=0.01)),
+                       ("momentum", lambda ps: xs.optim.Momentum(ps, lr=0.05)),
+                       ("rmsprop", lambda ps: xs.optim.RMSprop(ps, lr=0.01)),
+                       ("adagrad", lambda ps: xs.optim.AdaGrad(ps, lr=0.05)),
+                       ("adadelta", lambda ps: xs.optim.AdaDelta(ps))):
         ps = [nn.Parameter(init[f"p{i}"]) for i in range(n)]
         opt = ctor(ps)
         for step in range(4):

@@ -34,6 +34,7 @@ def test_relu_add(golden):
 
 def test_bn(golden):
     S.check_bn(golden, 1e-5)
+    S.check_bn_eval(1e-6)
 
 
 def test_dense_losses(golden):

@@ -102,7 +102,7 @@ def test_dense_and_losses(golden):
 def test_optimizers(golden):
     init = golden.case("optim/init")
     n = len(init)
-    for opt in ("sgd", "adam"):
+    for opt in ("sgd", "adam", "momentum", "rmsprop", "adagrad", "adadelta"):
         ps = [init[f"p{i}"].copy() for i in range(n)]
         state = {}
         for step in range(4):
@@ -110,8 +110,16 @@ def test_optimizers(golden):
             gs = [g[f"g{i}"] for i in range(n)]
             if opt == "sgd":
                 X.sgd_step(ps, gs, 0.1)
-            else:
+            elif opt == "adam":
                 X.adam_step(ps, gs, state, lr=0.01)
+            elif opt == "momentum":
+                X.momentum_step(ps, gs, state, lr=0.05)
+            elif opt == "rmsprop":
+                X.rmsprop_step(ps, gs, state, lr=0.01)
+            elif opt == "adagrad":
+                X.adagrad_step(ps, gs, state, lr=0.05)
+            else:
+                X.adadelta_step(ps, gs, state)
             want = golden.case(f"optim/{opt}/step{step}")
             for i in range(n):
                 close(ps[i], want[f"p{i}"])

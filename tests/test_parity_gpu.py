@@ -53,6 +53,7 @@ def test_relu_add(golden):
 def test_bn(golden):
     import parity_suite as S
     S.check_bn(golden, TOL)
+    S.check_bn_eval(TOL)
 
 
 def test_dense_losses(golden):

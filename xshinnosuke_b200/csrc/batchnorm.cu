@@ -509,6 +509,11 @@ bn_bwd_apply_k(const float* __restrict__ dy, const float* __restrict__ x, float*
     }
 }
 
+__global__ void invstd_k(const float* __restrict__ var, float* __restrict__ invstd, int C, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) invstd[c] = 1.0f / sqrtf(var[c] + eps);
+}
+
 inline bool use_vec4(int C, const void* a, const void* b = nullptr, const void* c = nullptr) {
     return (C % 4 == 0) && aligned16(a) && (!b || aligned16(b)) && (!c || aligned16(c));
 }
@@ -548,6 +553,27 @@ int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, floa
         bn_apply_k<4><<<blocks, kThreads, 0, s>>>(x, y, save_mean, save_invstd, gamma, beta, nvec, g.CV, cv_mask);
     else
         bn_apply_k<1><<<blocks, kThreads, 0, s>>>(x, y, save_mean, save_invstd, gamma, beta, nvec, g.CV, cv_mask);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// Inference branch (xs/nn/functional.py:708-725): y = gamma * (x - moving_mean) / sqrt(moving_var + eps) + beta.
+int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const float* moving_mean,
+                    const float* moving_var, float* y, int64_t R, int C, float eps, float* ws, void* stream) {
+    XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
+    cudaStream_t s = xsb_stream(stream);
+    float* invstd = ws + kCounterSlots;   // partial-sum area of the scratch buffer; free between launches
+    invstd_k<<<(C + 255) / 256, 256, 0, s>>>(moving_var, invstd, C, eps);
+    XSB_LAUNCH_CHECK();
+    const bool v4 = use_vec4(C, x, y);
+    const int V = v4 ? 4 : 1, CV = C / V;
+    const int64_t nvec = R * CV;
+    const int cv_mask = (CV & (CV - 1)) == 0 ? CV - 1 : -1;
+    const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
+    if (v4)
+        bn_apply_k<4><<<blocks, kThreads, 0, s>>>(x, y, moving_mean, invstd, gamma, beta, nvec, CV, cv_mask);
+    else
+        bn_apply_k<1><<<blocks, kThreads, 0, s>>>(x, y, moving_mean, invstd, gamma, beta, nvec, CV, cv_mask);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

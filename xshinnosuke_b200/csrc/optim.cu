@@ -84,6 +84,49 @@ __global__ void adam_scalar(float* p, const float* __restrict__ g, float* v, flo
 
 __global__ void counter_inc_k(int* c) { c[0] += 1; }
 
+// Momentum / RMSprop / AdaGrad / AdaDelta over the flat buffer (xs/optim/sgd.py:12-29, rmsprop.py:4-21,
+// adagrad.py:4-18, adadelta.py:4-26). s1, s2: per-parameter state (s2 only for AdaDelta).
+template <int KIND>
+__device__ __forceinline__ void rule1(float& p, float g, float& s1, float& s2, float lr, float rho, float eps) {
+    if (KIND == 0) {          // momentum: v = rho v + (1-rho) g ; p -= lr v
+        s1 = rho * s1 + (1.f - rho) * g;
+        p -= lr * s1;
+    } else if (KIND == 1) {   // rmsprop: s = rho s + (1-rho) g^2 ; p -= lr g / sqrt(s + eps)
+        s1 = rho * s1 + (1.f - rho) * g * g;
+        p -= lr * g / sqrtf(s1 + eps);
+    } else if (KIND == 2) {   // adagrad: s += g^2 ; p -= lr g / sqrt(s + eps)
+        s1 += g * g;
+        p -= lr * g / sqrtf(s1 + eps);
+    } else {                  // adadelta: s = rho s + (1-rho) g^2 ; d = sqrt((x+eps)/(s+eps)) g ; p -= d ; x = rho x + (1-rho) d^2
+        s1 = rho * s1 + (1.f - rho) * g * g;
+        const float d = sqrtf((s2 + eps) / (s1 + eps)) * g;
+        p -= d;
+        s2 = rho * s2 + (1.f - rho) * d * d;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+rule_vec(float4* p, const float4* __restrict__ g, float4* s1, float4* s2, int64_t n4, float lr, float rho, float eps,
+         float gscale) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * 2) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        if (i < n4) {
+            float4 pv = p[i], a = s1[i], b = KIND == 3 ? s2[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 gv = ldg_stream(g + i);
+            rule1<KIND>(pv.x, gv.x * gscale, a.x, b.x, lr, rho, eps);
+            rule1<KIND>(pv.y, gv.y * gscale, a.y, b.y, lr, rho, eps);
+            rule1<KIND>(pv.z, gv.z * gscale, a.z, b.z, lr, rho, eps);
+            rule1<KIND>(pv.w, gv.w * gscale, a.w, b.w, lr, rho, eps);
+            p[i] = pv;
+            s1[i] = a;
+            if (KIND == 3) s2[i] = b;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -113,6 +156,25 @@ int xsb_adam_step(float* p, const float* g, float* v, float* m, int64_t n, float
     else
         adam_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(p, g, v, m, n, lr, beta1, beta2, eps, grad_scale,
                                                                  step_dev);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// kind: 0 momentum, 1 rmsprop, 2 adagrad, 3 adadelta. n must be a multiple of 4 (the flat buffers are padded).
+int xsb_rule_step(int kind, float* p, const float* g, float* s1, float* s2, int64_t n, float lr, float rho, float eps,
+                  float grad_scale, void* stream) {
+    if (n <= 0) return XSB_OK;
+    XSB_CHECK_ARG(n % 4 == 0 && aligned16(p) && aligned16(g) && aligned16(s1) && (kind != 3 || aligned16(s2)),
+                  "rule_step: flat buffers must be 16-byte aligned with n %% 4 == 0");
+    XSB_CHECK_ARG(kind >= 0 && kind <= 3, "rule_step: unknown kind %d", kind);
+    cudaStream_t s = xsb_stream(stream);
+    const unsigned blocks = (unsigned)ceil_div64(n / 4, (int64_t)kThreads * 2);
+    float4 *P = (float4*)p, *S1 = (float4*)s1, *S2 = (float4*)s2;
+    const float4* G = (const float4*)g;
+    if (kind == 0) rule_vec<0><<<blocks, kThreads, 0, s>>>(P, G, S1, S2, n / 4, lr, rho, eps, grad_scale);
+    else if (kind == 1) rule_vec<1><<<blocks, kThreads, 0, s>>>(P, G, S1, S2, n / 4, lr, rho, eps, grad_scale);
+    else if (kind == 2) rule_vec<2><<<blocks, kThreads, 0, s>>>(P, G, S1, S2, n / 4, lr, rho, eps, grad_scale);
+    else rule_vec<3><<<blocks, kThreads, 0, s>>>(P, G, S1, S2, n / 4, lr, rho, eps, grad_scale);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

@@ -317,12 +317,20 @@ def batch_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, moving_mean: Tensor,
         pass
     else:
         raise NotImplementedError(f"batch_norm over axis {axis} of a {x.ndim}-D tensor is outside the hot path")
-    if not training:
-        raise NotImplementedError("batch_norm eval branch: SURVEY.md 8f rank 4 (next)")
     C = x.shape[1]
     R = x.size // C
     out, y = _out_arr(out, x.shape)
     y.cl = x.cl
+    if not training:
+        # inference branch (functional.py:708-725): normalise with the running statistics; no backward
+        lib.xsb_bn_eval_fwd(x.ptr, gamma.arr.ptr, beta.arr.ptr, moving_mean.arr.ptr, moving_variance.arr.ptr, y.wptr, R,
+                            C, float(epsilon), rt.ws_small.data_ptr(), rt.stream())
+        rt.launches += 2
+        out.requires_grad = False
+        if out.is_dynamic:
+            out.add_in_bounds(inputs, gamma, beta)
+            inputs.add_out_bounds(out)
+        return out
     save_mean, save_invstd = DevArray.empty((C,)), DevArray.empty((C,))
     lib.xsb_bn_train_fwd(x.ptr, gamma.arr.ptr, beta.arr.ptr, moving_mean.arr.ptr, moving_variance.arr.ptr, y.wptr,
                          save_mean.wptr, save_invstd.wptr, R, C, float(epsilon), float(momentum),

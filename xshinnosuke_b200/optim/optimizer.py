@@ -138,3 +138,59 @@ class Adam(Optimizer):
                               float(self.beta2), float(self.epsilon), float(self.grad_scale),
                               self._step_dev.data_ptr(), st)
         rt.launches += 2
+
+
+class _RuleOptimizer(Optimizer):
+    """Momentum / RMSprop / AdaGrad / AdaDelta as one fused launch of xsb_rule_step over the flat
+    buffers. All four raise NameError in the reference as shipped (missing `np` import, Q7); the formulas are
+    theirs (xs/optim/sgd.py:12-29, rmsprop.py:4-21, adagrad.py:4-18, adadelta.py:4-26)."""
+    kind = 0
+    n_state = 1
+    rho = 0.0
+    epsilon = 0.0
+
+    def step(self):
+        flat = self._ensure_flat()
+        self._materialize_grads()
+        if self.before_step is not None:
+            self.before_step(self)
+        if flat.total:
+            s2 = flat.extra[1].data_ptr() if self.n_state > 1 else None
+            lib.xsb_rule_step(self.kind, flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), flat.extra[0].data_ptr(), s2,
+                              flat.total, float(self.lr), float(self.rho), float(self.epsilon), float(self.grad_scale),
+                              rt.stream())
+            rt.launches += 1
+        self.iterations += 1
+
+
+class Momentum(_RuleOptimizer):
+    kind = 0
+
+    def __init__(self, parameters=None, lr=0.01, weight_decay=0.0, rho=0.9):
+        self.rho = rho
+        super().__init__(parameters=parameters, lr=lr, weight_decay=weight_decay)
+
+
+class RMSprop(_RuleOptimizer):
+    kind = 1
+
+    def __init__(self, parameters=None, lr=0.001, weight_decay=0.0, rho=0.9, epsilon=1e-7):
+        self.rho, self.epsilon = rho, epsilon
+        super().__init__(parameters=parameters, lr=lr, weight_decay=weight_decay)
+
+
+class AdaGrad(_RuleOptimizer):
+    kind = 2
+
+    def __init__(self, parameters=None, lr=0.01, weight_decay=0.0, epsilon=1e-7):
+        self.epsilon = epsilon
+        super().__init__(parameters=parameters, lr=lr, weight_decay=weight_decay)
+
+
+class AdaDelta(_RuleOptimizer):
+    kind = 3
+    n_state = 2
+
+    def __init__(self, parameters=None, lr=1.0, weight_decay=0.0, rho=0.95, epsilon=1e-7):
+        self.rho, self.epsilon = rho, epsilon
+        super().__init__(parameters=parameters, lr=lr, weight_decay=weight_decay)
