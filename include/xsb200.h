@@ -57,6 +57,8 @@ int xsb_relu_bwd_mask(const float* dy, const uint8_t* mask, float* dx, int64_t n
  *      xs/core/base.py:312-316 (zero_grad). ---- */
 int xsb_add(const float* a, const float* b, float* y, int64_t n, void* stream);
 int xsb_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream);
+/* residual add fused with the in-place ReLU that follows it: y = max(0, a+b), mask bit e = [(a+b)[e] < 0] */
+int xsb_add_relu(const float* a, const float* b, float* y, uint8_t* mask, int64_t n, void* stream);
 int xsb_fill(float* dst, float value, int64_t n, void* stream);
 
 /* ---- mean/sum over one axis and its backward. replaces xs/nn/functional.py mean/sum + grad_fn.py:122-137 ---- */
@@ -85,9 +87,17 @@ int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, floa
 /* inference branch, xs/nn/functional.py:708-725 */
 int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const float* moving_mean,
                     const float* moving_var, float* y, int64_t R, int C, float eps, float* ws, void* stream);
+/* the two halves of xsb_bn_train_fwd; `relu` fuses the BatchNormalization -> ReLU(inplace=True) pair of
+ * xs/layers/activators.py:37-50 (y = max(0, bn(x)), bit mask of bn(x) < 0 written in the same pass). */
+int xsb_bn_stats(const float* x, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                 int64_t R, int C, float eps, float momentum, float* ws, void* stream);
+int xsb_bn_apply(const float* x, float* y, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, int64_t R, int C, int relu, uint8_t* relu_mask /* nullable */, void* stream);
+/* relu_mask (nullable): dy is masked with the in-place ReLU's bit mask on the fly (xs/nn/grad_fn.py:147-151 fused). */
 int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                float* dx /* nullable */, float* dgamma /* nullable */, float* dbeta /* nullable */, int64_t R, int C,
-               int acc_dx, int acc_dgamma, int acc_dbeta, float* ws, void* stream);
+               int acc_dx, int acc_dgamma, int acc_dbeta, const uint8_t* relu_mask /* nullable */, float* ws,
+               void* stream);
 
 /* ---- out[c] (+)= sum_r x[r,c]: conv / Dense bias gradient. replaces xs/nn/grad_fn.py:196-197, 89-95 ---- */
 int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, float* ws, void* stream);

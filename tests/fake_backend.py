@@ -157,8 +157,34 @@ class FakeLib:
         if rv:
             f32(rv, C)[...] = mom * f32(rv, C).astype(np.float64) + (1 - mom) * var
 
-    def _bn_bwd(self, dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, ws, s):
+    def _bn_stats(self, x, rm, rv, smean, sinv, R, C, eps, mom, ws, s):
+        xv = f32(x, R * C).reshape(R, C).astype(np.float64)
+        mean, var = xv.mean(axis=0), xv.var(axis=0)
+        f32(smean, C)[...] = mean
+        f32(sinv, C)[...] = 1.0 / np.sqrt(var + eps)
+        if rm:
+            f32(rm, C)[...] = mom * f32(rm, C).astype(np.float64) + (1 - mom) * mean
+        if rv:
+            f32(rv, C)[...] = mom * f32(rv, C).astype(np.float64) + (1 - mom) * var
+
+    def _bn_apply(self, x, y, mean, invstd, gamma, beta, R, C, relu, mask, s):
+        xv = f32(x, R * C).reshape(R, C).astype(np.float64)
+        o = ((xv - f32(mean, C)) * f32(invstd, C) * f32(gamma, C) + f32(beta, C)).astype(np.float32)
+        if relu:
+            u8(mask, (R * C + 7) // 8)[...] = np.packbits(o.reshape(-1) < 0, bitorder="little")
+            o = np.maximum(o, 0)
+        f32(y, R * C).reshape(R, C)[...] = o
+
+    def _add_relu(self, a, b, y, mask, n, s):
+        t = f32(a, n) + f32(b, n)
+        u8(mask, (n + 7) // 8)[...] = np.packbits(t < 0, bitorder="little")
+        f32(y, n)[...] = np.maximum(t, 0)
+
+    def _bn_bwd(self, dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, rmask, ws, s):
         g = f32(dy, R * C).reshape(R, C).astype(np.float64)
+        if rmask:
+            m = np.unpackbits(u8(rmask, (R * C + 7) // 8), bitorder="little")[:R * C].astype(bool).reshape(R, C)
+            g = np.where(m, 0.0, g)
         xhat = (f32(x, R * C).reshape(R, C).astype(np.float64) - f32(smean, C)) * f32(sinv, C)
         sdy, sdyx = g.sum(axis=0), (g * xhat).sum(axis=0)
         if dgamma:

@@ -111,7 +111,7 @@ def main():
         if "bn_bwd" in ops:
             dxo, dg, db = dev(N, OH, OH, OC), dev(OC), dev(OC)
             args = (dy.data_ptr(), y.data_ptr(), gam.data_ptr(), sm.data_ptr(), si.data_ptr(), dxo.data_ptr(), dg.data_ptr(),
-                    db.data_ptr(), R, OC, 0, 0, 0, wss, st)
+                    db.data_ptr(), R, OC, 0, 0, 0, None, wss, st)
             report("bn_bwd", lname, "xsb_bn_bwd", args, timed(lambda: lib.xsb_bn_bwd(*args), a.iters), note)
         if "colsum" in ops:
             args = (dy.data_ptr(), b.data_ptr(), R, OC, 0, wss, st)

@@ -111,7 +111,8 @@ class DevArray:
         self.dtype = dtype
         self.cl = (len(self.shape) == 4 and dtype == "float32") if cl is None else cl
         if _share is None:
-            self._pz = [bool(pending_zero)]   # one cell shared by an array and all its prefix views
+            # one cell shared by an array and all its views: [pending_zero, pending_op]
+            self._pz = [bool(pending_zero), None]
             self._root = None
         else:
             self._pz = _share._pz
@@ -124,6 +125,23 @@ class DevArray:
     @pending_zero.setter
     def pending_zero(self, v):
         self._pz[0] = bool(v)
+
+    # pending_op: a deferred producer kernel (BN apply, residual add). It runs the first time the contents are
+    # needed -- unless the consumer is an in-place ReLU, which runs the fused producer+ReLU(+mask) kernel instead
+    # (layers/act.py). Called as op(mask_or_None).
+    @property
+    def pending_op(self):
+        return self._pz[1]
+
+    @pending_op.setter
+    def pending_op(self, op):
+        self._pz[1] = op
+
+    def flush(self):
+        op = self._pz[1]
+        if op is not None:
+            self._pz[1] = None
+            op(None)
 
     def _materialize_zero(self):
         root = self if self._root is None else self._root
@@ -184,6 +202,8 @@ class DevArray:
     @property
     def ptr(self):
         """Pointer for a kernel that will READ (or read-modify-write) the contents."""
+        if self._pz[1] is not None:
+            self.flush()
         if self.pending_zero:
             self._materialize_zero()
         return self.buf.data_ptr()
@@ -191,6 +211,7 @@ class DevArray:
     @property
     def wptr(self):
         """Pointer for a kernel that fully OVERWRITES the contents."""
+        self._pz[1] = None
         self.pending_zero = False
         return self.buf.data_ptr()
 
@@ -202,6 +223,8 @@ class DevArray:
         return 1
 
     def peek_ptr(self):
+        if self._pz[1] is not None:
+            self.flush()
         return self.buf.data_ptr()
 
     @property
@@ -214,6 +237,7 @@ class DevArray:
     # ---- host transfer
     def to_numpy(self):
         rt.ensure()
+        self.flush()
         if self.pending_zero:
             return np.zeros(self.shape, dtype=np.float32 if self.dtype == "float32" else np.int64)
         n = self.size
@@ -245,6 +269,7 @@ class DevArray:
         return DevArray(self.buf[: max(n * per, 1)], (n,) + self.shape[1:], self.dtype, self.cl, _share=self)
 
     def clone(self):
+        self.flush()
         if self.pending_zero:
             return DevArray.empty(self.shape, self.dtype, pending_zero=True)
         return DevArray(self.buf.clone(), self.shape, self.dtype, self.cl)

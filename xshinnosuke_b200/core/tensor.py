@@ -244,6 +244,7 @@ class Tensor(object):
             self._arr = DevArray.from_numpy(self._arr.to_numpy().astype(np.int64))
 
     def zero_(self):
+        self.arr.pending_op = None
         self.arr.buf.zero_()
         self.arr.pending_zero = False
 
@@ -251,6 +252,7 @@ class Tensor(object):
         self.fill_(1.0)
 
     def fill_(self, value):
+        self.arr.pending_op = None
         self.arr.buf.fill_(value)
         self.arr.pending_zero = False
 

@@ -76,6 +76,20 @@ __device__ __forceinline__ void load_param(const float* p, float (&v)[V]) {
     }
 }
 
+// ReLU mask (1 bit per element, bit e <=> pre-activation[e] < 0) applied to a gradient vector starting at element e0
+template <int V>
+__device__ __forceinline__ void apply_relu_mask(const uint8_t* __restrict__ mask, int64_t e0, float (&g)[V]) {
+    if (V == 4) {
+        const unsigned m = (__ldg(mask + (e0 >> 3)) >> (e0 & 4)) & 0xFu;
+        if (m & 1u) g[0] = 0.f;
+        if (m & 2u) g[1 % V] = 0.f;
+        if (m & 4u) g[2 % V] = 0.f;
+        if (m & 8u) g[3 % V] = 0.f;
+    } else {
+        if ((__ldg(mask + (e0 >> 3)) >> (e0 & 7)) & 1u) g[0] = 0.f;
+    }
+}
+
 struct Moments {  // count, mean, sum of squared deviations
     float n, mean, m2;
 };
@@ -271,11 +285,12 @@ bn_stats_k(const float* __restrict__ x, int64_t R, int C, int LX, int LY, int ro
 }
 
 // ------------------------------------------------------------------ forward apply: y = gamma*(x-mean)*invstd + beta
-template <int V>
+// kRelu: y = max(0, bn(x)) and bit e of `mask` = [bn(x)[e] < 0] (the in-place ReLU protocol's mask), fused
+template <int V, bool kRelu>
 __global__ void __launch_bounds__(kThreads)
 bn_apply_k(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
            const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-           int64_t nvec, int CV, int cv_mask) {
+           int64_t nvec, int CV, int cv_mask, uint8_t* __restrict__ mask) {
     constexpr int U = 4;
     const int64_t base = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
     float v[U][V];
@@ -287,15 +302,28 @@ bn_apply_k(const float* __restrict__ x, float* __restrict__ y, const float* __re
 #pragma unroll
     for (int j = 0; j < U; ++j) {
         const int64_t i = base + (int64_t)j * kThreads;
+        float o[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) o[q] = 0.f;
         if (i < nvec) {
             const int c = (cv_mask >= 0 ? (int)((unsigned)i & (unsigned)cv_mask) : (int)(i % CV)) * V;
-            float o[V], pm[V], pi[V], pg[V], pb[V];
+            float pm[V], pi[V], pg[V], pb[V];
             load_param<V>(mean + c, pm);
             load_param<V>(invstd + c, pi);
             load_param<V>(gamma + c, pg);
             load_param<V>(beta + c, pb);
 #pragma unroll
             for (int q = 0; q < V; ++q) o[q] = fmaf((v[j][q] - pm[q]) * pi[q], pg[q], pb[q]);
+        }
+        if (kRelu) {   // V == 4 only: two lanes share one mask byte (same layout as relu_fwd_vec)
+            unsigned nib = (o[0] < 0.f ? 1u : 0u) | (o[1 % V] < 0.f ? 2u : 0u) | (o[2 % V] < 0.f ? 4u : 0u) |
+                           (o[3 % V] < 0.f ? 8u : 0u);
+            const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
+            if ((threadIdx.x & 1) == 0 && i < nvec) mask[i >> 1] = (uint8_t)(nib | (hi << 4));
+#pragma unroll
+            for (int q = 0; q < V; ++q) o[q] = fmaxf(o[q], 0.f);
+        }
+        if (i < nvec) {
             if (V == 4)
                 stg_stream(reinterpret_cast<float4*>(y + i * V), make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]));
             else
@@ -311,7 +339,8 @@ template <int V, bool kXhat>
 __global__ void __launch_bounds__(kThreads)
 col_sums_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
            const float* __restrict__ invstd, const float* __restrict__ gamma, int64_t R, int C, int LX, int LY,
-           int rows_per_block, float* ws, float* dgamma, float* dbeta, float* coef, int acc_gamma, int acc_beta) {
+           int rows_per_block, float* ws, float* dgamma, float* dbeta, float* coef, int acc_gamma, int acc_beta,
+           const uint8_t* __restrict__ rmask) {
     __shared__ float s_a[kThreads * V];
     __shared__ float s_b[kThreads * V];
     __shared__ unsigned s_ticket;
@@ -346,6 +375,10 @@ col_sums_k(const float* __restrict__ dy, const float* __restrict__ x, const floa
                 load_vec<V>(dy + (r + (int64_t)u * LY) * C + coff, g[u]);
                 if (kXhat) load_vec<V>(x + (r + (int64_t)u * LY) * C + coff, xv[u]);
             }
+            if (rmask) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) apply_relu_mask<V>(rmask, (r + (int64_t)u * LY) * C + coff, g[u]);
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -358,6 +391,7 @@ col_sums_k(const float* __restrict__ dy, const float* __restrict__ x, const floa
             float g[V], xv[V];
             load_vec<V>(dy + r * C + coff, g);
             if (kXhat) load_vec<V>(x + r * C + coff, xv);
+            if (rmask) apply_relu_mask<V>(rmask, r * C + coff, g);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 sa[i] += g[i];
@@ -466,7 +500,7 @@ template <int V, bool kAcc>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_k(const float* __restrict__ dy, const float* __restrict__ x, float* dx, const float* __restrict__ mean,
                const float* __restrict__ invstd, const float* __restrict__ coef, int64_t nvec, int CV, int C,
-               int cv_mask) {
+               int cv_mask, const uint8_t* __restrict__ rmask) {
     constexpr int U = 4;
     const int64_t base = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
     float g[U][V], xv[U][V];
@@ -476,6 +510,7 @@ bn_bwd_apply_k(const float* __restrict__ dy, const float* __restrict__ x, float*
         if (i < nvec) {
             load_vec<V>(dy + i * V, g[j]);
             load_vec<V>(x + i * V, xv[j]);
+            if (rmask) apply_relu_mask<V>(rmask, i * V, g[j]);
         }
     }
 #pragma unroll
@@ -529,13 +564,31 @@ int64_t xsb_bn_workspace_floats(int64_t R, int C) {
     return kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks + 3 * (int64_t)C;
 }
 
-// Training-mode forward. x,y [R,C]; gamma,beta,running_*,save_* [C]. running_* nullable.
-int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                     float* y, float* save_mean, float* save_invstd, int64_t R, int C, float eps, float momentum,
-                     float* ws, void* stream) {
+static int launch_bn_apply(const float* x, float* y, const float* mean, const float* invstd, const float* gamma,
+                           const float* beta, int64_t R, int C, uint8_t* relu_mask, bool relu, cudaStream_t s) {
+    const bool v4 = use_vec4(C, x, y);
+    const int V = v4 ? 4 : 1, CV = C / V;
+    const int64_t nvec = R * CV;
+    const int cv_mask = (CV & (CV - 1)) == 0 ? CV - 1 : -1;
+    const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
+    if (relu) {
+        XSB_CHECK_ARG(v4 && nvec % 2 == 0 && relu_mask, "bn_apply: fused ReLU needs C %% 4 == 0, an even vector count and a mask");
+        bn_apply_k<4, true><<<blocks, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, cv_mask, relu_mask);
+    } else if (v4) {
+        bn_apply_k<4, false><<<blocks, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, cv_mask, nullptr);
+    } else {
+        bn_apply_k<1, false><<<blocks, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, cv_mask, nullptr);
+    }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// Batch statistics of x [R,C]: save_mean / save_invstd and the running-statistics update (functional.py:689-706).
+int xsb_bn_stats(const float* x, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                 int64_t R, int C, float eps, float momentum, float* ws, void* stream) {
     XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
     cudaStream_t s = xsb_stream(stream);
-    const bool v4 = use_vec4(C, x, y);
+    const bool v4 = use_vec4(C, x);
     const Geom g = make_geom(R, C, v4);
     XSB_CHECK_ARG(g.chunks <= kCounterSlots, "bn: C=%d too large", C);
     dim3 grid(g.nb, g.chunks);
@@ -546,15 +599,24 @@ int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, floa
         bn_stats_k<1><<<grid, kThreads, 0, s>>>(x, R, C, g.LX, g.LY, g.rows_per_block, ws, save_mean, save_invstd,
                                                 running_mean, running_var, eps, momentum);
     XSB_LAUNCH_CHECK();
-    const int64_t nvec = R * g.CV;
-    const int cv_mask = (g.CV & (g.CV - 1)) == 0 ? g.CV - 1 : -1;
-    const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
-    if (v4)
-        bn_apply_k<4><<<blocks, kThreads, 0, s>>>(x, y, save_mean, save_invstd, gamma, beta, nvec, g.CV, cv_mask);
-    else
-        bn_apply_k<1><<<blocks, kThreads, 0, s>>>(x, y, save_mean, save_invstd, gamma, beta, nvec, g.CV, cv_mask);
-    XSB_LAUNCH_CHECK();
     return XSB_OK;
+}
+
+// y = gamma * (x - mean) * invstd + beta, optionally followed by ReLU with the x<0 bit mask written in the same
+// pass (relu != 0: the fusion of BatchNormalization -> ReLU(inplace=True); needs C % 4 == 0).
+int xsb_bn_apply(const float* x, float* y, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, int64_t R, int C, int relu, uint8_t* relu_mask, void* stream) {
+    XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
+    return launch_bn_apply(x, y, mean, invstd, gamma, beta, R, C, relu_mask, relu != 0, xsb_stream(stream));
+}
+
+// Training-mode forward = xsb_bn_stats + xsb_bn_apply. x,y [R,C]; gamma,beta,running_*,save_* [C]. running_* nullable.
+int xsb_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float* y, float* save_mean, float* save_invstd, int64_t R, int C, float eps, float momentum,
+                     float* ws, void* stream) {
+    int rc = xsb_bn_stats(x, running_mean, running_var, save_mean, save_invstd, R, C, eps, momentum, ws, stream);
+    if (rc != XSB_OK) return rc;
+    return launch_bn_apply(x, y, save_mean, save_invstd, gamma, beta, R, C, nullptr, false, xsb_stream(stream));
 }
 
 // Inference branch (xs/nn/functional.py:708-725): y = gamma * (x - moving_mean) / sqrt(moving_var + eps) + beta.
@@ -565,23 +627,14 @@ int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const
     float* invstd = ws + kCounterSlots;   // partial-sum area of the scratch buffer; free between launches
     invstd_k<<<(C + 255) / 256, 256, 0, s>>>(moving_var, invstd, C, eps);
     XSB_LAUNCH_CHECK();
-    const bool v4 = use_vec4(C, x, y);
-    const int V = v4 ? 4 : 1, CV = C / V;
-    const int64_t nvec = R * CV;
-    const int cv_mask = (CV & (CV - 1)) == 0 ? CV - 1 : -1;
-    const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
-    if (v4)
-        bn_apply_k<4><<<blocks, kThreads, 0, s>>>(x, y, moving_mean, invstd, gamma, beta, nvec, CV, cv_mask);
-    else
-        bn_apply_k<1><<<blocks, kThreads, 0, s>>>(x, y, moving_mean, invstd, gamma, beta, nvec, CV, cv_mask);
-    XSB_LAUNCH_CHECK();
-    return XSB_OK;
+    return launch_bn_apply(x, y, moving_mean, invstd, gamma, beta, R, C, nullptr, false, s);
 }
 
 // Backward. dx nullable (input needs no grad); dgamma/dbeta nullable. acc_* : 1 = "+=", 0 = "=".
+// relu_mask (nullable): dy is first masked with the in-place ReLU's bit mask (fused ReLUBackward).
 int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
-               float* ws, void* stream) {
+               const uint8_t* relu_mask, float* ws, void* stream) {
     XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
     cudaStream_t s = xsb_stream(stream);
     const bool v4 = use_vec4(C, dy, x, dx);
@@ -591,10 +644,12 @@ int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float*
     dim3 grid(g.nb, g.chunks);
     if (v4)
         col_sums_k<4, true><<<grid, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, gamma, R, C, g.LX, g.LY,
-                                                      g.rows_per_block, ws, dgamma, dbeta, coef, acc_dgamma, acc_dbeta);
+                                                      g.rows_per_block, ws, dgamma, dbeta, coef, acc_dgamma, acc_dbeta,
+                                                      relu_mask);
     else
         col_sums_k<1, true><<<grid, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, gamma, R, C, g.LX, g.LY,
-                                                      g.rows_per_block, ws, dgamma, dbeta, coef, acc_dgamma, acc_dbeta);
+                                                      g.rows_per_block, ws, dgamma, dbeta, coef, acc_dgamma, acc_dbeta,
+                                                      relu_mask);
     XSB_LAUNCH_CHECK();
     if (dx) {
         const int64_t nvec = R * g.CV;
@@ -602,14 +657,14 @@ int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float*
         const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
         if (v4) {
             if (acc_dx)
-                bn_bwd_apply_k<4, true><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+                bn_bwd_apply_k<4, true><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask, relu_mask);
             else
-                bn_bwd_apply_k<4, false><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+                bn_bwd_apply_k<4, false><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask, relu_mask);
         } else {
             if (acc_dx)
-                bn_bwd_apply_k<1, true><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+                bn_bwd_apply_k<1, true><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask, relu_mask);
             else
-                bn_bwd_apply_k<1, false><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask);
+                bn_bwd_apply_k<1, false><<<blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, coef, nvec, g.CV, C, cv_mask, relu_mask);
         }
         XSB_LAUNCH_CHECK();
     }
@@ -626,10 +681,10 @@ int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, flo
     dim3 grid(g.nb, g.chunks);
     if (v4)
         col_sums_k<4, false><<<grid, kThreads, 0, s>>>(x, nullptr, nullptr, nullptr, nullptr, R, C, g.LX, g.LY,
-                                                       g.rows_per_block, ws, nullptr, out, nullptr, 0, accumulate);
+                                                       g.rows_per_block, ws, nullptr, out, nullptr, 0, accumulate, nullptr);
     else
         col_sums_k<1, false><<<grid, kThreads, 0, s>>>(x, nullptr, nullptr, nullptr, nullptr, R, C, g.LX, g.LY,
-                                                       g.rows_per_block, ws, nullptr, out, nullptr, 0, accumulate);
+                                                       g.rows_per_block, ws, nullptr, out, nullptr, 0, accumulate, nullptr);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

@@ -142,6 +142,27 @@ __global__ void __launch_bounds__(kThreads) add_vec(const float4* __restrict__ a
         if (i < n4) stg_stream(y + i, make_float4(u[j].x + v[j].x, u[j].y + v[j].y, u[j].z + v[j].z, u[j].w + v[j].w));
     }
 }
+// y = max(0, a + b) with the (a+b) < 0 bit mask: residual add fused with the in-place ReLU that follows it
+__global__ void __launch_bounds__(kThreads) add_relu_vec(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                         float4* __restrict__ y, uint8_t* __restrict__ mask, int64_t n4) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    float4 u[kUnroll], v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        u[j] = v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) { u[j] = ldg_stream(a + i); v[j] = ldg_stream(b + i); }
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + (int64_t)j * kThreads;
+        const float4 t = make_float4(u[j].x + v[j].x, u[j].y + v[j].y, u[j].z + v[j].z, u[j].w + v[j].w);
+        unsigned nib = (t.x < 0.f ? 1u : 0u) | (t.y < 0.f ? 2u : 0u) | (t.z < 0.f ? 4u : 0u) | (t.w < 0.f ? 8u : 0u);
+        const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
+        if ((threadIdx.x & 1) == 0 && i < n4) mask[i >> 1] = (uint8_t)(nib | (hi << 4));
+        if (i < n4) stg_stream(y + i, make_float4(relu1(t.x), relu1(t.y), relu1(t.z), relu1(t.w)));
+    }
+}
 __global__ void add_scalar(const float* a, const float* b, float* y, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = a[i] + b[i];
@@ -281,6 +302,16 @@ int xsb_add(const float* a, const float* b, float* y, int64_t n, void* stream) {
         add_vec<<<vec_blocks(n / 4), kThreads, 0, s>>>((const float4*)a, (const float4*)b, (float4*)y, n / 4);
     else
         add_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(a, b, y, n);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// y = max(0, a + b), mask bit e = [(a+b)[e] < 0]; n % 8 == 0 and 16-byte aligned buffers required
+int xsb_add_relu(const float* a, const float* b, float* y, uint8_t* mask, int64_t n, void* stream) {
+    if (n <= 0) return XSB_OK;
+    XSB_CHECK_ARG(mask && vec_ok(n, a, b, y), "add_relu: needs n %% 8 == 0, aligned buffers and a mask");
+    add_relu_vec<<<vec_blocks(n / 4), kThreads, 0, xsb_stream(stream)>>>((const float4*)a, (const float4*)b, (float4*)y,
+                                                                        mask, n / 4);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

@@ -34,7 +34,16 @@ class ReLU(Layer):
                 mask = rt.empty((x.numel() + 7) // 8, "uint8")
                 x.cache["mask"] = mask
                 x.grad_fn = F.ReLUBackward
-            F.relu(x, True, None, _mask=mask)
+            arr = x.arr
+            producer = arr.pending_op
+            if track and producer is not None and getattr(producer, "fusable_relu", False):
+                # the producer (BN apply / residual add) has not run yet: run it fused with this ReLU + mask
+                if GLOBAL.INPUTS is None:
+                    GLOBAL.INPUTS = x
+                arr.pending_op = None
+                producer(mask)
+            else:
+                F.relu(x, True, None, _mask=mask)
             if track:
                 x.cache["inplace"] = True
                 initialize_ops_grad(x)

@@ -64,7 +64,9 @@ class Add(Layer):
         ins = [b.data for b in self._in_bounds]
         y = self._data.arr
         if len(ins) == 1:
-            y.buf[: y.size].copy_(ins[0].arr.as_cl().buf[: y.size])
+            src = ins[0].arr.as_cl()
+            src.flush()
+            y.buf[: y.size].copy_(src.buf[: y.size])
             y.pending_zero = False
         else:
             a, b = ins[0].arr.as_cl(), ins[1].arr.as_cl()

@@ -89,8 +89,18 @@ def add(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
         b = b.as_cl() if a.cl else b.logical_rowmajor()
     out, y = _out_arr(out, a.shape)
     y.cl = a.cl
-    lib.xsb_add(a.ptr, b.ptr, y.wptr, y.size, rt.stream())
-    rt.launches += 1
+    ybuf, n = y.buf, y.size
+    y.wptr  # noqa: B018 -- clears stale pending state of a reused (static) buffer
+
+    def run(mask=None, _a=a, _b=b):
+        # deferred: a following ReLU(inplace=True) turns this into ONE add+ReLU(+mask) pass
+        if mask is None:
+            lib.xsb_add(_a.ptr, _b.ptr, ybuf.data_ptr(), n, rt.stream())
+        else:
+            lib.xsb_add_relu(_a.ptr, _b.ptr, ybuf.data_ptr(), mask.data_ptr(), n, rt.stream())
+        rt.launches += 1
+    run.fusable_relu = n % 8 == 0
+    y.pending_op = run
     return _wire(out, (lhs, rhs), lhs.requires_grad or rhs.requires_grad, AddBackward)
 
 
@@ -206,6 +216,7 @@ def flatten(inputs: Tensor, start: int = 1, out: Tensor = None) -> Tensor:
         if dst is None:
             out._arr = flat
         else:
+            flat.flush()
             dst.buf[: flat.size].copy_(flat.buf[: flat.size])
             dst.pending_zero = False
     return _wire(out, (inputs,), inputs.requires_grad, FlattenBackward)
@@ -227,6 +238,7 @@ def view(inputs: Tensor, shape, out: Tensor = None) -> Tensor:
         if dst is None:
             out._arr = v
         else:
+            v.flush()
             dst.buf[: v.size].copy_(v.as_cl().buf[: v.size] if dst.cl else v.buf[: v.size])
             dst.pending_zero = False
     return _wire(out, (inputs,), inputs.requires_grad, ViewBackward)
@@ -332,10 +344,19 @@ def batch_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, moving_mean: Tensor,
             inputs.add_out_bounds(out)
         return out
     save_mean, save_invstd = DevArray.empty((C,)), DevArray.empty((C,))
-    lib.xsb_bn_train_fwd(x.ptr, gamma.arr.ptr, beta.arr.ptr, moving_mean.arr.ptr, moving_variance.arr.ptr, y.wptr,
-                         save_mean.wptr, save_invstd.wptr, R, C, float(epsilon), float(momentum),
-                         rt.ws_small.data_ptr(), rt.stream())
-    rt.launches += 2
+    lib.xsb_bn_stats(x.ptr, moving_mean.arr.ptr, moving_variance.arr.ptr, save_mean.wptr, save_invstd.wptr, R, C,
+                     float(epsilon), float(momentum), rt.ws_small.data_ptr(), rt.stream())
+    rt.launches += 1
+    ybuf = y.buf
+    y.wptr  # noqa: B018 -- clears stale pending state of a reused (static) buffer
+
+    def run(mask=None, _x=x, _g=gamma.arr, _b=beta.arr):
+        # deferred apply pass: a following ReLU(inplace=True) fuses into it (y = max(0, bn(x)) + bit mask)
+        lib.xsb_bn_apply(_x.ptr, ybuf.data_ptr(), save_mean.peek_ptr(), save_invstd.peek_ptr(), _g.ptr, _b.ptr, R, C,
+                         0 if mask is None else 1, None if mask is None else mask.data_ptr(), rt.stream())
+        rt.launches += 1
+    run.fusable_relu = C % 4 == 0 and (R * (C // 4)) % 2 == 0 and x.cl == y.cl
+    y.pending_op = run
     rg = inputs.requires_grad or gamma.requires_grad or beta.requires_grad
     axis_field = tuple(i for i in range(x.ndim) if i != (axis % x.ndim))
     return _wire(out, (inputs, gamma, beta), rg, BatchNormBackward,

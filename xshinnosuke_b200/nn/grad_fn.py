@@ -40,6 +40,7 @@ def accumulate_into(t, src):
     elif src.pending_zero:
         g.buf[: g.size].zero_()
     else:
+        src.flush()
         g.buf[: g.size].copy_(src.buf[: g.size])   # first write: a plain device-to-device copy
 
 
@@ -56,12 +57,23 @@ def accumulate_rowmajor_into(t, src_rm):
 
 
 # ------------------------------------------------------------------ elementwise
-def AddBackward(outputs: Tensor):
-    """xs/nn/grad_fn.py:6-16 (same-shape operands)."""
+def AddBackward(outputs: Tensor, relu_mask=None):
+    """xs/nn/grad_fn.py:6-16 (same-shape operands). With `relu_mask` (handed over by the in-place ReLUBackward
+    that precedes it) the mask is applied while the gradient is written into each operand: one pass per
+    operand instead of mask-in-place + copies."""
     dy = outputs.grad.arr
-    for in_bound in outputs.in_bounds:
-        if in_bound.requires_grad:
-            accumulate_into(in_bound, dy)
+    targets = [t for t in outputs.in_bounds if t.requires_grad]
+    if relu_mask is not None:
+        if all(_grad_arr(t).cl == dy.cl for t in targets):
+            for t in targets:
+                g = _grad_arr(t)
+                lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), g.peek_ptr(), g.size, g.take_acc(), rt.stream())
+                rt.launches += 1
+            return
+        lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), dy.peek_ptr(), dy.size, 0, rt.stream())
+        rt.launches += 1
+    for t in targets:
+        accumulate_into(t, dy)
 
 
 def ReLUBackward(outputs: Tensor):
@@ -69,12 +81,16 @@ def ReLUBackward(outputs: Tensor):
     recorded by the forward, pop the producer's closure and run it; otherwise dX += dY*[x>=0]."""
     if outputs.cache.get("inplace"):
         mask = outputs.cache["mask"]
+        fn = outputs.cache["grad_fn"].pop()
+        outputs.grad_fn = fn
+        if fn is BatchNormBackward or fn is AddBackward:
+            fn(outputs, relu_mask=mask)      # the producer's backward kernels apply the mask on the fly
+            return
         g = outputs.grad.arr
         lib.xsb_relu_bwd_mask(g.ptr, mask.data_ptr(), g.peek_ptr(), g.size, 0, rt.stream())
         rt.launches += 1
-        outputs.grad_fn = outputs.cache["grad_fn"].pop()
-        if outputs.grad_fn is not None:
-            outputs.grad_fn(outputs)
+        if fn is not None:
+            fn(outputs)
     else:
         inputs, = outputs.in_bounds
         if inputs.requires_grad:
@@ -216,9 +232,10 @@ def Avgpool2DBackward(outputs: Tensor):
         rt.launches += 1
 
 
-def BatchNormBackward(outputs: Tensor):
+def BatchNormBackward(outputs: Tensor, relu_mask=None):
     """xs/nn/grad_fn.py:379-411. xhat is recomputed from the retained input and the saved
-    mean / invstd (the reference caches xhat and sqrtvar and destroys them here)."""
+    mean / invstd (the reference caches xhat and sqrtvar and destroys them here). `relu_mask`: the bit mask of
+    an in-place ReLU applied to this BN's output; dY is masked inside the kernels (fused ReLUBackward)."""
     inputs, gamma, beta = outputs.in_bounds
     dy = outputs.grad.arr
     x = inputs.arr
@@ -233,7 +250,8 @@ def BatchNormBackward(outputs: Tensor):
                    gx.peek_ptr() if gx is not None else None, gg.peek_ptr() if gg is not None else None,
                    gb.peek_ptr() if gb is not None else None, R, C,
                    gx.take_acc() if gx is not None else 0, gg.take_acc() if gg is not None else 0,
-                   gb.take_acc() if gb is not None else 0, rt.ws_small.data_ptr(), rt.stream())
+                   gb.take_acc() if gb is not None else 0, relu_mask.data_ptr() if relu_mask is not None else None,
+                   rt.ws_small.data_ptr(), rt.stream())
     rt.launches += 2 if gx is not None else 1
     _done(gamma)
     _done(beta)

@@ -56,6 +56,12 @@ def cost(name, a):
         return "byte", 4.0 * (N * H * W * C + N * OH * OW * C)
     if name == "xsb_bn_train_fwd":
         return "byte", 12.0 * a[8] * a[9]
+    if name == "xsb_bn_stats":
+        return "byte", 4.0 * a[5] * a[6]
+    if name == "xsb_bn_apply":
+        return "byte", 8.0 * a[6] * a[7] + (a[6] * a[7] / 8.0 if a[8] else 0.0)
+    if name == "xsb_add_relu":
+        return "byte", 12.0 * a[4] + a[4] / 8.0
     if name == "xsb_bn_bwd":
         return "byte", (20.0 if a[5] else 8.0) * a[8] * a[9]
     if name == "xsb_colsum":
