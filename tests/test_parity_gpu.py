@@ -278,3 +278,25 @@ def test_cuda_graph_step_matches_eager(optimizer):
     np.testing.assert_allclose(losses_g, losses_e[2:], rtol=1e-5)
     for pe, pg in zip(net_e.parameters(), net_g.parameters()):
         assert float(np.max(np.abs(pe.eval - pg.eval))) <= 1e-5 * max(float(np.max(np.abs(pe.eval))), 1e-2)
+
+
+def test_dataloader_prefetch_matches_plain():
+    """the pinned / side-stream prefetching loader yields exactly the reference's batches
+    (same order incl. the per-epoch reseeding), and rank shards are contiguous slices."""
+    from xshinnosuke_b200.utils.data import DataLoader, DataSet
+    rs = np.random.RandomState(0)
+    X_, Y_ = rs.rand(70, 3, 9, 9).astype(np.float32), rs.randint(0, 10, (70,))
+    for shuffle in (False, True):
+        a = DataLoader(DataSet(X_, Y_), 16, shuffle, prefetch=True)
+        b = DataLoader(DataSet(X_, Y_), 16, shuffle, prefetch=False)
+        for epoch in range(2):
+            got = [(x.eval, y.eval) for x, y in a]
+            want = [(x.eval, y.eval) for x, y in b]
+            assert len(got) == len(want) == 5
+            for (gx, gy), (wx, wy) in zip(got, want):
+                assert np.array_equal(gx, wx) and np.array_equal(gy, wy)
+    full = DataLoader(DataSet(X_, Y_), 16, False, prefetch=False)
+    r1 = DataLoader(DataSet(X_, Y_), 16, False, rank=1, world=2)
+    for (fx, fy), (sx, sy) in zip(full, r1):
+        per = fx.shape[0] // 2
+        assert np.array_equal(sx.eval, fx.eval[per:2 * per]) and np.array_equal(sy.eval, fy.eval[per:2 * per])

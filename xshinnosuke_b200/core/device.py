@@ -179,7 +179,7 @@ class DevArray:
             host = host.copy()   # torch.from_numpy refuses read-only arrays (e.g. views of an .npz)
         shape = host.shape if host.ndim else (1,)  # 0-d scalars behave as shape (1,) (xs/core/base.py:82-84)
         t = torch()
-        dev = t.from_numpy(host.reshape(-1)).to(rt.device)
+        dev = t.from_numpy(host.reshape(-1)).to(rt.device, non_blocking=True)   # async when `host` is pinned
         out = DevArray(dev, shape, dtype)
         if out.cl and out.size > 0:
             n, c, h, w = out.shape
@@ -254,7 +254,10 @@ class DevArray:
     def assign_numpy(self, a):
         """Overwrite the contents from a host array of the same logical shape (keeps the buffer:
         parameter storage may be a view into the flat optimizer buffer)."""
-        new = DevArray.from_numpy(np.broadcast_to(np.asarray(a), self.shape))
+        a = np.asarray(a)
+        if tuple(a.shape) != tuple(self.shape):
+            a = np.broadcast_to(a, self.shape)       # (read-only view: from_numpy copies it)
+        new = DevArray.from_numpy(a)
         if new.dtype != self.dtype:
             raise TypeError(f"cannot assign {new.dtype} data to a {self.dtype} tensor")
         self.buf[: max(self.size, 1)].copy_(new.buf[: max(self.size, 1)])

@@ -291,7 +291,7 @@ struct WgradParams {
 };
 
 template <int BN, int BKP, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (STAGES * (4 + BN / 32) * BKP * 128 <= 100 * 1024) ? 2 : 1)
 conv_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy, const WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int BOX_BYTES = BKP * A_ROW_BYTES;       // one {32 elements x BKP pixels} box
@@ -793,7 +793,12 @@ static int fprop_dispatch(const float* in, const float* flt, const float* bias, 
         xsb_set_error("cuTensorMapEncode* entry points unavailable");
         return XSB_ERR_CUDA;
     }
-    const int BN = (OCx % 256 == 0) ? 256 : (OCx % 128 == 0) ? 128 : 64;
+    int BN = (OCx % 256 == 0) ? 256 : (OCx % 128 == 0) ? 128 : 64;
+    {   // a 256-wide tile that leaves SMs idle loses to twice as many 128-wide CTAs (XSB_TC_NARROW=0 disables)
+        static const int narrow = [] { const char* e = getenv("XSB_TC_NARROW"); return (e && e[0] == '1') ? 1 : 0; }();   // measured slower on layer4: off
+        const int64_t ctas = (int64_t)((N * OH * OW + BM - 1) / BM) * (OCx / BN);
+        if (narrow && BN == 256 && ctas < xsb_sm_count_cached()) BN = 128;
+    }
     CUtensorMap ta, tb;
     if (!make_map_im2col(&ta, in, N, H, W, Cx, KH, KW, sh, sw, pad, BM, CU_TENSOR_MAP_SWIZZLE_128B, extra_w, extra_h) ||
         !make_map_2d(&tb, flt, (uint64_t)OCx, (uint64_t)KH * KW * Cx, (uint32_t)BN)) {
@@ -1014,7 +1019,9 @@ int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
         return XSB_ERR_CUDA;
     }
     const int P = g.N * g.OH * g.OW;
-    const int BN = (g.OC % 256 == 0) ? 256 : (g.OC % 128 == 0) ? 128 : 64;
+    static const int wg_bn_cap = [] { const char* e = getenv("XSB_TC_WG_BN"); return e ? atoi(e) : 128; }();   // measured: 128-wide tiles + 64-pixel k-blocks beat 256 x 32 (layer4 93 -> 73 us)
+    int BN = (g.OC % 256 == 0) ? 256 : (g.OC % 128 == 0) ? 128 : 64;
+    if (BN > wg_bn_cap) BN = wg_bn_cap;
     const int BKP = BN == 256 ? 32 : 64;
     CUtensorMap tx, tdy;
     if (!make_map_im2col(&tx, x, g.N, g.H, g.W, g.C, g.KH, g.KW, g.sh, g.sw, g.pad, (uint32_t)BKP,
@@ -1035,8 +1042,10 @@ int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
     if (use_atomics && !accumulate) XSB_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.OC * rows * sizeof(float), s));
     WgradParams p{dw, P, g.C, g.OC, g.KH, g.KW, g.OH, g.OW, g.sh, g.sw, g.pad, kb_per, use_atomics};
     dim3 grid(m_tiles, n_tiles, splits);
+    static const int wg_occ = [] { const char* e = getenv("XSB_TC_WG_OCC"); return (e && e[0] == '2') ? 2 : 1; }();   // measured: no gain from 2 CTAs/SM
     if (BN == 256) return launch_wgrad<256, 32, 4>(tx, tdy, p, grid, s);
     if (BN == 128) return launch_wgrad<128, 64, 3>(tx, tdy, p, grid, s);
+    if (wg_occ == 2) return launch_wgrad<64, 64, 2>(tx, tdy, p, grid, s);   // 2 x 48 KB stages: two CTAs per SM
     return launch_wgrad<64, 64, 4>(tx, tdy, p, grid, s);
 }
 
