@@ -41,7 +41,7 @@ def oracle_shard_grads(x, y, P):
     return float(loss[0]), [dw1, dg1, dbe1, dw2, dg2, dbe2, dwf, dbf.reshape(1, -1)]
 
 
-def run(rank, world, port, use_fake, steps, optimizer, out_queue=None, bucket_mb=0.001):
+def run(rank, world, port, use_fake, steps, optimizer, out_queue=None, bucket_mb=0.001, use_graph=False):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     if use_fake:
@@ -65,14 +65,31 @@ def run(rank, world, port, use_fake, steps, optimizer, out_queue=None, bucket_mb
     dp = DataParallel(net, opt, bucket_mb=bucket_mb)
     xs_x, xs_y = shard(X_all, rank, world), shard(Y_all, rank, world)
     ref_params, adam_state, errs, losses = None, {}, [], []
+    tx, ty = xs.tensor(xs_x), xs.tensor(xs_y)
+    graphed = None
     for step in range(steps):
-        opt.zero_grad()
-        loss = nn.CrossEntropyLoss()(net(xs.tensor(xs_x)), xs.tensor(xs_y))
-        if ref_params is None:   # parameters exist after the first forward
-            ref_params = [p.eval.astype(np.float64) for p in net.parameters()]
-        losses.append(loss.item())
-        loss.backward()
-        opt.step()
+        if use_graph and step == 1:
+            # steps 1.. are replays of ONE captured step (kernels + bucket all-reduces); GraphedStep's own
+            # warm-up step is step 1, the capture itself executes nothing
+            def one_step():
+                opt.zero_grad()
+                l_ = nn.CrossEntropyLoss()(net(tx), ty)
+                l_.backward()
+                opt.step()
+                return l_
+            graphed = xs.GraphedStep(one_step, warmup=1)
+            loss = graphed.result
+            losses.append(float("nan"))
+        elif graphed is not None:
+            losses.append(graphed().item())
+        else:
+            opt.zero_grad()
+            loss = nn.CrossEntropyLoss()(net(tx), ty)
+            if ref_params is None:   # parameters exist after the first forward
+                ref_params = [p.eval.astype(np.float64) for p in net.parameters()]
+            losses.append(loss.item())
+            loss.backward()
+            opt.step()
         # oracle: every shard separately, averaged gradients, one update
         grads, ref_losses = None, []
         for r in range(world):
@@ -87,7 +104,8 @@ def run(rank, world, port, use_fake, steps, optimizer, out_queue=None, bucket_mb
         # conv biases in front of a BN have a (mathematically) zero gradient and stay ~0: floor the denominator
         errs.append(max(float(np.max(np.abs(p.eval - r)) / max(np.max(np.abs(r)), 1e-3))
                         for p, r in zip(net.parameters(), ref_params)))
-        errs.append(abs(losses[-1] - ref_losses[rank]) / ref_losses[rank])
+        if losses[-1] == losses[-1]:   # (the capture step has no readable loss)
+            errs.append(abs(losses[-1] - ref_losses[rank]) / ref_losses[rank])
     result = dict(rank=rank, max_err=max(errs), n_allreduce=dp.n_allreduce, n_buckets=len(dp._buckets),
                   losses=losses)
     dp.dist.barrier()
@@ -99,6 +117,6 @@ def run(rank, world, port, use_fake, steps, optimizer, out_queue=None, bucket_mb
 if __name__ == "__main__":   # torchrun entry (GPU): python tests/dp_worker.py [sgd|adam]
     opt_name = sys.argv[1] if len(sys.argv) > 1 else "sgd"
     r = run(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("MASTER_PORT", 29511)),
-            False, 3, opt_name)
+            False, 4, opt_name, use_graph="graph" in sys.argv[2:])
     print("DP_RESULT", r, flush=True)
     assert r["max_err"] <= 2e-5, r
