@@ -180,7 +180,11 @@ def _tc_stats():
     (4, 64, 14, 64, 3, 1, 1, 3), (8, 64, 28, 128, 3, 2, 1, 3), (8, 64, 28, 128, 1, 2, 0, 3), (4, 64, 15, 128, 3, 2, 1, 3), (4, 128, 14, 256, 3, 1, 1, 3),
     (2, 256, 7, 512, 3, 1, 1, 3), (2, 64, 12, 64, 5, 1, 2, 3), (16, 64, 56, 64, 3, 1, 1, 3), (3, 32, 9, 64, 3, 1, 1, 2),
     (2, 3, 20, 64, 7, 2, 3, 2), (4, 3, 56, 64, 7, 2, 3, 2), (2, 1, 28, 64, 2, 1, 0, 2), (3, 3, 33, 128, 3, 1, 1, 2),
-    (2, 4, 19, 64, 5, 2, 2, 2), (2, 3, 20, 8, 3, 1, 1, 0)])
+    (2, 4, 19, 64, 5, 2, 2, 2), (2, 3, 20, 8, 3, 1, 1, 0),
+    # strided dgrad = one stride-1 conv per parity class (5x5/2; trailing row without gradient; classes no tap reaches)
+    (2, 64, 16, 64, 5, 2, 2, 3), (2, 64, 10, 64, 3, 2, 0, 3), (2, 64, 8, 64, 2, 3, 0, 3), (2, 64, 17, 128, 7, 2, 3, 3),
+    # filter-resident halo kernel (fwd and stride-1 dgrad), incl. partial tiles and zero padding via TMA OOB fill
+    (2, 64, 32, 64, 3, 1, 1, 3), (2, 64, 30, 64, 3, 1, 2, 3), (3, 32, 34, 128, 3, 1, 0, 2), (150, 64, 16, 64, 3, 1, 1, 3)])
 def test_conv_tf32_tensor_cores(n, c, h, oc, k, s, p, n_tc):
     """fwd / dgrad / wgrad on tcgen05 (kind::tf32) against the float64 oracle; `n_tc` = how many of the three
     must have run on the tensor cores for this shape (C <= 4 stems: fwd + wgrad via the padded-4-channel kernels,

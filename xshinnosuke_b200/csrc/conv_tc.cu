@@ -17,7 +17,7 @@
 // Reference arithmetic: xs/nn/functional.py:405-442, xs/nn/grad_fn.py:186-203 (see gemm_conv.cu).
 // Shapes outside the envelope (C or OC not multiples of 32/64, strided dgrad) return
 // XSB_ERR_UNSUPPORTED from the xsb_tc_* probes and the caller runs the fp32 FFMA kernel instead.
-#include "tc_common.cuh"
+#include "conv_halo_tc.cuh"
 
 namespace tc {
 
@@ -26,8 +26,11 @@ struct FpropParams {
     float* out;          // [M, ldo] row-major (channels-last output)
     const float* bias;   // [OCtot] or null
     int M, ldo;          // M = N*OH*OW output pixels, ldo = total output channels
-    int C, KH, KW, OH, OW, sh, sw, pad;
+    int C, KH, KW, OH, OW, sh, sw, pad_h, pad_w;
     int accumulate;
+    // strided destination (dgrad of a strided conv: one launch produces one parity class of dX):
+    // GEMM row (n,i,j) lands on pixel (n, o_a + i*o_sh, o_b + j*o_sw) of an [N, o_H, o_W, ldo] tensor
+    int o_strided, o_H, o_W, o_sh, o_sw, o_a, o_b;
 };
 
 template <int BN, int STAGES, int OCC>
@@ -69,45 +72,59 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // first pixel of the tile -> window origin in the input image
-            const int hw = p.OH * p.OW;
-            const int n_img = m0 / hw, rem = m0 - n_img * hw;
-            const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
-            const int w0 = ow0 * p.sw - p.pad, h0 = oh0 * p.sh - p.pad;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-                const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                tma_load_im2col(sA + s * A_BYTES, &tmA, &full[s], cb * 32, w0, h0, n_img, (uint16_t)kw, (uint16_t)kh);
-                tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], tap * p.C + cb * 32, n0);
-            }
-        }
+        // first pixel of the tile -> window origin in the input image
+        const int hw = p.OH * p.OW;
+        const int n_img = m0 / hw, rem = m0 - n_img * hw;
+        const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+        const int w0 = ow0 * p.sw - p.pad_w, h0 = oh0 * p.sh - p.pad_h;
+        int s = 0, kb = 0;
+        uint32_t ph = 0;
+        for (int kh = 0; kh < p.KH; ++kh)
+            for (int kw = 0; kw < p.KW; ++kw)
+                for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                        tma_load_im2col(sA + s * A_BYTES, &tmA, &full[s], cb * 32, w0, h0, n_img, (uint16_t)kw, (uint16_t)kh);
+                        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * 32, n0);   // column (tap*C + cb*32) = kb*32
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&full[s], (kb / STAGES) & 1);
-                tc_fence_after();
-                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), 16, 1024);
-                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), 16, 1024);
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t da = make_desc(a_base + s * A_BYTES, 16, 1024);
+                const uint64_t db = make_desc(b_base + s * B_BYTES, 16, 1024);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 = 32 B) per 128-byte row
                     umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                 umma_commit(&empty[s]);
             }
-            umma_commit(tmem_full);
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
     } else {
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        float* orow = p.out + (int64_t)m * p.ldo + n0;
+        int64_t pix = m;
+        if (p.o_strided) {
+            const int hw = p.OH * p.OW;
+            const int n_img = m / hw, rem = m - n_img * hw;
+            const int i = rem / p.OW, j = rem - i * p.OW;
+            pix = ((int64_t)n_img * p.o_H + p.o_a + i * p.o_sh) * p.o_W + p.o_b + j * p.o_sw;
+        }
+        float* orow = p.out + pix * p.ldo + n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -194,50 +211,66 @@ conv_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int box_c[4], box_kh[4], box_kw[4], nvalid = 0;
+        int box_c[4], box_kh[4], box_kw[4], nvalid = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int mrow = r0 + i * 32;
-                const int tap = mrow / p.C;
-                box_c[i] = mrow - tap * p.C;
-                box_kh[i] = tap / p.KW;
-                box_kw[i] = tap - box_kh[i] * p.KW;
-                if (tap < taps) nvalid = i + 1;   // valid boxes are a prefix
-            }
-            const int hw = p.OH * p.OW;
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        for (int i = 0; i < 4; ++i) {
+            const int mrow = r0 + i * 32;
+            const int tap = mrow / p.C;
+            box_c[i] = mrow - tap * p.C;
+            box_kh[i] = tap / p.KW;
+            box_kw[i] = tap - box_kh[i] * p.KW;
+            if (tap < taps) nvalid = i + 1;   // valid boxes are a prefix
+        }
+        const int hw = p.OH * p.OW;
+        // running pixel coordinates of the k-block (no divisions in the loop)
+        int p0 = kb_begin * BKP;
+        int n_img = p0 / hw, rem = p0 - n_img * hw;
+        int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < num_kb; ++i) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&full[s], nvalid * BOX_BYTES + B_BYTES);
-                const int p0 = (kb_begin + i) * BKP;
-                const int n_img = p0 / hw, rem = p0 - n_img * hw;
-                const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
                 const int w0 = ow0 * p.sw - p.pad, h0 = oh0 * p.sh - p.pad;
-                for (int b = 0; b < nvalid; ++b)
-                    tma_load_im2col(sA + s * A_BYTES + b * BOX_BYTES, &tmX, &full[s], box_c[b], w0, h0, n_img,
-                                    (uint16_t)box_kw[b], (uint16_t)box_kh[b]);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b < nvalid)
+                        tma_load_im2col(sA + s * A_BYTES + b * BOX_BYTES, &tmX, &full[s], box_c[b], w0, h0, n_img,
+                                        (uint16_t)box_kw[b], (uint16_t)box_kh[b]);
 #pragma unroll
                 for (int b = 0; b < BN / 32; ++b)
                     tma_load_2d(sB + s * B_BYTES + b * BOX_BYTES, &tmDy, &full[s], n0 + b * 32, p0);
             }
+            p0 += BKP;
+            ow0 += BKP;
+            while (ow0 >= p.OW) {
+                ow0 -= p.OW;
+                if (++oh0 == p.OH) { oh0 = 0; ++n_img; }
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                mbar_wait(&full[s], (i / STAGES) & 1);
-                tc_fence_after();
-                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
-                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
+        constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < num_kb; ++i) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t da = make_desc(a_base + s * A_BYTES, BOX_BYTES, 512, kLayoutSW128Base32B);
+                const uint64_t db = make_desc(b_base + s * B_BYTES, BOX_BYTES, 512, kLayoutSW128Base32B);
 #pragma unroll
                 for (int k = 0; k < BKP / 8; ++k)  // K = 8 pixels = two 4-row swizzle atoms = 1024 bytes
                     umma_tf32(tmem_base, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (i | k) != 0);
                 umma_commit(&empty[s]);
             }
-            umma_commit(tmem_full);
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
     } else {
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
@@ -277,9 +310,10 @@ conv_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // k-block exists. The image is first copied into a zero-bordered 4-channel buffer xp[N,Hp,Wp,4]; then for a fixed
 // filter row kh the taps (kw, c) of one output pixel are 32 CONTIGUOUS floats starting at pixel
 // (oh*sh+kh, ow*sw) -- 8 pixels x 4 channels, columns kw >= KW / c >= C meet zero filter entries. A 5-D TILED tensor
-// map with overlapping strides {ow: sw*16 B, oh: sh*Wp*16 B, kh: Wp*16 B, n} exposes exactly those rows, so the
-// mainloop is the usual TMA -> tcgen05 pipeline with KH k-blocks of 32.
-constexpr int STEM_TW = 16, STEM_TH = 8;    // fprop tile: 16 x 8 output pixels = 128 rows of D
+// map with overlapping strides {ow: sw*16 B, ...} exposes exactly those rows: fprop runs the filter-resident halo
+// kernel (conv_halo_tc.cuh) on {32 floats, ow, input row, n}, wgrad a TMA -> tcgen05 pipeline over
+// {32 floats, ow, oh, kh, n} with pixels as the K dimension.
+constexpr int STEM_TW = 16;                 // wgrad pixel block is 16 wide
 constexpr int STEM_WTH = 4;                 // wgrad pixel block: 16 x 4 = 64 pixels (the K dimension)
 
 struct StemParams {
@@ -316,106 +350,6 @@ __global__ void stem_pack_filter_k(const float* __restrict__ w, float* __restric
     const int j = t % 32, kh = (t / 32) % KH, oc = t / (32 * KH);
     const int kw = j / 4, c = j % 4;
     wq[t] = (kw < KW && c < C) ? w[((oc * KH + kh) * KW + kw) * C + c] : 0.f;
-}
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
-stem_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StemParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    constexpr int A_BYTES = BM * A_ROW_BYTES;
-    constexpr int B_BYTES = BN * A_ROW_BYTES;
-    uint8_t* smem = align1024(smem_raw);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = p.KH;
-    const int t = blockIdx.x;
-    const int tw_i = t % p.tiles_w, th_i = (t / p.tiles_w) % p.tiles_h, n_img = t / (p.tiles_w * p.tiles_h);
-    const int n0 = blockIdx.y * BN;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmA);
-        prefetch_tmap(&tmB);
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
-        }
-        mbar_init(tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-                tma_load_5d(sA + s * A_BYTES, &tmA, &full[s], 0, tw_i * STEM_TW, th_i * STEM_TH, kb, n_img);
-                tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * 32, n0);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&full[s], (kb / STAGES) & 1);
-                tc_fence_after();
-                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), 16, 1024);
-                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), 16, 1024);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                umma_commit(&empty[s]);
-            }
-            umma_commit(tmem_full);
-        }
-    } else {
-        const int q = warp & 3;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int row = q * 32 + lane;
-        const int oh = th_i * STEM_TH + row / STEM_TW, ow = tw_i * STEM_TW + row % STEM_TW;
-        const bool valid = oh < p.OH && ow < p.OW;
-        float* orow = p.out + (((int64_t)n_img * p.OH + oh) * p.OW + ow) * p.OC + n0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_wait_ld();
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                           __uint_as_float(r[j + 3]));
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                    }
-                    *reinterpret_cast<float4*>(orow + c0 + j) = v;
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
-    }
 }
 
 // dwq[(kh, kw, c4), oc] = sum over pixel blocks of xp-rows^T . dY ; both operands MN-major (pixels = K)
@@ -467,39 +401,51 @@ stem_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        int n_img = kb_begin / blocks_per_img, rem = kb_begin - n_img * blocks_per_img;
+        int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < num_kb; ++i) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&full[s], nvalid * BOX_BYTES + B_BYTES);
-                const int kb = kb_begin + i;
-                const int n_img = kb / blocks_per_img, rem = kb - n_img * blocks_per_img;
-                const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
-                for (int b = 0; b < nvalid; ++b)
-                    tma_load_5d(sA + s * A_BYTES + b * BOX_BYTES, &tmX, &full[s], 0, tw_i * STEM_TW, th_i * STEM_WTH,
-                                kh0 + b, n_img);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b < nvalid)
+                        tma_load_5d(sA + s * A_BYTES + b * BOX_BYTES, &tmX, &full[s], 0, tw_i * STEM_TW, th_i * STEM_WTH,
+                                    kh0 + b, n_img);
 #pragma unroll
                 for (int b = 0; b < BN / 32; ++b)
                     tma_load_4d(sB + s * B_BYTES + b * BOX_BYTES, &tmDy, &full[s], n0 + b * 32, tw_i * STEM_TW,
                                 th_i * STEM_WTH, n_img);
             }
+            if (++tw_i == p.tiles_w) {
+                tw_i = 0;
+                if (++th_i == p.tiles_h) { th_i = 0; ++n_img; }
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                mbar_wait(&full[s], (i / STAGES) & 1);
-                tc_fence_after();
-                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
-                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES), BOX_BYTES, 512, kLayoutSW128Base32B);
+        constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < num_kb; ++i) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t da = make_desc(a_base + s * A_BYTES, BOX_BYTES, 512, kLayoutSW128Base32B);
+                const uint64_t db = make_desc(b_base + s * B_BYTES, BOX_BYTES, 512, kLayoutSW128Base32B);
 #pragma unroll
                 for (int k = 0; k < BKP / 8; ++k)
                     umma_tf32(tmem_base, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (i | k) != 0);
                 umma_commit(&empty[s]);
             }
-            umma_commit(tmem_full);
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
     } else {
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
@@ -533,8 +479,20 @@ stem_wgrad_tc_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
 }
 
-// wt[c, KH-1-kh, KW-1-kw, oc] = w[oc, kh, kw, c]: the filter of the equivalent forward conv on dY
-__global__ void flip_transpose_filter_k(const float* __restrict__ w, float* __restrict__ wt, int OC, int taps, int C) {
+// dgrad as forward convolutions of dY. For a forward conv of stride (sh, sw) the input pixels split into sh*sw
+// parity classes (a, b) = (h % sh, w % sw); class (a, b) only ever meets the filter taps kh = r_a + sh*t,
+// kw = r_b + sw*t' (r_a = (a + pad) % sh), so
+//   dX[n, a + sh*i, b + sw*j, c] = sum_{ua, ub, oc} dY[n, i - pad_a + ua, j - pad_b + ub, oc] * wt_ab[c, ua, ub, oc]
+// is a STRIDE-1 convolution of dY with the T_a x T_b sub-filter wt_ab[c, ua, ub, oc] = w[oc, r_a + sh*(T_a-1-ua),
+// r_b + sw*(T_b-1-ub), c] (flipped and transposed). Stride 1 is the single class with the whole flipped filter.
+// No zero-inserted copy of dY, no multiplications by inserted zeros.
+struct TapPlace {
+    int base[64];     // float offset of the class' sub-filter in the workspace
+    int pos[64];      // tap position (ua*T_b + ub) inside the sub-filter
+    int ntaps[64];    // T_a*T_b of the class
+};
+__global__ void gather_subfilters_k(const float* __restrict__ w, float* __restrict__ wt, int OC, int taps, int C,
+                                    const TapPlace tp) {
     __shared__ float tile[32][33];
     const int tap = blockIdx.z;
     const int c0 = blockIdx.x * 32, oc0 = blockIdx.y * 32;
@@ -543,38 +501,41 @@ __global__ void flip_transpose_filter_k(const float* __restrict__ w, float* __re
         if (oc < OC && c < C) tile[j][threadIdx.x] = w[((int64_t)oc * taps + tap) * C + c];
     }
     __syncthreads();
+    float* dst = wt + tp.base[tap];
+    const int pos = tp.pos[tap], nt = tp.ntaps[tap];
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int c = c0 + j, oc = oc0 + threadIdx.x;
-        if (oc < OC && c < C) wt[((int64_t)c * taps + (taps - 1 - tap)) * OC + oc] = tile[threadIdx.x][j];
+        if (oc < OC && c < C) dst[((int64_t)c * nt + pos) * OC + oc] = tile[threadIdx.x][j];
     }
 }
 
-// up[n, oh*sh, ow*sw, :] = dy[n, oh, ow, :] (up is pre-zeroed): the zero-insertion that turns a strided
-// dgrad into a stride-1 convolution of the up-sampled dY with the flipped filter.
-__global__ void zero_insert_k(const float4* __restrict__ dy, float4* __restrict__ up, int OH, int OW, int C4, int Hu,
-                              int Wu, int sh, int sw, int64_t total) {
+// dst[n, a + sh*i, b + sw*j, :] = 0 for one parity class (classes no filter tap reaches)
+__global__ void zero_class_k(float4* __restrict__ dx, int Ha, int Wb, int C4, int H, int W, int sh, int sw, int a, int b,
+                             int64_t total) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int c = (int)(t % C4);
     int64_t r = t / C4;
-    const int ow = (int)(r % OW);
-    r /= OW;
-    const int oh = (int)(r % OH);
-    const int n = (int)(r / OH);
-    up[(((int64_t)n * Hu + (int64_t)oh * sh) * Wu + (int64_t)ow * sw) * C4 + c] = dy[t];
+    const int j = (int)(r % Wb);
+    r /= Wb;
+    const int i = (int)(r % Ha);
+    const int n = (int)(r / Ha);
+    dx[(((int64_t)n * H + a + (int64_t)i * sh) * W + b + (int64_t)j * sw) * C4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------ host side
-// im2col view of a channels-last activation [N,H,W,Cx]: box {32 channels, pixels_per_col output pixels};
-// window origins span [-pad, W+pad-KW] (step = conv stride), taps are given per load as {kw, kh} offsets.
-static bool make_map_im2col(CUtensorMap* m, const float* base, int N, int H, int W, int Cx, int KH, int KW, int sh,
-                            int sw, int pad, uint32_t pixels_per_col,
-                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int extra_w = 0, int extra_h = 0) {
+// im2col view of a channels-last activation [N,H,W,Cx]: box {32 channels, pixels_per_col window origins};
+// origins run over [lo_w, W - 1 + up_w] x [lo_h, H - 1 + up_h] in steps of the conv stride (taps are given per
+// load as {kw, kh} offsets from the origin; whatever falls outside the tensor reads as zero).
+static bool make_map_im2col(CUtensorMap* m, const float* base, int N, int H, int W, int Cx, int sh, int sw, int lo_h,
+                            int lo_w, int up_h, int up_w, uint32_t pixels_per_col,
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    if (lo_h < -128 || lo_w < -128 || up_h < -128 || up_w < -128 || lo_h > 127 || lo_w > 127 || up_h > 127 || up_w > 127)
+        return false;
     cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)Cx * 4, (cuuint64_t)W * Cx * 4, (cuuint64_t)H * W * Cx * 4};
-    int lower[2] = {-pad, -pad};
-    // extra_*: additional window origins past the symmetric-padding range (their taps read the zero OOB fill)
-    int upper[2] = {pad - (KW - 1) + extra_w, pad - (KH - 1) + extra_h};
+    int lower[2] = {lo_w, lo_h};
+    int upper[2] = {up_w, up_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
     CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower,
                                  upper, 32, pixels_per_col, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -612,42 +573,46 @@ static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const FpropP
     dim3 grid((p.M + BM - 1) / BM, n_tiles);
     conv_fprop_tc_k<BN, STAGES, OCC><<<grid, kThreads, smem, s>>>(a, b, p);
     XSB_LAUNCH_CHECK();
-    ++g_tc_launches;
     return XSB_OK;
 }
 
-// D[M, OCx] (+)= conv of channels-last `in` [N,H,W,Cx] with filter `flt` [OCx, KH*KW*Cx] (+ bias)
-static int fprop_dispatch(const float* in, const float* flt, const float* bias, float* out, int N, int H, int W, int Cx,
-                          int OCx, int KH, int KW, int sh, int sw, int pad, int OH, int OW, int accumulate,
-                          cudaStream_t s, int extra_w = 0, int extra_h = 0) {
+// One implicit-GEMM launch: D[(n,i,j), OCx] (+)= sum_{kh,kw,c} in[n, i*sh - pad_h + kh, j*sw - pad_w + kw, c] *
+// flt[ocx, kh, kw, c] (+ bias) over the OH x OW window origins of every image of channels-last `in` [N,H,W,Cx].
+struct FpropJob {
+    const float* in; int N, H, W, Cx;
+    const float* flt; int OCx, KH, KW, sh, sw, pad_h, pad_w, OH, OW;
+    const float* bias; float* out; int accumulate;
+    int o_strided, o_H, o_W, o_sh, o_sw, o_a, o_b;
+};
+
+static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
     if (!load_driver_entry_points()) {
         xsb_set_error("cuTensorMapEncode* entry points unavailable");
         return XSB_ERR_CUDA;
     }
-    int BN = (OCx % 256 == 0) ? 256 : (OCx % 128 == 0) ? 128 : 64;
-    {   // a 256-wide tile that leaves SMs idle loses to twice as many 128-wide CTAs (XSB_TC_NARROW=0 disables)
-        static const int narrow = [] { const char* e = getenv("XSB_TC_NARROW"); return (e && e[0] == '1') ? 1 : 0; }();   // measured slower on layer4: off
-        const int64_t ctas = (int64_t)((N * OH * OW + BM - 1) / BM) * (OCx / BN);
-        if (narrow && BN == 256 && ctas < xsb_sm_count_cached()) BN = 128;
-    }
+    int BN = (j.OCx % 256 == 0) ? 256 : (j.OCx % 128 == 0) ? 128 : 64;
+    // window origins: first at -pad, last such that exactly OH x OW of them exist
+    const int lo_h = -j.pad_h, lo_w = -j.pad_w;
+    const int up_h = lo_h + (j.OH - 1) * j.sh - (j.H - 1), up_w = lo_w + (j.OW - 1) * j.sw - (j.W - 1);
     CUtensorMap ta, tb;
-    if (!make_map_im2col(&ta, in, N, H, W, Cx, KH, KW, sh, sw, pad, BM, CU_TENSOR_MAP_SWIZZLE_128B, extra_w, extra_h) ||
-        !make_map_2d(&tb, flt, (uint64_t)OCx, (uint64_t)KH * KW * Cx, (uint32_t)BN)) {
-        xsb_set_error("cuTensorMapEncode failed (fprop N=%d H=%d W=%d C=%d OC=%d k=%dx%d s=%d p=%d)", N, H, W, Cx, OCx, KH,
-                      KW, sh, pad);
+    if (!make_map_im2col(&ta, j.in, j.N, j.H, j.W, j.Cx, j.sh, j.sw, lo_h, lo_w, up_h, up_w, BM) ||
+        !make_map_2d(&tb, j.flt, (uint64_t)j.OCx, (uint64_t)j.KH * j.KW * j.Cx, (uint32_t)BN)) {
+        xsb_set_error("cuTensorMapEncode failed (fprop N=%d H=%d W=%d C=%d OC=%d k=%dx%d s=%d p=%d,%d)", j.N, j.H, j.W,
+                      j.Cx, j.OCx, j.KH, j.KW, j.sh, j.pad_h, j.pad_w);
         return XSB_ERR_CUDA;
     }
-    FpropParams p{out, bias, N * OH * OW, OCx, Cx, KH, KW, OH, OW, sh, sw, pad, accumulate};
+    FpropParams p{j.out, j.bias, j.N * j.OH * j.OW, j.OCx, j.Cx, j.KH, j.KW, j.OH, j.OW, j.sh, j.sw, j.pad_h, j.pad_w,
+                  j.accumulate, j.o_strided, j.o_H, j.o_W, j.o_sh, j.o_sw, j.o_a, j.o_b};
     if (tc_occupancy() == 1) {
-        if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, OCx / 256, s);
-        if (BN == 128) return launch_fprop<128, 6, 1>(ta, tb, p, OCx / 128, s);
-        return launch_fprop<64, 8, 1>(ta, tb, p, OCx / 64, s);
+        if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, j.OCx / 256, s);
+        if (BN == 128) return launch_fprop<128, 6, 1>(ta, tb, p, j.OCx / 128, s);
+        return launch_fprop<64, 8, 1>(ta, tb, p, j.OCx / 64, s);
     }
     // measured on B200 (tests/op_bench.py, R224): 2 CTAs/SM is +45 % for BN=64 and +19 % for BN=128, but -25 % for
     // BN=256 (only 2 stages fit) -> the widest tile keeps one CTA per SM with a 4-stage ring
-    if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, OCx / 256, s);
-    if (BN == 128) return launch_fprop<128, 3, 2>(ta, tb, p, OCx / 128, s);
-    return launch_fprop<64, 4, 2>(ta, tb, p, OCx / 64, s);
+    if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, j.OCx / 256, s);
+    if (BN == 128) return launch_fprop<128, 3, 2>(ta, tb, p, j.OCx / 128, s);
+    return launch_fprop<64, 4, 2>(ta, tb, p, j.OCx / 64, s);
 }
 
 template <int BN, int BKP, int STAGES>
@@ -660,7 +625,6 @@ static int launch_wgrad(const CUtensorMap& x, const CUtensorMap& dy, const Wgrad
     }
     conv_wgrad_tc_k<BN, BKP, STAGES><<<grid, kThreads, smem, s>>>(x, dy, p);
     XSB_LAUNCH_CHECK();
-    ++g_tc_launches;
     return XSB_OK;
 }
 
@@ -705,31 +669,34 @@ static int stem_fwd(const float* x, const float* w, const float* bias, float* y,
                     int64_t ws_floats, cudaStream_t s) {
     const StemPlan pl = stem_plan(g);
     if (!ws || ws_floats < pl.xp_floats + pl.wq_floats) return XSB_ERR_UNSUPPORTED;
+    if ((g.OC != 64 && g.OC != 128) || g.KH > HALO_MAX_KH) return XSB_ERR_UNSUPPORTED;
+    const int rows = (HALO_TH - 1) * g.sh + g.KH;
+    const int stages = halo_stages(g.KH, g.OC, rows * 1024);
+    if (stages == 0 || rows > 256) return XSB_ERR_UNSUPPORTED;
     if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
     float* xp = ws;
     float* wq = ws + pl.xp_floats;
     CUtensorMap ta, tb;
-    if (!stem_map_x(&ta, xp, g, pl, STEM_TW, STEM_TH, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_map_2d(&tb, wq, (uint64_t)g.OC, (uint64_t)g.KH * 32, 64))
+    // rows of 32 floats starting every sw pixels: {32, OW, Hp, N} with OVERLAPPING dim-1 stride
+    cuuint64_t dims[4] = {32, (cuuint64_t)g.OW, (cuuint64_t)pl.Hp, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.sw * 16, (cuuint64_t)pl.Wp * 16, (cuuint64_t)pl.Hp * pl.Wp * 16};
+    cuuint32_t box[4] = {32, HALO_TW, (cuuint32_t)rows, 1};
+    if (!make_map_tiled(&ta, xp, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_map_2d(&tb, wq, (uint64_t)g.OC, (uint64_t)g.KH * 32, (uint32_t)g.OC))
         return XSB_ERR_UNSUPPORTED;   // driver rejected the overlapping-stride map: FFMA kernel takes the call
     int rc = stem_prepare(x, g, pl, xp, s);
     if (rc != XSB_OK) return rc;
     stem_pack_filter_k<<<(g.OC * g.KH * 32 + 255) / 256, 256, 0, s>>>(w, wq, g.OC, g.KH, g.KW, g.C);
     XSB_LAUNCH_CHECK();
-    StemParams p{y, bias, g.N, g.OH, g.OW, g.OC, g.KH, g.KW, g.C, (g.OW + STEM_TW - 1) / STEM_TW,
-                 (g.OH + STEM_TH - 1) / STEM_TH, 0, 0};
-    constexpr int STAGES = 4, BN = 64;
-    constexpr int smem = STAGES * (BM * A_ROW_BYTES + BN * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        XSB_CUDA(cudaFuncSetAttribute(stem_fprop_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
-    dim3 grid(g.N * p.tiles_w * p.tiles_h, g.OC / BN);
-    stem_fprop_tc_k<BN, STAGES><<<grid, kThreads, smem, s>>>(ta, tb, p);
-    XSB_LAUNCH_CHECK();
-    ++g_tc_launches;
-    return XSB_OK;
+    HaloParams p{};
+    p.out = y; p.bias = bias; p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.ldo = g.OC;
+    p.tiles_w = (g.OW + HALO_TW - 1) / HALO_TW; p.tiles_h = (g.OH + HALO_TH - 1) / HALO_TH;
+    p.n_tiles = g.N * p.tiles_w * p.tiles_h;
+    p.n_loads = 1; p.KH = g.KH; p.sh = g.sh; p.h_off = 0;
+    p.stage_bytes = rows * 1024; p.n_stages = stages; p.n_btiles = g.KH; p.accumulate = 0;
+    p.load_c[0] = 0; p.load_wofs[0] = 0;
+    for (int kh = 0; kh < g.KH; ++kh) p.btile[0][kh] = (uint8_t)kh;
+    return g.OC == 64 ? launch_halo<64>(ta, tb, p, s) : launch_halo<128>(ta, tb, p, s);
 }
 
 static int stem_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
@@ -769,7 +736,6 @@ static int stem_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
     dim3 grid(m_tiles, n_tiles, splits);
     stem_wgrad_tc_k<BN, STAGES><<<grid, kThreads, smem, s>>>(tx, tdy, p);
     XSB_LAUNCH_CHECK();
-    ++g_tc_launches;
     return XSB_OK;
 }
 
@@ -790,49 +756,110 @@ int xsb_tc_gemm(const float*, const float*, float*, const float*, int, int, int,
     return XSB_ERR_UNSUPPORTED;   // Dense layers of the hot path are < 1 % of the FLOPs: FFMA kernel
 }
 
-int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                    int64_t ws_floats, cudaStream_t s) {
+// XSB_TC_HALO=0 (env, read once) routes everything through the im2col kernel (A/B measurements)
+static bool halo_enabled() {
+    static const int on = [] { const char* e = getenv("XSB_TC_HALO"); return (e && e[0] == '0') ? 0 : 1; }();
+    return on != 0;
+}
+
+// g_tc_launches counts ENTRY-POINT calls served by tensor-core kernels (a strided dgrad is several launches)
+static int counted(int rc) {
+    if (rc == XSB_OK) ++g_tc_launches;
+    return rc;
+}
+
+static int tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
+                       int64_t ws_floats, cudaStream_t s) {
     if (stem_ok(g) && aligned16(x) && aligned16(w) && aligned16(y)) return stem_fwd(x, w, bias, y, g, ws, ws_floats, s);
     if (!fprop_ok(g.C, g.OC, x, w, y) || g.KW > 255 || g.KH > 255) return XSB_ERR_UNSUPPORTED;
-    return fprop_dispatch(x, w, bias, y, g.N, g.H, g.W, g.C, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.OH, g.OW, 0, s);
+    if (g.sh == 1 && g.sw == 1 && halo_enabled()) {
+        const int rc = halo_conv_s1(x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.pad, g.pad, g.OH, g.OW, bias, y, 0, s);
+        if (rc != XSB_ERR_UNSUPPORTED) return rc;
+    }
+    const FpropJob j{x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, bias, y, 0,
+                     0, 0, 0, 1, 1, 0, 0};
+    return fprop_dispatch(j, s);
+}
+
+int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
+                    int64_t ws_floats, cudaStream_t s) {
+    return counted(tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s));
+}
+
+static int tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
+                         int64_t ws_floats, cudaStream_t s) {
+    // see gather_subfilters_k: one stride-1 convolution of dY per parity class of dX
+    if (!fprop_ok(g.OC, g.C, dy, w, dx)) return XSB_ERR_UNSUPPORTED;
+    const int taps = g.KH * g.KW;
+    const int64_t wn = (int64_t)g.OC * taps * g.C;
+    if (taps > 64 || g.sh > 8 || g.sw > 8 || wn >= ((int64_t)1 << 31) || !ws || ws_floats < wn) return XSB_ERR_UNSUPPORTED;
+    struct Cls { int r, T, padp, n; };   // first tap, #taps, padding of the equivalent conv, #rows (cols) of dX
+    Cls ch[8], cw[8];
+    for (int a = 0; a < g.sh; ++a) {
+        const int r = (a + g.pad) % g.sh, T = g.KH > r ? (g.KH - r + g.sh - 1) / g.sh : 0;
+        ch[a] = {r, T, T - 1 - (a + g.pad - r) / g.sh, g.H > a ? (g.H - a + g.sh - 1) / g.sh : 0};
+    }
+    for (int b = 0; b < g.sw; ++b) {
+        const int r = (b + g.pad) % g.sw, T = g.KW > r ? (g.KW - r + g.sw - 1) / g.sw : 0;
+        cw[b] = {r, T, T - 1 - (b + g.pad - r) / g.sw, g.W > b ? (g.W - b + g.sw - 1) / g.sw : 0};
+    }
+    // sub-filters packed back to back: class (a,b) at cls_base[a][b], [C, T_a*T_b, OC] each (offsets stay 16-byte
+    // aligned because C*OC is a multiple of 32*64)
+    int64_t cls_base[8][8];
+    int64_t off = 0;
+    for (int a = 0; a < g.sh; ++a)
+        for (int b = 0; b < g.sw; ++b) {
+            cls_base[a][b] = off;
+            off += (int64_t)g.C * ch[a].T * cw[b].T * g.OC;
+        }
+    TapPlace tp;
+    for (int kh = 0; kh < g.KH; ++kh)
+        for (int kw = 0; kw < g.KW; ++kw) {
+            const int ra = kh % g.sh, rb = kw % g.sw;
+            const int a = ((ra - g.pad) % g.sh + g.sh) % g.sh, b = ((rb - g.pad) % g.sw + g.sw) % g.sw;
+            const int ua = ch[a].T - 1 - kh / g.sh, ub = cw[b].T - 1 - kw / g.sw;
+            const int t = kh * g.KW + kw;
+            tp.base[t] = (int)cls_base[a][b];
+            tp.pos[t] = ua * cw[b].T + ub;
+            tp.ntaps[t] = ch[a].T * cw[b].T;
+        }
+    dim3 grid((g.C + 31) / 32, (g.OC + 31) / 32, taps), block(32, 8);
+    gather_subfilters_k<<<grid, block, 0, s>>>(w, ws, g.OC, taps, g.C, tp);
+    XSB_LAUNCH_CHECK();
+    const int strided = (g.sh != 1 || g.sw != 1) ? 1 : 0;
+    for (int a = 0; a < g.sh; ++a)
+        for (int b = 0; b < g.sw; ++b) {
+            const int Ha = ch[a].n, Wb = cw[b].n;
+            if (Ha == 0 || Wb == 0) continue;
+            if (ch[a].T == 0 || cw[b].T == 0) {      // no filter tap reaches this class: its gradient is zero
+                if (!accumulate) {
+                    const int64_t total = (int64_t)g.N * Ha * Wb * (g.C / 4);
+                    zero_class_k<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(reinterpret_cast<float4*>(dx), Ha, Wb,
+                                                                                 g.C / 4, g.H, g.W, g.sh, g.sw, a, b, total);
+                    XSB_LAUNCH_CHECK();
+                }
+                continue;
+            }
+            if (!strided && halo_enabled()) {
+                const int rc = halo_conv_s1(dy, g.N, g.OH, g.OW, g.OC, ws, g.C, g.KH, g.KW, ch[0].padp, cw[0].padp, g.H, g.W,
+                                            nullptr, dx, accumulate, s);
+                if (rc != XSB_ERR_UNSUPPORTED) return rc;
+            }
+            const FpropJob j{dy, g.N, g.OH, g.OW, g.OC, ws + cls_base[a][b], g.C, ch[a].T, cw[b].T, 1, 1, ch[a].padp,
+                             cw[b].padp, Ha, Wb, nullptr, dx, accumulate, strided, g.H, g.W, g.sh, g.sw, a, b};
+            const int rc = fprop_dispatch(j, s);
+            if (rc != XSB_OK) return rc;
+        }
+    return XSB_OK;
 }
 
 int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
                       int64_t ws_floats, cudaStream_t s) {
-    // dX = conv_stride1(dY (zero-inserted when the forward conv was strided), flip/transpose(w)), pad' = K-1-pad
-    if (g.pad > g.KH - 1 || g.pad > g.KW - 1 || g.KH != g.KW) return XSB_ERR_UNSUPPORTED;
-    if (!fprop_ok(g.OC, g.C, dy, w, dx)) return XSB_ERR_UNSUPPORTED;
-    const int64_t wn = (int64_t)g.OC * g.KH * g.KW * g.C;
-    const bool strided = g.sh != 1 || g.sw != 1;
-    const int Hu = (g.OH - 1) * g.sh + 1, Wu = (g.OW - 1) * g.sw + 1;
-    const int64_t un = strided ? (int64_t)g.N * Hu * Wu * g.OC : 0;
-    const int64_t wn_al = (wn + 255) / 256 * 256;
-    if (!ws || ws_floats < wn_al + un) return XSB_ERR_UNSUPPORTED;
-    const int taps = g.KH * g.KW;
-    dim3 grid((g.C + 31) / 32, (g.OC + 31) / 32, taps), block(32, 8);
-    flip_transpose_filter_k<<<grid, block, 0, s>>>(w, ws, g.OC, taps, g.C);
-    XSB_LAUNCH_CHECK();
-    const int padp = g.KH - 1 - g.pad;
-    const float* src = dy;
-    if (strided) {
-        float* up = ws + wn_al;
-        XSB_CUDA(cudaMemsetAsync(up, 0, (size_t)un * sizeof(float), s));
-        const int64_t total = (int64_t)g.N * g.OH * g.OW * (g.OC / 4);
-        zero_insert_k<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(dy),
-                                                                      reinterpret_cast<float4*>(up), g.OH, g.OW,
-                                                                      g.OC / 4, Hu, Wu, g.sh, g.sw, total);
-        XSB_LAUNCH_CHECK();
-        src = up;
-    }
-    // rows/cols of dX past the last forward window get no gradient: extend the im2col box so they are produced (as 0)
-    const int extra_h = g.H - (Hu + 2 * padp - g.KH + 1), extra_w = g.W - (Wu + 2 * padp - g.KW + 1);
-    if (extra_h < 0 || extra_w < 0 || extra_h > 64 || extra_w > 64) return XSB_ERR_UNSUPPORTED;
-    return fprop_dispatch(src, ws, nullptr, dx, g.N, strided ? Hu : g.OH, strided ? Wu : g.OW, g.OC, g.C, g.KH, g.KW, 1, 1,
-                          padp, g.H, g.W, accumulate, s, extra_w, extra_h);
+    return counted(tc_conv_dgrad(dy, w, dx, g, accumulate, ws, ws_floats, s));
 }
 
-int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
-                      int64_t ws_floats, cudaStream_t s) {
+static int tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
+                         int64_t ws_floats, cudaStream_t s) {
     if (stem_ok(g) && aligned16(dy) && aligned16(x)) return stem_wgrad(dy, x, dw, g, accumulate, ws, ws_floats, s);
     if (g.C % 32 != 0 || g.OC % 64 != 0 || !aligned16(dy) || !aligned16(x) || !aligned16(dw)) return XSB_ERR_UNSUPPORTED;
     if (!load_driver_entry_points()) {
@@ -845,8 +872,8 @@ int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
     if (BN > wg_bn_cap) BN = wg_bn_cap;
     const int BKP = BN == 256 ? 32 : 64;
     CUtensorMap tx, tdy;
-    if (!make_map_im2col(&tx, x, g.N, g.H, g.W, g.C, g.KH, g.KW, g.sh, g.sw, g.pad, (uint32_t)BKP,
-                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+    if (!make_map_im2col(&tx, x, g.N, g.H, g.W, g.C, g.sh, g.sw, -g.pad, -g.pad, g.pad - (g.KH - 1), g.pad - (g.KW - 1),
+                         (uint32_t)BKP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
         !make_map_2d(&tdy, dy, (uint64_t)P, (uint64_t)g.OC, (uint32_t)BKP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
         xsb_set_error("cuTensorMapEncode failed (wgrad)");
         return XSB_ERR_CUDA;
@@ -870,8 +897,13 @@ int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
     return launch_wgrad<64, 64, 4>(tx, tdy, p, grid, s);
 }
 
+int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
+                      int64_t ws_floats, cudaStream_t s) {
+    return counted(tc_conv_wgrad(dy, x, dw, g, accumulate, ws, ws_floats, s));
+}
+
 extern "C" {
-// counters: [0] tensor-core kernel launches, [1] GEMM-shaped calls that ran the fp32 FFMA kernel in TF32 mode
+// counters: [0] GEMM-shaped calls served by tensor-core kernels, [1] GEMM-shaped calls that ran the fp32 FFMA kernel in TF32 mode
 int xsb_tc_stats(uint64_t* out2) {
     out2[0] = tc::g_tc_launches;
     out2[1] = tc::g_ffma_fallbacks;

@@ -32,6 +32,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// One lane of the (converged) warp gets `true`. ptxas knows an elect.sync-guarded region runs on a single lane and keeps
+// TMA / tcgen05 operands in uniform registers; guarding with `lane == 0` instead makes it wrap every UTMALDG / UTCHMMA
+// in a vote + branch "waterfall" loop (measured: ~130 clk per MMA issued, i.e. the issue thread became the bottleneck).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xFFFFFFFF;\n"
+        "selp.b32 %0, 1, 0, px;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
