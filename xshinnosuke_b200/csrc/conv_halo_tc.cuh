@@ -21,32 +21,36 @@
 namespace tc {
 
 constexpr int HALO_TW = 8, HALO_TH = 16;
-constexpr int HALO_MAX_LOADS = 16, HALO_MAX_KH = 8;
+constexpr int HALO_MAX_KH = 8;
+constexpr int HALO_OUT_BYTES = 4 * 4096;
 
 struct HaloParams {
     float* out;              // [N, OH, OW, ldo]
     const float* bias;       // [ldo] or null
     int N, OH, OW, ldo;
     int tiles_w, tiles_h, n_tiles;
-    int n_loads, KH, sh;
+    // per tile: cblocks x KWl loads (channel block cb, filter column kw), each followed by KH k-blocks (filter rows);
+    // load (cb, kw) has TMA coordinates {cb*32, w0 + kw - pad_w, h0, n}; k-block kh multiplies the view at stage +
+    // kh*1024 with resident filter tile kh*bt_kh_stride + kw*cblocks + cb
+    int cblocks, KWl, KH, sh, pad_w, bt_kh_stride;
     int h_off;               // TMA row coordinate of output row 0, filter row 0 (= -pad, or 0 for a pre-padded image)
     int stage_bytes, n_stages, n_btiles;
     int accumulate;
-    int load_c[HALO_MAX_LOADS];       // TMA coordinate 0 (k-element offset) of load l
-    int load_wofs[HALO_MAX_LOADS];    // TMA coordinate 1 offset (filter column - pad) of load l
-    uint8_t btile[HALO_MAX_LOADS][HALO_MAX_KH];   // resident filter tile multiplied with (load l, filter row kh)
 };
 
-template <int BN>
+// KH_T > 0: filter height known at compile time (k-block loop fully unrolled); 0: runtime p.KH
+template <int BN, int KH_T>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int B_TILE = BN * A_ROW_BYTES;
     constexpr int MAXS = 8;
     uint8_t* smem = align1024(smem_raw);
     uint8_t* sB = smem;
     uint8_t* sA = smem + p.n_btiles * B_TILE;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.n_stages * p.stage_bytes);
+    uint8_t* sOut = sA + p.n_stages * p.stage_bytes;      // 4 x 4 KB: one SWIZZLE_128B staging block per epilogue warp
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + HALO_OUT_BYTES);
     uint64_t* empty = full + MAXS;
     uint64_t* bfull = empty + MAXS;
     uint64_t* tmem_full = bfull + 1;    // [2]
@@ -55,10 +59,12 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.n_stages;
+    const int KH = KH_T > 0 ? KH_T : p.KH;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        prefetch_tmap(&tmO);
         for (int i = 0; i < S; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
@@ -92,16 +98,17 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         const int step_img = gridDim.x / tiles_per_img, step_rem = gridDim.x - step_img * tiles_per_img;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int w0 = tw * HALO_TW, h0 = th * HALO_TH * p.sh + p.h_off;
-            for (int l = 0; l < p.n_loads; ++l) {
-                mbar_wait(&empty[s], ph ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(&full[s], p.stage_bytes);
-                    tma_load_4d(sA + s * p.stage_bytes, &tmA, &full[s], p.load_c[l], w0 + p.load_wofs[l], h0, n_img);
+            const int w0 = tw * HALO_TW - p.pad_w, h0 = th * HALO_TH * p.sh + p.h_off;
+            for (int cb = 0; cb < p.cblocks; ++cb)
+                for (int kw = 0; kw < p.KWl; ++kw) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[s], p.stage_bytes);
+                        tma_load_4d(sA + s * p.stage_bytes, &tmA, &full[s], cb * 32, w0 + kw, h0, n_img);
+                    }
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
-                if (++s == S) { s = 0; ph ^= 1; }
-            }
-            // next tile of this CTA: (n_img, th, tw) += gridDim.x tiles, without divisions
+            // next tile of this CTA: (n_img, th, tw) += gridDim.x tiles
             rem += step_rem;
             n_img += step_img;
             if (rem >= tiles_per_img) { rem -= tiles_per_img; ++n_img; }
@@ -110,31 +117,49 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-        const uint32_t a_sbo = (uint32_t)p.sh * 1024;
+        constexpr uint32_t B_ENC = B_TILE >> 4;
+        // descriptors as {lo = start address | LBO, hi = SBO | version | layout}: only lo moves
+        const uint32_t a_hi = desc_hi((uint32_t)p.sh * 1024, kLayoutSW128), b_hi = desc_hi(1024, kLayoutSW128);
+        const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16), b_lo0 = desc_lo(smem_u32(sB), 16);
+        const uint32_t stage_enc = (uint32_t)p.stage_bytes >> 4;
+        const uint32_t bt_kh_enc = (uint32_t)p.bt_kh_stride * B_ENC;
         mbar_wait(bfull, 0);
         int s = 0, buf = 0;
-        uint32_t ph = 0, tph = 0;
+        uint32_t ph = 0, tph = 0, a_lo_s = a_lo0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&tmem_empty[buf], tph ^ 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-            for (int l = 0; l < p.n_loads; ++l) {
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a0 = a_base + s * p.stage_bytes;
-                    for (int kh = 0; kh < p.KH; ++kh) {
-                        const uint64_t da = make_desc(a0 + kh * 1024, 16, a_sbo);
-                        const uint64_t db = make_desc(b_base + p.btile[l][kh] * B_TILE, 16, 1024);
+            uint32_t fresh = 0;   // 0 for the first MMA of the tile (overwrite the accumulator), 1 afterwards
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+                uint32_t b_lo_l = b_lo0 + (uint32_t)cb * B_ENC;
+                for (int kw = 0; kw < p.KWl; ++kw, b_lo_l += (uint32_t)p.cblocks * B_ENC) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (KH_T > 0) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (l | kh | k) != 0);
+                            for (int kh = 0; kh < (KH_T > 0 ? KH_T : 1); ++kh)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_tf32_split(tacc, a_lo_s + (uint32_t)(kh * 64 + k * 2), a_hi,
+                                                    b_lo_l + (uint32_t)kh * bt_kh_enc + (uint32_t)(k * 2), b_hi, idesc,
+                                                    (kh | k) ? 1u : fresh);
+                        } else {
+                            for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_tf32_split(tacc, a_lo_s + (uint32_t)(kh * 64 + k * 2), a_hi,
+                                                    b_lo_l + (uint32_t)kh * bt_kh_enc + (uint32_t)(k * 2), b_hi, idesc,
+                                                    (kh | k) ? 1u : fresh);
+                        }
+                        umma_commit(&empty[s]);
                     }
-                    umma_commit(&empty[s]);
+                    __syncwarp();
+                    fresh = 1;
+                    a_lo_s += stage_enc;
+                    if (++s == S) { s = 0; ph ^= 1; a_lo_s = a_lo0; }
                 }
-                __syncwarp();
-                if (++s == S) { s = 0; ph ^= 1; }
             }
             if (elect_one()) umma_commit(&tmem_full[buf]);
             __syncwarp();
@@ -142,17 +167,18 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (buf == 0) tph ^= 1;
         }
     } else {
+        // epilogue warp q owns accumulator rows 32q..32q+31 = output rows 4q..4q+3 of the tile (8 pixels each): TMEM ->
+        // registers (+bias) -> swizzled staging block -> ONE TMA store (or reduce-add) of a {32 ch, 8 w, 4 h} box; the
+        // tensor map clips rows / columns past the image, so partial tiles need no predication
         const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int r = row / HALO_TW, jw = row % HALO_TW;
+        uint8_t* stage = sOut + q * 4096;
         int buf = 0;
         uint32_t tph = 0;
+        int n_img = blockIdx.x / tiles_per_img, rem = blockIdx.x - n_img * tiles_per_img;
+        const int step_img = gridDim.x / tiles_per_img, step_rem = gridDim.x - step_img * tiles_per_img;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int n_img = tile / tiles_per_img, rem = tile - n_img * tiles_per_img;
             const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-            const int oh = th * HALO_TH + r, ow = tw * HALO_TW + jw;
-            const bool valid = oh < p.OH && ow < p.OW;
-            float* orow = p.out + (((int64_t)n_img * p.OH + oh) * p.OW + ow) * p.ldo;
+            const int oh0 = th * HALO_TH + q * 4, ow0 = tw * HALO_TW;
             mbar_wait(&tmem_full[buf], tph);
             tc_fence_after();
 #pragma unroll 1
@@ -160,22 +186,27 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
                 tmem_wait_ld();
-                if (valid) {
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+                if (p.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                               __uint_as_float(v[j + 3]));
-                        if (p.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
-                        if (p.accumulate) {
-                            const float4 e = *dst;
-                            o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-                        }
-                        *dst = o;
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                        o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
                     }
+                }
+                if (lane == 0) bulk_wait_read<0>();     // the previous store has finished reading the staging block
+                __syncwarp();
+                stage_rows_sw128(stage, lane, o);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && oh0 < p.OH) {
+                    if (p.accumulate)
+                        tma_reduce_add_4d(&tmO, stage, c0, ow0, oh0, n_img);
+                    else
+                        tma_store_4d(&tmO, stage, c0, ow0, oh0, n_img);
+                    bulk_commit();
                 }
             }
             tc_fence_before();
@@ -183,7 +214,11 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             buf ^= 1;
             if (buf == 0) tph ^= 1;
+            rem += step_rem;
+            n_img += step_img;
+            if (rem >= tiles_per_img) { rem -= tiles_per_img; ++n_img; }
         }
+        if (lane == 0) bulk_wait_all<0>();   // global writes complete before the CTA exits
     }
     __syncthreads();
     if (warp == 1) {
@@ -194,27 +229,46 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 constexpr int HALO_SMEM_MAX = 227 * 1024;
 
+
 // -> number of A stages that fit next to the resident filter (0: does not fit)
 static int halo_stages(int n_btiles, int BN, int stage_bytes) {
-    const int fixed = 1024 + n_btiles * BN * A_ROW_BYTES + 256;
+    const int fixed = 1024 + n_btiles * BN * A_ROW_BYTES + HALO_OUT_BYTES + 256;
     int s = (HALO_SMEM_MAX - fixed) / stage_bytes;
     if (s > 6) s = 6;
     return s >= 2 ? s : 0;
 }
 
-template <int BN>
-static int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HaloParams& p, cudaStream_t s) {
-    const int smem = 1024 + p.n_btiles * BN * A_ROW_BYTES + p.n_stages * p.stage_bytes + 256;
-    static int configured = 0;
-    if (configured < smem) {
-        XSB_CUDA(cudaFuncSetAttribute(conv_halo_tc_k<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX));
-        configured = HALO_SMEM_MAX;
+template <int BN, int KH_T>
+static int launch_halo_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const HaloParams& p,
+                         cudaStream_t s) {
+    const int smem = 1024 + p.n_btiles * BN * A_ROW_BYTES + p.n_stages * p.stage_bytes + HALO_OUT_BYTES + 256;
+    static bool configured = false;
+    if (!configured) {
+        XSB_CUDA(cudaFuncSetAttribute(conv_halo_tc_k<BN, KH_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX));
+        configured = true;
     }
     int grid = xsb_sm_count_cached();
     if (grid > p.n_tiles) grid = p.n_tiles;
-    conv_halo_tc_k<BN><<<grid, kThreads, smem, s>>>(a, b, p);
+    conv_halo_tc_k<BN, KH_T><<<grid, kThreads, smem, s>>>(a, b, o, p);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
+}
+
+// output tensor [N, OH, OW, OC] as a TMA-store target: box {32 ch, 8 w, 4 h} (one epilogue warp's rows)
+static bool halo_out_map(CUtensorMap* m, float* out, int N, int OH, int OW, int OC) {
+    cuuint64_t dims[4] = {(cuuint64_t)OC, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)OC * 4, (cuuint64_t)OW * OC * 4, (cuuint64_t)OH * OW * OC * 4};
+    cuuint32_t box[4] = {32, HALO_TW, 4, 1};
+    return make_map_tiled(m, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int BN>
+static int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HaloParams& p, cudaStream_t s) {
+    CUtensorMap o;
+    if (!halo_out_map(&o, p.out, p.N, p.OH, p.OW, p.ldo)) return XSB_ERR_UNSUPPORTED;
+    if (p.KH == 3) return launch_halo_t<BN, 3>(a, b, o, p, s);
+    if (p.KH == 7) return launch_halo_t<BN, 7>(a, b, o, p, s);
+    return launch_halo_t<BN, 0>(a, b, o, p, s);
 }
 
 // Generic stride-1 path: conv of channels-last in[N,H,W,Cx] with flt[OCx, KH*KW*Cx] -> out[N,OH,OW,OCx].
@@ -222,9 +276,8 @@ static int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HaloPar
 static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const float* flt, int OCx, int KH, int KW, int pad_h,
                         int pad_w, int OH, int OW, const float* bias, float* out, int accumulate, cudaStream_t s) {
     const int cblocks = Cx / 32;
-    if (Cx % 32 != 0 || (OCx != 64 && OCx != 128) || KH > HALO_MAX_KH || cblocks * KW > HALO_MAX_LOADS) return XSB_ERR_UNSUPPORTED;
+    if (Cx % 32 != 0 || (OCx != 64 && OCx != 128) || KH > HALO_MAX_KH) return XSB_ERR_UNSUPPORTED;
     const int n_btiles = KH * KW * cblocks;
-    if (n_btiles > 255) return XSB_ERR_UNSUPPORTED;
     const int rows = HALO_TH - 1 + KH;
     const int stage_bytes = rows * 1024;
     const int stages = halo_stages(n_btiles, OCx, stage_bytes);
@@ -243,15 +296,9 @@ static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const floa
     HaloParams p{};
     p.out = out; p.bias = bias; p.N = N; p.OH = OH; p.OW = OW; p.ldo = OCx;
     p.tiles_w = tiles_w; p.tiles_h = tiles_h; p.n_tiles = N * tiles_w * tiles_h;
-    p.n_loads = cblocks * KW; p.KH = KH; p.sh = 1; p.h_off = -pad_h;
+    p.cblocks = cblocks; p.KWl = KW; p.KH = KH; p.sh = 1; p.pad_w = pad_w; p.bt_kh_stride = KW * cblocks;
+    p.h_off = -pad_h;
     p.stage_bytes = stage_bytes; p.n_stages = stages; p.n_btiles = n_btiles; p.accumulate = accumulate;
-    for (int cb = 0; cb < cblocks; ++cb)
-        for (int kw = 0; kw < KW; ++kw) {
-            const int l = cb * KW + kw;
-            p.load_c[l] = cb * 32;
-            p.load_wofs[l] = kw - pad_w;
-            for (int kh = 0; kh < KH; ++kh) p.btile[l][kh] = (uint8_t)((kh * KW + kw) * cblocks + cb);
-        }
     return OCx == 64 ? launch_halo<64>(ta, tb, p, s) : launch_halo<128>(ta, tb, p, s);
 }
 
