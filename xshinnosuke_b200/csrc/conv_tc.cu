@@ -35,7 +35,8 @@ struct FpropParams {
 
 template <int BN, int STAGES, int OCC>
 __global__ void __launch_bounds__(kThreads, OCC)
-conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropParams p) {
+conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const FpropParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int A_BYTES = BM * A_ROW_BYTES;
     constexpr int B_BYTES = BN * A_ROW_BYTES;
@@ -117,34 +118,67 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        int64_t pix = m;
-        if (p.o_strided) {
+        if (!p.o_strided) {
+            // every MMA has completed, so the operand ring is idle: its first 16 KB become four SWIZZLE_128B staging
+            // blocks (one per epilogue warp); a warp's 32 rows x 32 columns leave as ONE TMA store / reduce-add of a
+            // {32 ch, 32 pixel} box of out[M, ldo] (rows >= M are clipped by the tensor map)
+            uint8_t* stage = sA + q * 4096;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                tmem_wait_ld();
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                        o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+                    }
+                }
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                stage_rows_sw128(stage, lane, o);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && m0 + q * 32 < p.M) {
+                    if (p.accumulate)
+                        tma_reduce_add_2d(&tmO, stage, n0 + c0, m0 + q * 32);
+                    else
+                        tma_store_2d(&tmO, stage, n0 + c0, m0 + q * 32);
+                    bulk_commit();
+                }
+            }
+            if (lane == 0) bulk_wait_all<0>();
+        } else {
             const int hw = p.OH * p.OW;
             const int n_img = m / hw, rem = m - n_img * hw;
-            const int i = rem / p.OW, j = rem - i * p.OW;
-            pix = ((int64_t)n_img * p.o_H + p.o_a + i * p.o_sh) * p.o_W + p.o_b + j * p.o_sw;
-        }
-        float* orow = p.out + pix * p.ldo + n0;
+            const int i = rem / p.OW, j2 = rem - i * p.OW;
+            const int64_t pix = ((int64_t)n_img * p.o_H + p.o_a + i * p.o_sh) * p.o_W + p.o_b + j2 * p.o_sw;
+            float* orow = p.out + pix * p.ldo + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_wait_ld();
-            if (m < p.M) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                tmem_wait_ld();
+                if (m < p.M) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                           __uint_as_float(r[j + 3]));
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        if (p.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
+                        if (p.accumulate) {
+                            const float4 o = *dst;
+                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        }
+                        *dst = v;
                     }
-                    float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
-                    if (p.accumulate) {
-                        const float4 o = *dst;
-                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                    }
-                    *dst = v;
                 }
             }
         }
@@ -563,7 +597,8 @@ static int tc_occupancy() {
 }
 
 template <int BN, int STAGES, int OCC>
-static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const FpropParams& p, int n_tiles, cudaStream_t s) {
+static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const FpropParams& p, int n_tiles,
+                        cudaStream_t s) {
     constexpr int smem = STAGES * (BM * A_ROW_BYTES + BN * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
@@ -571,7 +606,7 @@ static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const FpropP
         configured = true;
     }
     dim3 grid((p.M + BM - 1) / BM, n_tiles);
-    conv_fprop_tc_k<BN, STAGES, OCC><<<grid, kThreads, smem, s>>>(a, b, p);
+    conv_fprop_tc_k<BN, STAGES, OCC><<<grid, kThreads, smem, s>>>(a, b, o, p);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }
@@ -603,16 +638,21 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
     }
     FpropParams p{j.out, j.bias, j.N * j.OH * j.OW, j.OCx, j.Cx, j.KH, j.KW, j.OH, j.OW, j.sh, j.sw, j.pad_h, j.pad_w,
                   j.accumulate, j.o_strided, j.o_H, j.o_W, j.o_sh, j.o_sw, j.o_a, j.o_b};
+    CUtensorMap to = ta;   // unused by strided-destination launches
+    if (!j.o_strided && !make_map_2d(&to, j.out, (uint64_t)p.M, (uint64_t)j.OCx, 32)) {
+        xsb_set_error("cuTensorMapEncode failed (fprop output M=%d OC=%d)", p.M, j.OCx);
+        return XSB_ERR_CUDA;
+    }
     if (tc_occupancy() == 1) {
-        if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, j.OCx / 256, s);
-        if (BN == 128) return launch_fprop<128, 6, 1>(ta, tb, p, j.OCx / 128, s);
-        return launch_fprop<64, 8, 1>(ta, tb, p, j.OCx / 64, s);
+        if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, to, p, j.OCx / 256, s);
+        if (BN == 128) return launch_fprop<128, 6, 1>(ta, tb, to, p, j.OCx / 128, s);
+        return launch_fprop<64, 8, 1>(ta, tb, to, p, j.OCx / 64, s);
     }
     // measured on B200 (tests/op_bench.py, R224): 2 CTAs/SM is +45 % for BN=64 and +19 % for BN=128, but -25 % for
     // BN=256 (only 2 stages fit) -> the widest tile keeps one CTA per SM with a 4-stage ring
-    if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, p, j.OCx / 256, s);
-    if (BN == 128) return launch_fprop<128, 3, 2>(ta, tb, p, j.OCx / 128, s);
-    return launch_fprop<64, 4, 2>(ta, tb, p, j.OCx / 64, s);
+    if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, to, p, j.OCx / 256, s);
+    if (BN == 128) return launch_fprop<128, 3, 2>(ta, tb, to, p, j.OCx / 128, s);
+    return launch_fprop<64, 4, 2>(ta, tb, to, p, j.OCx / 64, s);
 }
 
 template <int BN, int BKP, int STAGES>
