@@ -99,6 +99,19 @@ int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float*
                int acc_dx, int acc_dgamma, int acc_dbeta, const uint8_t* relu_mask /* nullable */, float* ws,
                void* stream);
 
+/* xsb_bn_bwd that also gathers dxsum[c] (+)= sum_r dx_contribution[r,c] while dx is written: the bias gradient of the
+ * convolution feeding this BatchNorm (xs/nn/grad_fn.py:196-197 without a second pass over dx). *dxsum_done (HOST int)
+ * = 1 when produced, 0 when the shape ran the generic kernels (then call xsb_colsum). */
+int xsb_bn_bwd_dxsum(const float* dy, const float* x, const float* gamma, const float* save_mean,
+                     const float* save_invstd, float* dx, float* dgamma /* nullable */, float* dbeta /* nullable */,
+                     int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
+                     const uint8_t* relu_mask /* nullable */, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done,
+                     void* stream);
+/* batch statistics from the per-CTA (count, mean, M2) partials a convolution's epilogue left (xsb_conv2d_fwd_stats):
+ * same outputs and running-statistics update as xsb_bn_stats (xs/nn/functional.py:689-706), no pass over x. */
+int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* running_mean, float* running_var,
+                    float* save_mean, float* save_invstd, float eps, float momentum, void* stream);
+
 /* ---- out[c] (+)= sum_r x[r,c]: conv / Dense bias gradient. replaces xs/nn/grad_fn.py:196-197, 89-95 ---- */
 int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, float* ws, void* stream);
 
@@ -113,6 +126,11 @@ int xsb_gemm(const float* A, const float* B, float* C, const float* bias /* null
 int xsb_conv2d_fwd(const float* x, const float* w, const float* bias /* nullable */, float* y, int N, int H, int W,
                    int C, int OC, int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws, int64_t ws_floats,
                    void* stream);
+/* forward conv that also leaves BatchNorm partial statistics of y in stats[p][3][OC] (tensor-core kernels only);
+ * *n_partials (HOST int) = p, or 0 when the kernel that served the call gathers none -> use xsb_bn_stats then. */
+int xsb_conv2d_fwd_stats(const float* x, const float* w, const float* bias /* nullable */, float* y, int N, int H, int W,
+                         int C, int OC, int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws,
+                         int64_t ws_floats, float* stats, int64_t stats_floats, int* n_partials, void* stream);
 int xsb_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int C, int OC, int KH, int KW,
                      int sh, int sw, int pad, int accumulate, int math_mode, float* ws, int64_t ws_floats,
                      void* stream);

@@ -195,6 +195,29 @@ class FakeLib:
             d = f32(gamma, C).astype(np.float64) * f32(sinv, C) * (g - sdy / R - xhat * sdyx / R)
             _store(f32(dx, R * C).reshape(R, C), d, acc_dx)
 
+    def _bn_bwd_dxsum(self, dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, rmask, ws,
+                      dxsum, acc_dxsum, done, s):
+        # contract: dxsum (+)= column sums of the dx CONTRIBUTION; done (host int) = 1
+        before = f32(dx, R * C).reshape(R, C).astype(np.float64).copy() if acc_dx else 0.0
+        self._bn_bwd(dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, rmask, ws, s)
+        contrib = f32(dx, R * C).reshape(R, C).astype(np.float64) - before
+        _store(f32(dxsum, C), contrib.sum(axis=0), acc_dxsum)
+        done._obj.value = 1
+
+    def _bn_finalize(self, part, P, R, C, rm, rv, smean, sinv, eps, mom, s):
+        pv = f32(part, P * 3 * C).reshape(P, 3, C).astype(np.float64)
+        n, mean, m2 = pv[:, 0], pv[:, 1], pv[:, 2]
+        tot = n.sum(axis=0)
+        gm = (n * mean).sum(axis=0) / tot
+        var = (m2 + n * (mean - gm) ** 2).sum(axis=0) / R
+        assert np.all(tot == R)
+        f32(smean, C)[...] = gm
+        f32(sinv, C)[...] = 1.0 / np.sqrt(var + eps)
+        if rm:
+            f32(rm, C)[...] = mom * f32(rm, C).astype(np.float64) + (1 - mom) * gm
+        if rv:
+            f32(rv, C)[...] = mom * f32(rv, C).astype(np.float64) + (1 - mom) * var
+
     def _colsum(self, x, out, R, C, acc, ws, s):
         _store(f32(out, C), f32(x, R * C).reshape(R, C).astype(np.float64).sum(axis=0), acc)
 
@@ -216,6 +239,24 @@ class FakeLib:
         yv, _ = X.conv2d_fwd(self._nchw(x, N, H, W, C).astype(np.float64), self._w_oihw(w, OC, KH, KW, C).astype(np.float64),
                              b, (sh, sw), pad)
         f32(y, yv.size)[...] = yv.transpose(0, 2, 3, 1).reshape(-1)
+
+    def _conv2d_fwd_stats(self, x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, stats, stats_n,
+                          n_partials, s):
+        # contract: y as xsb_conv2d_fwd; stats[p][{n, mean, M2}][OC] partials (two here, split over the rows)
+        self._conv2d_fwd(x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, s)
+        OH, OW = (H - KH + 2 * pad) // sh + 1, (W - KW + 2 * pad) // sw + 1
+        R = N * OH * OW
+        yv = f32(y, R * OC).reshape(R, OC).astype(np.float64)
+        halves = [yv[: R // 2], yv[R // 2:]] if R > 1 else [yv]
+        if stats_n < len(halves) * 3 * OC:
+            n_partials._obj.value = 0
+            return
+        pv = f32(stats, len(halves) * 3 * OC).reshape(len(halves), 3, OC)
+        for i, hv in enumerate(halves):
+            pv[i, 0] = hv.shape[0]
+            pv[i, 1] = hv.mean(axis=0)
+            pv[i, 2] = ((hv - hv.mean(axis=0)) ** 2).sum(axis=0)
+        n_partials._obj.value = len(halves)
 
     def _conv_bwd(self, dy, x, w, N, H, W, C, OC, KH, KW, sh, sw, pad, need_dx):
         OH, OW = (H - KH + 2 * pad) // sh + 1, (W - KW + 2 * pad) // sw + 1
@@ -323,7 +364,7 @@ def install(monkeypatch=None):
         else:
             m.lib = fake
     rt = D.rt
-    state = dict(ready=rt.ready, device=rt.device, ws_small=rt._ws_small, ws_big=rt._ws_big)
+    state = dict(ready=rt.ready, device=rt.device, ws_small=rt._ws_small, ws_big=rt._ws_big, ws_stats=rt._ws_stats)
 
     def set_(obj, name, val):
         if monkeypatch is not None:
@@ -334,6 +375,7 @@ def install(monkeypatch=None):
     set_(rt, "device", torch.device("cpu"))
     set_(rt, "_ws_small", torch.zeros(1024))
     set_(rt, "_ws_big", torch.zeros(1024))
+    set_(rt, "_ws_stats", torch.zeros(rt.WS_STATS_FLOATS // 8))
     set_(rt, "stream", lambda: 0)
     set_(rt, "synchronize", lambda: None)
     return fake

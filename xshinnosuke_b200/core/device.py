@@ -28,7 +28,8 @@ class Runtime:
     """One process drives one GPU (LOCAL_RANK) from one host thread."""
 
     WS_SMALL_FLOATS = 4 << 20     # BN / colsum partials + ticket counters (zero-initialised once)
-    WS_BIG_FLOATS = 80 << 20      # split-K partials (FP32 implicit GEMM); flipped filter + zero-inserted dY (tcgen05 dgrad)
+    WS_BIG_FLOATS = 80 << 20      # split-K partials (FP32 implicit GEMM); flipped / per-class sub-filters (tcgen05 dgrad)
+    WS_STATS_FLOATS = 8 << 20     # BatchNorm (count, mean, M2) partials left by a conv epilogue (xsb_conv2d_fwd_stats)
 
     def __init__(self):
         self.ready = False
@@ -36,6 +37,7 @@ class Runtime:
         self.math_mode = MATH_FP32
         self._ws_small = None
         self._ws_big = None
+        self._ws_stats = None
         self.launches = 0          # kernel-launching C-ABI calls issued (bench.py reports it)
 
     def ensure(self):
@@ -70,6 +72,12 @@ class Runtime:
         if self._ws_big is None:
             self._ws_big = torch().empty(self.WS_BIG_FLOATS, dtype=torch().float32, device=self.device)
         return self._ws_big
+
+    @property
+    def ws_stats(self):
+        if self._ws_stats is None:
+            self._ws_stats = torch().empty(self.WS_STATS_FLOATS, dtype=torch().float32, device=self.device)
+        return self._ws_stats
 
     def synchronize(self):
         torch().cuda.current_stream().synchronize()

@@ -549,6 +549,225 @@ __global__ void invstd_k(const float* __restrict__ var, float* __restrict__ invs
     if (c < C) invstd[c] = 1.0f / sqrtf(var[c] + eps);
 }
 
+// ------------------------------------------------------------------ persistent backward (C = 4 * 2^k <= 1024)
+// Both passes walk the tensor grid-stride with a stride that is a multiple of the row length, so a thread meets the
+// SAME four channels in every iteration: parameters are loaded once, the per-channel sums stay in registers, and a
+// block contributes C atomic adds at the end (no per-block partial arrays, no serial last-block merge).
+//   sums[0..C) = sum(dy), sums[C..2C) = sum(dy * xhat)   (zeroed by the caller)
+constexpr int kPersistBlocksPerSM = 4;
+
+template <bool kXhat>
+__global__ void __launch_bounds__(kThreads)
+col_sums_atomic_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, int64_t nvec, int CV, float* sums, const uint8_t* __restrict__ rmask) {
+    __shared__ float4 s_a[kThreads], s_b[kThreads];
+    constexpr int U = kXhat ? 4 : 8;
+    const int tid = threadIdx.x;
+    const int c = (tid & (CV - 1)) * 4;     // CV divides kThreads: the channel group depends on the thread only
+    const int C = CV * 4;
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu;
+    if (kXhat) {
+        mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+        is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    }
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    const int64_t stride = (int64_t)gridDim.x * (kThreads * U);
+    for (int64_t base = (int64_t)blockIdx.x * (kThreads * U) + tid; base < nvec; base += stride) {
+        float4 g[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads;
+            g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[u] = mu;
+            if (i < nvec) {
+                g[u] = ldg_stream(reinterpret_cast<const float4*>(dy) + i);
+                if (kXhat) xv[u] = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+            }
+        }
+        if (rmask) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + (int64_t)u * kThreads;
+                if (i < nvec) {
+                    const int64_t e0 = i * 4;
+                    const unsigned m = (__ldg(rmask + (e0 >> 3)) >> (e0 & 4)) & 0xFu;
+                    if (m & 1u) g[u].x = 0.f;
+                    if (m & 2u) g[u].y = 0.f;
+                    if (m & 4u) g[u].z = 0.f;
+                    if (m & 8u) g[u].w = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sa.x += g[u].x; sa.y += g[u].y; sa.z += g[u].z; sa.w += g[u].w;
+            if (kXhat) {
+                sb.x = fmaf(g[u].x, (xv[u].x - mu.x) * is.x, sb.x);
+                sb.y = fmaf(g[u].y, (xv[u].y - mu.y) * is.y, sb.y);
+                sb.z = fmaf(g[u].z, (xv[u].z - mu.z) * is.z, sb.z);
+                sb.w = fmaf(g[u].w, (xv[u].w - mu.w) * is.w, sb.w);
+            }
+        }
+    }
+    s_a[tid] = sa;
+    if (kXhat) s_b[tid] = sb;
+    __syncthreads();
+    for (int st = kThreads / 2; st >= CV; st >>= 1) {   // threads tid, tid+CV, tid+2CV ... share a channel group
+        if (tid < st) {
+            float4 a = s_a[tid], b = s_a[tid + st];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            s_a[tid] = a;
+            if (kXhat) {
+                float4 p = s_b[tid], q = s_b[tid + st];
+                p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+                s_b[tid] = p;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < CV) {
+        const float4 a = s_a[tid];
+        atomicAdd(sums + c, a.x); atomicAdd(sums + c + 1, a.y); atomicAdd(sums + c + 2, a.z); atomicAdd(sums + c + 3, a.w);
+        if (kXhat) {
+            const float4 b = s_b[tid];
+            atomicAdd(sums + C + c, b.x); atomicAdd(sums + C + c + 1, b.y); atomicAdd(sums + C + c + 2, b.z);
+            atomicAdd(sums + C + c + 3, b.w);
+        }
+    }
+}
+
+// dx (+)= gamma*invstd * (dy - sum_dy/M - xhat * sum_dyxhat/M); block 0 also writes dgamma / dbeta (+)= from `sums`;
+// dxsum (nullable): per-channel column sums of the dx CONTRIBUTION, accumulated with atomics (the bias gradient of the
+// convolution that produced x: xs/nn/grad_fn.py:196-197 computed without a second pass over dx).
+template <bool kAcc>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x, float* dx, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ sums,
+                       float invM, int64_t nvec, int CV, const uint8_t* __restrict__ rmask, float* dgamma, float* dbeta,
+                       int acc_gamma, int acc_beta, float* dxsum) {
+    __shared__ float4 s_a[kThreads];
+    constexpr int U = 4;
+    const int tid = threadIdx.x;
+    const int c = (tid & (CV - 1)) * 4;
+    const int C = CV * 4;
+    if (blockIdx.x == 0) {
+        for (int ch = tid; ch < C; ch += kThreads) {
+            if (dbeta) dbeta[ch] = acc_beta ? dbeta[ch] + sums[ch] : sums[ch];
+            if (dgamma) dgamma[ch] = acc_gamma ? dgamma[ch] + sums[C + ch] : sums[C + ch];
+        }
+    }
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    float4 k1 = *reinterpret_cast<const float4*>(sums + c), k2 = *reinterpret_cast<const float4*>(sums + C + c);
+    k1.x *= invM; k1.y *= invM; k1.z *= invM; k1.w *= invM;
+    k2.x *= invM; k2.y *= invM; k2.z *= invM; k2.w *= invM;
+    const float4 kg = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t stride = (int64_t)gridDim.x * (kThreads * U);
+    for (int64_t base = (int64_t)blockIdx.x * (kThreads * U) + tid; base < nvec; base += stride) {
+        float4 g[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads;
+            if (i < nvec) {
+                g[u] = ldg_stream(reinterpret_cast<const float4*>(dy) + i);
+                xv[u] = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads;
+            if (i < nvec) {
+                if (rmask) {
+                    const int64_t e0 = i * 4;
+                    const unsigned m = (__ldg(rmask + (e0 >> 3)) >> (e0 & 4)) & 0xFu;
+                    if (m & 1u) g[u].x = 0.f;
+                    if (m & 2u) g[u].y = 0.f;
+                    if (m & 4u) g[u].z = 0.f;
+                    if (m & 8u) g[u].w = 0.f;
+                }
+                float4 o;
+                o.x = kg.x * (g[u].x - k1.x - (xv[u].x - mu.x) * is.x * k2.x);
+                o.y = kg.y * (g[u].y - k1.y - (xv[u].y - mu.y) * is.y * k2.y);
+                o.z = kg.z * (g[u].z - k1.z - (xv[u].z - mu.z) * is.z * k2.z);
+                o.w = kg.w * (g[u].w - k1.w - (xv[u].w - mu.w) * is.w * k2.w);
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                float4* p = reinterpret_cast<float4*>(dx) + i;
+                if (kAcc) {
+                    const float4 d = *p;
+                    o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
+                }
+                stg_stream(p, o);
+            }
+        }
+    }
+    if (dxsum) {
+        s_a[tid] = acc;
+        __syncthreads();
+        for (int st = kThreads / 2; st >= CV; st >>= 1) {
+            if (tid < st) {
+                float4 a = s_a[tid], b = s_a[tid + st];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                s_a[tid] = a;
+            }
+            __syncthreads();
+        }
+        if (tid < CV) {
+            const float4 a = s_a[tid];
+            atomicAdd(dxsum + c, a.x); atomicAdd(dxsum + c + 1, a.y); atomicAdd(dxsum + c + 2, a.z); atomicAdd(dxsum + c + 3, a.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ statistics from conv-epilogue partials
+// part[p][{n, mean, M2}][C], p < P  ->  save_mean / save_invstd and the running-statistics update. block (32, TY).
+__global__ void bn_finalize_k(const float* __restrict__ part, int P, int C, float R, float* __restrict__ save_mean,
+                              float* __restrict__ save_invstd, float* running_mean, float* running_var, float eps,
+                              float momentum) {
+    __shared__ float s_n[32][33], s_mean[32][33], s_m2[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+    const int c = blockIdx.x * 32 + tx;
+    float an = 0.f, amean = 0.f, am2 = 0.f;
+    if (c < C) {
+        for (int p0 = ty; p0 < P; p0 += TY * 4) {
+            float pn[4], pm[4], p2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int p = p0 + u * TY;
+                pn[u] = 0.f; pm[u] = 0.f; p2[u] = 0.f;
+                if (p < P) {
+                    const float* q = part + (int64_t)p * 3 * C + c;
+                    pn[u] = __ldg(q); pm[u] = __ldg(q + C); p2[u] = __ldg(q + 2 * C);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const Moments m = merge(Moments{an, amean, am2}, Moments{pn[u], pm[u], p2[u]});
+                an = m.n; amean = m.mean; am2 = m.m2;
+            }
+        }
+    }
+    s_n[ty][tx] = an; s_mean[ty][tx] = amean; s_m2[ty][tx] = am2;
+    __syncthreads();
+    for (int st = TY / 2; st > 0; st >>= 1) {
+        if (ty < st) {
+            const Moments m = merge(Moments{s_n[ty][tx], s_mean[ty][tx], s_m2[ty][tx]},
+                                    Moments{s_n[ty + st][tx], s_mean[ty + st][tx], s_m2[ty + st][tx]});
+            s_n[ty][tx] = m.n; s_mean[ty][tx] = m.mean; s_m2[ty][tx] = m.m2;
+        }
+        __syncthreads();
+    }
+    if (ty == 0 && c < C) {
+        const float mean = s_mean[0][tx];
+        const float var = s_m2[0][tx] / R;
+        save_mean[c] = mean;
+        save_invstd[c] = 1.0f / sqrtf(var + eps);
+        if (running_mean) running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * mean;
+        if (running_var) running_var[c] = momentum * running_var[c] + (1.f - momentum) * var;
+    }
+}
+
 inline bool use_vec4(int C, const void* a, const void* b = nullptr, const void* c = nullptr) {
     return (C % 4 == 0) && aligned16(a) && (!b || aligned16(b)) && (!c || aligned16(c));
 }
@@ -630,14 +849,74 @@ int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const
     return launch_bn_apply(x, y, moving_mean, invstd, gamma, beta, R, C, nullptr, false, s);
 }
 
+// statistics of a conv output from the partials its epilogue left (xsb_conv2d_fwd_stats): replaces xsb_bn_stats
+int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* running_mean, float* running_var,
+                    float* save_mean, float* save_invstd, float eps, float momentum, void* stream) {
+    XSB_CHECK_ARG(P > 0 && R > 0 && C > 0, "bn_finalize: empty input");
+    const int TY = P > 256 ? 32 : 8;
+    bn_finalize_k<<<(C + 31) / 32, dim3(32, TY), 0, xsb_stream(stream)>>>(partials, P, C, (float)R, save_mean, save_invstd,
+                                                                          running_mean, running_var, eps, momentum);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                       float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
+                       const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done, void* stream);
+
 // Backward. dx nullable (input needs no grad); dgamma/dbeta nullable. acc_* : 1 = "+=", 0 = "=".
 // relu_mask (nullable): dy is first masked with the in-place ReLU's bit mask (fused ReLUBackward).
 int xsb_bn_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
                const uint8_t* relu_mask, float* ws, void* stream) {
+    return bn_bwd_impl(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, R, C, acc_dx, acc_dgamma, acc_dbeta, relu_mask,
+                       ws, nullptr, 0, nullptr, stream);
+}
+
+// Same, and dxsum[c] (+)= sum_r (dx contribution)[r, c]: the bias gradient of the convolution that feeds this BatchNorm
+// (xs/nn/grad_fn.py:196-197), gathered while dx is written. *dxsum_done (host) = 1 when it was produced, 0 when this
+// shape runs the generic kernels (then call xsb_colsum on dx).
+int xsb_bn_bwd_dxsum(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                     float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
+                     const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done, void* stream) {
+    return bn_bwd_impl(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, R, C, acc_dx, acc_dgamma, acc_dbeta, relu_mask,
+                       ws, dxsum, acc_dxsum, dxsum_done, stream);
+}
+
+static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                       float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
+                       const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done, void* stream) {
     XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
     cudaStream_t s = xsb_stream(stream);
+    if (dxsum_done) *dxsum_done = 0;
     const bool v4 = use_vec4(C, dy, x, dx);
+    const int CV4 = C / 4;
+    if (v4 && dx && C % 4 == 0 && CV4 <= kThreads && (CV4 & (CV4 - 1)) == 0 && aligned16(save_mean) &&
+        aligned16(save_invstd) && aligned16(gamma)) {
+        float* sums = ws + kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks;   // the coef area: 3C floats
+        XSB_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), s));
+        if (dxsum && !acc_dxsum) XSB_CUDA(cudaMemsetAsync(dxsum, 0, (size_t)C * sizeof(float), s));
+        const int64_t nvec = R * CV4;
+        // >= 4 grid-stride iterations per thread: a block ends with 2C (+C) atomics, keep them few on small tensors
+        int64_t blocks = ceil_div64(nvec, (int64_t)kThreads * 4 * 4);
+        const int64_t cap = (int64_t)xsb_sm_count_cached() * kPersistBlocksPerSM;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        col_sums_atomic_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, nvec, CV4, sums, relu_mask);
+        XSB_LAUNCH_CHECK();
+        const float invM = 1.0f / (float)R;
+        if (acc_dx)
+            bn_bwd_apply_persist_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
+                                                                              nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
+                                                                              acc_dbeta, dxsum);
+        else
+            bn_bwd_apply_persist_k<false><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
+                                                                               nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
+                                                                               acc_dbeta, dxsum);
+        XSB_LAUNCH_CHECK();
+        if (dxsum && dxsum_done) *dxsum_done = 1;
+        return XSB_OK;
+    }
     const Geom g = make_geom(R, C, v4, 2 * 148);   // two streamed arrays per thread: fewer, fatter CTAs measured faster
     XSB_CHECK_ARG(g.chunks <= kCounterSlots, "bn: C=%d too large", C);
     float* coef = ws + kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks;

@@ -36,6 +36,8 @@ struct HaloParams {
     int h_off;               // TMA row coordinate of output row 0, filter row 0 (= -pad, or 0 for a pre-padded image)
     int stage_bytes, n_stages, n_btiles;
     int accumulate;
+    // BatchNorm partial statistics (null = off): stats[(blockIdx.x*3 + {0:n, 1:mean, 2:M2}) * ldo + channel]
+    float* stats;
 };
 
 // KH_T > 0: filter height known at compile time (k-block loop fully unrolled); 0: runtime p.KH
@@ -174,14 +176,24 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* stage = sOut + q * 4096;
         int buf = 0;
         uint32_t tph = 0;
+        Moments run[BN / 32];   // lane j: running statistics of columns 32*i + j over this warp's rows of every tile
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) run[i] = Moments{0.f, 0.f, 0.f};
         int n_img = blockIdx.x / tiles_per_img, rem = blockIdx.x - n_img * tiles_per_img;
         const int step_img = gridDim.x / tiles_per_img, step_rem = gridDim.x - step_img * tiles_per_img;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
             const int oh0 = th * HALO_TH + q * 4, ow0 = tw * HALO_TW;
+            uint32_t vm = 0;   // valid rows of this warp's {8 w, 4 h} box
+            if (p.stats) {
+                const uint32_t wmask = ow0 + HALO_TW <= p.OW ? 0xFFu : ((1u << (p.OW - ow0)) - 1u);
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    if (oh0 + h < p.OH) vm |= wmask << (8 * h);
+            }
             mbar_wait(&tmem_full[buf], tph);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
@@ -208,6 +220,7 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_store_4d(&tmO, stage, c0, ow0, oh0, n_img);
                     bulk_commit();
                 }
+                if (p.stats) run[c0 / 32] = merge_moments(run[c0 / 32], stage_col_moments(stage, lane, vm));
             }
             tc_fence_before();
             __syncwarp();
@@ -219,6 +232,29 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (rem >= tiles_per_img) { rem -= tiles_per_img; ++n_img; }
         }
         if (lane == 0) bulk_wait_all<0>();   // global writes complete before the CTA exits
+        if (p.stats) {   // one partial per CTA and column: merge the four warps through the staging area
+            __syncwarp();
+            epilogue_bar();   // ... once EVERY warp's last store has finished reading its staging block
+            float* sStat = reinterpret_cast<float*>(sOut);
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) {
+                sStat[q * 3 * BN + i * 32 + lane] = run[i].n;
+                sStat[(q * 3 + 1) * BN + i * 32 + lane] = run[i].mean;
+                sStat[(q * 3 + 2) * BN + i * 32 + lane] = run[i].m2;
+            }
+            epilogue_bar();
+            for (int col = q * 32 + lane; col < BN; col += 128) {
+                Moments acc{0.f, 0.f, 0.f};
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4)
+                    acc = merge_moments(acc, Moments{sStat[w4 * 3 * BN + col], sStat[(w4 * 3 + 1) * BN + col],
+                                                     sStat[(w4 * 3 + 2) * BN + col]});
+                float* dst = p.stats + (int64_t)blockIdx.x * 3 * p.ldo + col;
+                dst[0] = acc.n;
+                dst[p.ldo] = acc.mean;
+                dst[2 * p.ldo] = acc.m2;
+            }
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -271,10 +307,26 @@ static int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HaloPar
     return launch_halo_t<BN, 0>(a, b, o, p, s);
 }
 
+// a caller's request for BatchNorm partial statistics of the conv output (see xsb_conv2d_fwd_stats)
+struct StatsReq {
+    float* buf;          // device, `floats` long
+    int64_t floats;
+    int* n_partials;     // host, receives the number of partials written (0: the kernel that ran produces none)
+};
+static void halo_attach_stats(HaloParams& p, StatsReq* st) {
+    int grid = xsb_sm_count_cached();
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    if (st && st->buf && st->floats >= (int64_t)grid * 3 * p.ldo) {
+        p.stats = st->buf;
+        if (st->n_partials) *st->n_partials = grid;
+    }
+}
+
 // Generic stride-1 path: conv of channels-last in[N,H,W,Cx] with flt[OCx, KH*KW*Cx] -> out[N,OH,OW,OCx].
 // Returns XSB_ERR_UNSUPPORTED when the shape is outside the envelope (caller runs the im2col kernel).
 static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const float* flt, int OCx, int KH, int KW, int pad_h,
-                        int pad_w, int OH, int OW, const float* bias, float* out, int accumulate, cudaStream_t s) {
+                        int pad_w, int OH, int OW, const float* bias, float* out, int accumulate, cudaStream_t s,
+                        StatsReq* st = nullptr) {
     const int cblocks = Cx / 32;
     if (Cx % 32 != 0 || (OCx != 64 && OCx != 128) || KH > HALO_MAX_KH) return XSB_ERR_UNSUPPORTED;
     const int n_btiles = KH * KW * cblocks;
@@ -299,6 +351,7 @@ static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const floa
     p.cblocks = cblocks; p.KWl = KW; p.KH = KH; p.sh = 1; p.pad_w = pad_w; p.bt_kh_stride = KW * cblocks;
     p.h_off = -pad_h;
     p.stage_bytes = stage_bytes; p.n_stages = stages; p.n_btiles = n_btiles; p.accumulate = accumulate;
+    halo_attach_stats(p, st);
     return OCx == 64 ? launch_halo<64>(ta, tb, p, s) : launch_halo<128>(ta, tb, p, s);
 }
 

@@ -31,6 +31,8 @@ struct FpropParams {
     // strided destination (dgrad of a strided conv: one launch produces one parity class of dX):
     // GEMM row (n,i,j) lands on pixel (n, o_a + i*o_sh, o_b + j*o_sw) of an [N, o_H, o_W, ldo] tensor
     int o_strided, o_H, o_W, o_sh, o_sw, o_a, o_b;
+    // BatchNorm partial statistics (null = off): stats[(blockIdx.x*3 + {0:n, 1:mean, 2:M2}) * ldo + channel]
+    float* stats;
 };
 
 template <int BN, int STAGES, int OCC>
@@ -150,8 +152,32 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tma_store_2d(&tmO, stage, n0 + c0, m0 + q * 32);
                     bulk_commit();
                 }
+                if (p.stats) {   // this warp's 32 rows of columns c0..c0+31 -> (n, mean, M2) per column
+                    const int left = p.M - (m0 + q * 32);
+                    const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? ((1u << left) - 1u) : 0u);
+                    const Moments mo = stage_col_moments(stage, lane, vm);
+                    float* sStat = reinterpret_cast<float*>(sA + 16384) + q * 3 * BN + c0 + lane;
+                    sStat[0] = mo.n;
+                    sStat[BN] = mo.mean;
+                    sStat[2 * BN] = mo.m2;
+                }
             }
             if (lane == 0) bulk_wait_all<0>();
+            if (p.stats) {   // merge the four warps, one partial per CTA and column
+                epilogue_bar();
+                const float* sStat = reinterpret_cast<const float*>(sA + 16384);
+                for (int col = row; col < BN; col += 128) {
+                    Moments acc{0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4)
+                        acc = merge_moments(acc, Moments{sStat[w4 * 3 * BN + col], sStat[(w4 * 3 + 1) * BN + col],
+                                                         sStat[(w4 * 3 + 2) * BN + col]});
+                    float* dst = p.stats + (int64_t)blockIdx.x * 3 * p.ldo + n0 + col;
+                    dst[0] = acc.n;
+                    dst[p.ldo] = acc.mean;
+                    dst[2 * p.ldo] = acc.m2;
+                }
+            }
         } else {
             const int hw = p.OH * p.OW;
             const int n_img = m / hw, rem = m - n_img * hw;
@@ -618,6 +644,8 @@ struct FpropJob {
     const float* flt; int OCx, KH, KW, sh, sw, pad_h, pad_w, OH, OW;
     const float* bias; float* out; int accumulate;
     int o_strided, o_H, o_W, o_sh, o_sw, o_a, o_b;
+    float* stats;          // BatchNorm partials (null = off)
+    int* n_partials;       // host: receives the number of partials written
 };
 
 static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
@@ -637,7 +665,8 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
         return XSB_ERR_CUDA;
     }
     FpropParams p{j.out, j.bias, j.N * j.OH * j.OW, j.OCx, j.Cx, j.KH, j.KW, j.OH, j.OW, j.sh, j.sw, j.pad_h, j.pad_w,
-                  j.accumulate, j.o_strided, j.o_H, j.o_W, j.o_sh, j.o_sw, j.o_a, j.o_b};
+                  j.accumulate, j.o_strided, j.o_H, j.o_W, j.o_sh, j.o_sw, j.o_a, j.o_b, j.o_strided ? nullptr : j.stats};
+    if (p.stats && j.n_partials) *j.n_partials = (p.M + BM - 1) / BM;
     CUtensorMap to = ta;   // unused by strided-destination launches
     if (!j.o_strided && !make_map_2d(&to, j.out, (uint64_t)p.M, (uint64_t)j.OCx, 32)) {
         xsb_set_error("cuTensorMapEncode failed (fprop output M=%d OC=%d)", p.M, j.OCx);
@@ -706,7 +735,7 @@ static int stem_prepare(const float* x, const ConvGeom& g, const StemPlan& pl, f
 }
 
 static int stem_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                    int64_t ws_floats, cudaStream_t s) {
+                    int64_t ws_floats, cudaStream_t s, StatsReq* st) {
     const StemPlan pl = stem_plan(g);
     if (!ws || ws_floats < pl.xp_floats + pl.wq_floats) return XSB_ERR_UNSUPPORTED;
     if ((g.OC != 64 && g.OC != 128) || g.KH > HALO_MAX_KH) return XSB_ERR_UNSUPPORTED;
@@ -734,6 +763,7 @@ static int stem_fwd(const float* x, const float* w, const float* bias, float* y,
     p.n_tiles = g.N * p.tiles_w * p.tiles_h;
     p.cblocks = 1; p.KWl = 1; p.KH = g.KH; p.sh = g.sh; p.pad_w = 0; p.bt_kh_stride = 1; p.h_off = 0;
     p.stage_bytes = rows * 1024; p.n_stages = stages; p.n_btiles = g.KH; p.accumulate = 0;
+    halo_attach_stats(p, st);
     return g.OC == 64 ? launch_halo<64>(ta, tb, p, s) : launch_halo<128>(ta, tb, p, s);
 }
 
@@ -807,21 +837,27 @@ static int counted(int rc) {
 }
 
 static int tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                       int64_t ws_floats, cudaStream_t s) {
-    if (stem_ok(g) && aligned16(x) && aligned16(w) && aligned16(y)) return stem_fwd(x, w, bias, y, g, ws, ws_floats, s);
+                       int64_t ws_floats, cudaStream_t s, StatsReq* st) {
+    if (stem_ok(g) && aligned16(x) && aligned16(w) && aligned16(y)) return stem_fwd(x, w, bias, y, g, ws, ws_floats, s, st);
     if (!fprop_ok(g.C, g.OC, x, w, y) || g.KW > 255 || g.KH > 255) return XSB_ERR_UNSUPPORTED;
     if (g.sh == 1 && g.sw == 1 && halo_enabled()) {
-        const int rc = halo_conv_s1(x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.pad, g.pad, g.OH, g.OW, bias, y, 0, s);
+        const int rc = halo_conv_s1(x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.pad, g.pad, g.OH, g.OW, bias, y, 0, s, st);
         if (rc != XSB_ERR_UNSUPPORTED) return rc;
     }
-    const FpropJob j{x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, bias, y, 0,
-                     0, 0, 0, 1, 1, 0, 0};
+    FpropJob j{x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, bias, y, 0,
+               0, 0, 0, 1, 1, 0, 0, nullptr, nullptr};
+    const int64_t m_tiles = ((int64_t)g.N * g.OH * g.OW + BM - 1) / BM;
+    if (st && st->buf && st->floats >= m_tiles * 3 * g.OC) {
+        j.stats = st->buf;
+        j.n_partials = st->n_partials;
+    }
     return fprop_dispatch(j, s);
 }
 
 int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                    int64_t ws_floats, cudaStream_t s) {
-    return counted(tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s));
+                    int64_t ws_floats, cudaStream_t s, float* stats, int64_t stats_floats, int* n_partials) {
+    StatsReq st{stats, stats_floats, n_partials};
+    return counted(tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, stats ? &st : nullptr));
 }
 
 static int tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
@@ -884,7 +920,7 @@ static int tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvG
                 if (rc != XSB_ERR_UNSUPPORTED) return rc;
             }
             const FpropJob j{dy, g.N, g.OH, g.OW, g.OC, ws + cls_base[a][b], g.C, ch[a].T, cw[b].T, 1, 1, ch[a].padp,
-                             cw[b].padp, Ha, Wb, nullptr, dx, accumulate, strided, g.H, g.W, g.sh, g.sw, a, b};
+                             cw[b].padp, Ha, Wb, nullptr, dx, accumulate, strided, g.H, g.W, g.sh, g.sw, a, b, nullptr, nullptr};
             const int rc = fprop_dispatch(j, s);
             if (rc != XSB_OK) return rc;
         }

@@ -18,7 +18,7 @@ using namespace igemm;
 int xsb_tc_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
                 int transB, int accumulate, float* ws, int64_t ws_floats, cudaStream_t s);
 int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                    int64_t ws_floats, cudaStream_t s);
+                    int64_t ws_floats, cudaStream_t s, float* stats, int64_t stats_floats, int* n_partials);
 int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
                       int64_t ws_floats, cudaStream_t s);
 int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
@@ -80,6 +80,25 @@ int xsb_gemm(const float* A, const float* B, float* C, const float* bias, int M,
     }
 }
 
+// y[N,OH,OW,OC] = conv(x[N,H,W,C], w[OC,KH,KW,C]) (+ bias[OC]). With `stats`: the tensor-core kernels also leave
+// per-CTA (count, mean, M2) partials of every output channel in stats[p][3][OC] and *n_partials = p > 0, which
+// xsb_bn_finalize turns into the batch statistics of a following BatchNorm without reading y again; *n_partials = 0
+// when the kernel that served the call gathers none (FFMA path, buffer too small) -- then use xsb_bn_stats.
+int xsb_conv2d_fwd_stats(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int C, int OC,
+                         int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws, int64_t ws_floats,
+                         float* stats, int64_t stats_floats, int* n_partials, void* stream) {
+    ConvGeom g;
+    XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_fwd: bad geometry");
+    cudaStream_t s = xsb_stream(stream);
+    if (n_partials) *n_partials = 0;
+    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, stats, stats_floats, n_partials));
+    if (n_partials) *n_partials = 0;
+    const int P = N * g.OH * g.OW, J = KH * KW * C;
+    PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
+    MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};
+    return launch(la, lb, y, OC, bias, P, OC, J, 0, true, ws, ws_floats, s);
+}
+
 // y[N,OH,OW,OC] = conv(x[N,H,W,C], w[OC,KH,KW,C]) (+ bias[OC])
 int xsb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int C, int OC,
                    int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws, int64_t ws_floats,
@@ -87,7 +106,7 @@ int xsb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
     ConvGeom g;
     XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_fwd: bad geometry");
     cudaStream_t s = xsb_stream(stream);
-    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s));
+    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, nullptr, 0, nullptr));
     const int P = N * g.OH * g.OW, J = KH * KW * C;
     PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
     MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};

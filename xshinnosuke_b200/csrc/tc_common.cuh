@@ -135,6 +135,48 @@ __device__ __forceinline__ void stage_rows_sw128(uint8_t* stage, int lane, const
         *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
+// ---- per-channel batch statistics of a conv output, gathered in the epilogue (feeds BatchNorm without re-reading y)
+struct Moments {   // count, mean, sum of squared deviations
+    float n, mean, m2;
+};
+__device__ __forceinline__ Moments merge_moments(const Moments& a, const Moments& b) {   // Chan et al. pairwise update
+    if (b.n == 0.f) return a;
+    if (a.n == 0.f) return b;
+    Moments r;
+    r.n = a.n + b.n;
+    const float d = b.mean - a.mean;
+    const float fb = b.n / r.n;
+    r.mean = a.mean + d * fb;
+    r.m2 = a.m2 + b.m2 + d * d * a.n * fb;
+    return r;
+}
+// Column `lane` of a staged 32 x 32 block (stage_rows_sw128 layout; conflict-free: the 32 lanes of one row read 32
+// different banks) over the rows whose bit is set in `vm`: pivoted sums (pivot = first valid row), so the variance
+// does not suffer E[x^2] - E[x]^2 cancellation.
+__device__ __forceinline__ Moments stage_col_moments(const uint8_t* stage, int lane, uint32_t vm) {
+    Moments m{0.f, 0.f, 0.f};
+    if (vm == 0u) return m;
+    const float* sf = reinterpret_cast<const float*>(stage);
+    const int cl = lane >> 2, ci = lane & 3;
+    const int r0 = __ffs(vm) - 1;
+    const float K = sf[r0 * 32 + (((cl ^ (r0 & 7)) << 2) | ci)];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+        if ((vm >> r) & 1u) {
+            const float d = sf[r * 32 + (((cl ^ (r & 7)) << 2) | ci)] - K;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+        }
+    m.n = (float)__popc(vm);
+    const float inv = 1.f / m.n;
+    m.mean = K + s1 * inv;
+    m.m2 = fmaxf(s2 - s1 * s1 * inv, 0.f);
+    return m;
+}
+// the 4 epilogue warps (128 threads) only
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                  : "memory");

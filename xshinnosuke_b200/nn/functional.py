@@ -7,6 +7,8 @@ two libxsb200 kernel launches on the current CUDA stream, (ii) wires the dynamic
 (`initialize_ops_grad`). `out=` is honoured (the static-graph front end passes preallocated buffers).
 Ops outside the hot path named in SURVEY.md section 8a are not provided.
 """
+import ctypes
+
 import numpy as np
 
 from ..core import state as GLOBAL
@@ -261,9 +263,25 @@ def conv2d(inputs: Tensor, weight: Tensor, bias: Tensor = None, stride=(1, 1), p
     ow = (wd - kw + 2 * padding) // sw + 1
     out, y = _out_arr(out, (n, oc, oh, ow))
     y.cl = True
-    lib.xsb_conv2d_fwd(x.ptr, w.ptr, bias.arr.ptr if bias is not None else None, y.wptr, n, h, wd, c, oc, kh, kw,
-                       sh, sw, padding, rt.math_mode, rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream())
-    rt.launches += 1
+    ybuf = y.buf
+    y.wptr  # noqa: B018 -- clears stale pending state of a reused (static) buffer
+    barr = bias.arr if bias is not None else None
+
+    def run(mask=None, stats=False, _x=x, _w=w):
+        # deferred by one op: a BatchNorm that consumes y asks for `stats` and the conv epilogue gathers the
+        # per-channel (count, mean, M2) partials on the way out -> no statistics pass over y (returns #partials)
+        args = (_x.ptr, _w.ptr, barr.ptr if barr is not None else None, ybuf.data_ptr(), n, h, wd, c, oc, kh, kw, sh, sw,
+                padding, rt.math_mode, rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS)
+        rt.launches += 1
+        if not stats:
+            lib.xsb_conv2d_fwd(*args, rt.stream())
+            return 0
+        nparts = ctypes.c_int(0)
+        lib.xsb_conv2d_fwd_stats(*args, rt.ws_stats.data_ptr(), rt.WS_STATS_FLOATS, ctypes.byref(nparts), rt.stream())
+        return nparts.value
+    run.fusable_relu = False
+    run.conv_stats = True
+    y.pending_op = run
     rg = inputs.requires_grad or weight.requires_grad or bool(bias is not None and bias.requires_grad)
     return _wire(out, (inputs, weight, bias), rg, Conv2DBackward, cache={"stride": (sh, sw), "padding": padding})
 
@@ -323,6 +341,11 @@ def batch_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, moving_mean: Tensor,
     """xs/nn/functional.py:676-740, training branch (the only one the reference ever reaches, Q5)."""
     _mark_inputs(inputs)
     x = inputs.arr
+    nparts = 0
+    producer = x.pending_op
+    if training and producer is not None and getattr(producer, "conv_stats", False) and x.ndim == 4 and axis == 1:
+        x.pending_op = None
+        nparts = producer(None, stats=True)   # the producing conv runs now and leaves statistics partials
     if x.ndim == 4 and axis == 1:
         x = x.as_cl()
     elif x.ndim == 2 and axis in (1, -1):
@@ -344,8 +367,12 @@ def batch_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, moving_mean: Tensor,
             inputs.add_out_bounds(out)
         return out
     save_mean, save_invstd = DevArray.empty((C,)), DevArray.empty((C,))
-    lib.xsb_bn_stats(x.ptr, moving_mean.arr.ptr, moving_variance.arr.ptr, save_mean.wptr, save_invstd.wptr, R, C,
-                     float(epsilon), float(momentum), rt.ws_small.data_ptr(), rt.stream())
+    if nparts > 0:
+        lib.xsb_bn_finalize(rt.ws_stats.data_ptr(), nparts, R, C, moving_mean.arr.ptr, moving_variance.arr.ptr,
+                            save_mean.wptr, save_invstd.wptr, float(epsilon), float(momentum), rt.stream())
+    else:
+        lib.xsb_bn_stats(x.ptr, moving_mean.arr.ptr, moving_variance.arr.ptr, save_mean.wptr, save_invstd.wptr, R, C,
+                         float(epsilon), float(momentum), rt.ws_small.data_ptr(), rt.stream())
     rt.launches += 1
     ybuf = y.buf
     y.wptr  # noqa: B018 -- clears stale pending state of a reused (static) buffer

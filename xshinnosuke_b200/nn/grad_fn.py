@@ -6,6 +6,8 @@ Each one is a thin launcher of libxsb200 kernels; "accumulate" is passed to the 
 (0 the first time a freshly zeroed gradient is written, 1 afterwards), so no zero-fill and no
 separate `+=` pass is ever run.
 """
+import ctypes
+
 from ..core.device import DevArray, rt
 from ..core.tensor import Parameter, Tensor
 from .._lib import lib
@@ -191,9 +193,12 @@ def Conv2DBackward(outputs: Tensor):
         rt.launches += 1
         _done(weight)
     if bias is not None and bias.requires_grad:
-        g = _grad_arr(bias)
-        lib.xsb_colsum(dy.ptr, g.peek_ptr(), dy.size // oc, oc, g.take_acc(), rt.ws_small.data_ptr(), st)
-        rt.launches += 1
+        if outputs.cache.pop("bias_grad_done", False):
+            pass   # the BatchNorm backward that produced dY summed its columns into bias.grad on the way
+        else:
+            g = _grad_arr(bias)
+            lib.xsb_colsum(dy.ptr, g.peek_ptr(), dy.size // oc, oc, g.take_acc(), rt.ws_small.data_ptr(), st)
+            rt.launches += 1
         _done(bias)
     if inputs.requires_grad:
         g = _grad_arr(inputs)
@@ -246,6 +251,31 @@ def BatchNormBackward(outputs: Tensor, relu_mask=None):
     gx = _grad_arr(inputs) if inputs.requires_grad else None
     gg = _grad_arr(gamma) if gamma.requires_grad else None
     gb = _grad_arr(beta) if beta.requires_grad else None
+    # x is the output of a convolution with a trainable bias and this BN is its only consumer: the bias gradient
+    # (column sums of dX, xs/nn/grad_fn.py:196-197) is gathered while dX is written instead of by a second pass
+    cb = None
+    if (gx is not None and x.ndim == 4 and inputs.grad_fn is Conv2DBackward and inputs.is_dynamic
+            and len(inputs.out_bounds) == 1 and gx.pending_zero):
+        conv_bias = inputs.in_bounds[2]
+        if conv_bias is not None and conv_bias.requires_grad:
+            cb = _grad_arr(conv_bias)
+    if cb is not None:
+        was_zero = cb.pending_zero
+        done = ctypes.c_int(0)
+        lib.xsb_bn_bwd_dxsum(dy.ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
+                             gx.peek_ptr(), gg.peek_ptr() if gg is not None else None,
+                             gb.peek_ptr() if gb is not None else None, R, C, gx.take_acc(),
+                             gg.take_acc() if gg is not None else 0, gb.take_acc() if gb is not None else 0,
+                             relu_mask.data_ptr() if relu_mask is not None else None, rt.ws_small.data_ptr(),
+                             cb.peek_ptr(), cb.take_acc(), ctypes.byref(done), rt.stream())
+        if done.value:
+            inputs.cache["bias_grad_done"] = True
+        else:
+            cb.pending_zero = was_zero
+        rt.launches += 2
+        _done(gamma)
+        _done(beta)
+        return
     lib.xsb_bn_bwd(dy.ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
                    gx.peek_ptr() if gx is not None else None, gg.peek_ptr() if gg is not None else None,
                    gb.peek_ptr() if gb is not None else None, R, C,
