@@ -184,7 +184,9 @@ def _tc_stats():
     # strided dgrad = one stride-1 conv per parity class (5x5/2; trailing row without gradient; classes no tap reaches)
     (2, 64, 16, 64, 5, 2, 2, 3), (2, 64, 10, 64, 3, 2, 0, 3), (2, 64, 8, 64, 2, 3, 0, 3), (2, 64, 17, 128, 7, 2, 3, 3),
     # filter-resident halo kernel (fwd and stride-1 dgrad), incl. partial tiles and zero padding via TMA OOB fill
-    (2, 64, 32, 64, 3, 1, 1, 3), (2, 64, 30, 64, 3, 1, 2, 3), (3, 32, 34, 128, 3, 1, 0, 2), (150, 64, 16, 64, 3, 1, 1, 3)])
+    (2, 64, 32, 64, 3, 1, 1, 3), (2, 64, 30, 64, 3, 1, 2, 3), (3, 32, 34, 128, 3, 1, 0, 2), (150, 64, 16, 64, 3, 1, 1, 3),
+    # wave-aware tiling: fewer tiles than SMs -> column parts (incl. unequal 192/160/160); full wave + split tail wave
+    (24, 256, 7, 512, 3, 1, 1, 3), (100, 128, 14, 256, 3, 1, 1, 3)])
 def test_conv_tf32_tensor_cores(n, c, h, oc, k, s, p, n_tc):
     """fwd / dgrad / wgrad on tcgen05 (kind::tf32) against the float64 oracle; `n_tc` = how many of the three
     must have run on the tensor cores for this shape (C <= 4 stems: fwd + wgrad via the padded-4-channel kernels,
@@ -218,7 +220,8 @@ def test_conv_tf32_tensor_cores(n, c, h, oc, k, s, p, n_tc):
 
 @pytest.mark.parametrize("n,c,h,oc,k,s,p", [
     (4, 64, 14, 64, 3, 1, 1), (8, 64, 28, 128, 3, 2, 1), (2, 256, 7, 512, 3, 1, 1), (3, 3, 56, 64, 7, 2, 3),
-    (5, 64, 32, 64, 3, 1, 1), (4, 64, 30, 64, 3, 1, 2), (2, 128, 9, 256, 1, 2, 0), (150, 64, 16, 64, 3, 1, 1)])
+    (5, 64, 32, 64, 3, 1, 1), (4, 64, 30, 64, 3, 1, 2), (2, 128, 9, 256, 1, 2, 0), (150, 64, 16, 64, 3, 1, 1),
+    (24, 256, 7, 512, 3, 1, 1), (100, 128, 14, 256, 3, 1, 1)])
 def test_conv_bn_relu_fused_statistics_tf32(n, c, h, oc, k, s, p):
     """Conv2D -> BatchNormalization -> ReLU(inplace) in tf32 mode: the batch statistics come from the partials the conv
     epilogue gathers (xsb_conv2d_fwd_stats + xsb_bn_finalize, no pass over the conv output) and, backward, the conv

@@ -31,8 +31,13 @@ struct FpropParams {
     // strided destination (dgrad of a strided conv: one launch produces one parity class of dX):
     // GEMM row (n,i,j) lands on pixel (n, o_a + i*o_sh, o_b + j*o_sw) of an [N, o_H, o_W, ldo] tensor
     int o_strided, o_H, o_W, o_sh, o_sw, o_a, o_b;
-    // BatchNorm partial statistics (null = off): stats[(blockIdx.x*3 + {0:n, 1:mean, 2:M2}) * ldo + channel]
+    // BatchNorm partial statistics (null = off): stats[(m_tile*3 + {0:n, 1:mean, 2:M2}) * ldo + channel]
     float* stats;
+    // this launch covers m-tiles m_tile0 .. m_tile0 + gridDim.x - 1; CTA column blockIdx.y computes output channels
+    // part_n0[y] .. part_n0[y] + part_cols[y] - 1 (cols <= BN, multiple of 32): unequal column parts let a launch whose
+    // tile count does not fill the SMs split its N range into as many parts as there are idle SMs
+    int m_tile0;
+    short part_n0[16], part_cols[16];
 };
 
 template <int BN, int STAGES, int OCC>
@@ -53,7 +58,8 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblocks = p.C / 32;
     const int num_kb = p.KH * p.KW * cblocks;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m_tile = p.m_tile0 + blockIdx.x;
+    const int m0 = m_tile * BM, n0 = p.part_n0[blockIdx.y], ncols = p.part_cols[blockIdx.y];
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -65,8 +71,9 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
+    constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -94,7 +101,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        const uint32_t idesc = make_idesc(ncols, 0, 0);   // N = this CTA's column count (the B tile holds BN >= N rows)
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         int s = 0;
         uint32_t ph = 0;
@@ -126,7 +133,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // {32 ch, 32 pixel} box of out[M, ldo] (rows >= M are clipped by the tensor map)
             uint8_t* stage = sA + q * 4096;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 tmem_wait_ld();
@@ -166,13 +173,13 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (p.stats) {   // merge the four warps, one partial per CTA and column
                 epilogue_bar();
                 const float* sStat = reinterpret_cast<const float*>(sA + 16384);
-                for (int col = row; col < BN; col += 128) {
+                for (int col = row; col < ncols; col += 128) {
                     Moments acc{0.f, 0.f, 0.f};
 #pragma unroll
                     for (int w4 = 0; w4 < 4; ++w4)
                         acc = merge_moments(acc, Moments{sStat[w4 * 3 * BN + col], sStat[(w4 * 3 + 1) * BN + col],
                                                          sStat[(w4 * 3 + 2) * BN + col]});
-                    float* dst = p.stats + (int64_t)blockIdx.x * 3 * p.ldo + n0 + col;
+                    float* dst = p.stats + (int64_t)m_tile * 3 * p.ldo + n0 + col;
                     dst[0] = acc.n;
                     dst[p.ldo] = acc.mean;
                     dst[2 * p.ldo] = acc.m2;
@@ -185,7 +192,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int64_t pix = ((int64_t)n_img * p.o_H + p.o_a + i * p.o_sh) * p.o_W + p.o_b + j2 * p.o_sw;
             float* orow = p.out + pix * p.ldo + n0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 tmem_wait_ld();
@@ -213,7 +220,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -623,15 +630,15 @@ static int tc_occupancy() {
 }
 
 template <int BN, int STAGES, int OCC>
-static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const FpropParams& p, int n_tiles,
-                        cudaStream_t s) {
+static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const FpropParams& p, int m_tiles,
+                        int n_parts, cudaStream_t s) {
     constexpr int smem = STAGES * (BM * A_ROW_BYTES + BN * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
         XSB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_k<BN, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid((p.M + BM - 1) / BM, n_tiles);
+    dim3 grid(m_tiles, n_parts);
     conv_fprop_tc_k<BN, STAGES, OCC><<<grid, kThreads, smem, s>>>(a, b, o, p);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
@@ -666,22 +673,79 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
     }
     FpropParams p{j.out, j.bias, j.N * j.OH * j.OW, j.OCx, j.Cx, j.KH, j.KW, j.OH, j.OW, j.sh, j.sw, j.pad_h, j.pad_w,
                   j.accumulate, j.o_strided, j.o_H, j.o_W, j.o_sh, j.o_sw, j.o_a, j.o_b, j.o_strided ? nullptr : j.stats};
-    if (p.stats && j.n_partials) *j.n_partials = (p.M + BM - 1) / BM;
+    const int m_tiles = (p.M + BM - 1) / BM;
+    if (p.stats && j.n_partials) *j.n_partials = m_tiles;
     CUtensorMap to = ta;   // unused by strided-destination launches
     if (!j.o_strided && !make_map_2d(&to, j.out, (uint64_t)p.M, (uint64_t)j.OCx, 32)) {
         xsb_set_error("cuTensorMapEncode failed (fprop output M=%d OC=%d)", p.M, j.OCx);
         return XSB_ERR_CUDA;
     }
+    // one launch: m-tiles [m_tile0, m_tile0 + count) x `parts` column ranges of OCx (multiples of 32, widths differ by <= 32)
+    auto launch_parts = [&](int m_tile0, int count, int parts) -> int {
+        const int w32 = j.OCx / 32, base = w32 / parts, extra = w32 % parts;
+        int n0 = 0, widest = 0;
+        for (int i = 0; i < parts; ++i) {
+            const int cols = (base + (i < extra ? 1 : 0)) * 32;
+            p.part_n0[i] = (short)n0;
+            p.part_cols[i] = (short)cols;
+            n0 += cols;
+            if (cols > widest) widest = cols;
+        }
+        p.m_tile0 = m_tile0;
+        const int bn = widest <= 64 ? 64 : widest <= 96 ? 96 : widest <= 128 ? 128 : widest <= 192 ? 192 : 256;
+        CUtensorMap tbp;
+        if (!make_map_2d(&tbp, j.flt, (uint64_t)j.OCx, (uint64_t)j.KH * j.KW * j.Cx, (uint32_t)bn)) {
+            xsb_set_error("cuTensorMapEncode failed (fprop filter box %d)", bn);
+            return XSB_ERR_CUDA;
+        }
+        if (bn == 256) return launch_fprop<256, 4, 1>(ta, tbp, to, p, count, parts, s);
+        if (bn == 192) return launch_fprop<192, 5, 1>(ta, tbp, to, p, count, parts, s);
+        if (bn == 128) return launch_fprop<128, 6, 1>(ta, tbp, to, p, count, parts, s);
+        if (bn == 96) return launch_fprop<96, 6, 1>(ta, tbp, to, p, count, parts, s);
+        return launch_fprop<64, 8, 1>(ta, tbp, to, p, count, parts, s);
+    };
+    const int S = xsb_sm_count_cached();
+    static const int wave_aware = [] { const char* e = getenv("XSB_TC_WAVES"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (BN == 256 && wave_aware) {
+        // One CTA per SM: tile counts that are not a multiple of the SM count leave SMs idle (98 tiles on 148 SMs =
+        // 66 %, 196 tiles = two waves at 66 %). Fewer tiles than SMs: split every tile's columns into floor(S/tiles)
+        // parts. A short tail wave after full waves (OC = 256): the tail m-tiles are split the same way.
+        const int n_tiles = j.OCx / 256;
+        const int64_t units = (int64_t)m_tiles * n_tiles;
+        if (units < S) {
+            int parts = S / m_tiles;
+            if (parts > j.OCx / 32) parts = j.OCx / 32;
+            if (parts > 16) parts = 16;
+            if (parts > n_tiles) return launch_parts(0, m_tiles, parts);
+        } else if (n_tiles == 1 && units % S != 0 && (units % S) * 10 < (int64_t)S * 7) {
+            const int main_tiles = (int)(units / S) * S, tail = m_tiles - main_tiles;
+            int parts = S / tail;
+            if (parts > j.OCx / 32) parts = j.OCx / 32;
+            if (parts > 16) parts = 16;
+            if (parts > 1) {
+                const int rc = launch_parts(0, main_tiles, 1);
+                if (rc != XSB_OK) return rc;
+                return launch_parts(main_tiles, tail, parts);
+            }
+        }
+    }
+    const int parts = j.OCx / BN;
+    if (parts > 16) return XSB_ERR_UNSUPPORTED;
+    for (int i = 0; i < parts; ++i) {
+        p.part_n0[i] = (short)(i * BN);
+        p.part_cols[i] = (short)BN;
+    }
+    p.m_tile0 = 0;
     if (tc_occupancy() == 1) {
-        if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, to, p, j.OCx / 256, s);
-        if (BN == 128) return launch_fprop<128, 6, 1>(ta, tb, to, p, j.OCx / 128, s);
-        return launch_fprop<64, 8, 1>(ta, tb, to, p, j.OCx / 64, s);
+        if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, to, p, m_tiles, parts, s);
+        if (BN == 128) return launch_fprop<128, 6, 1>(ta, tb, to, p, m_tiles, parts, s);
+        return launch_fprop<64, 8, 1>(ta, tb, to, p, m_tiles, parts, s);
     }
     // measured on B200 (tests/op_bench.py, R224): 2 CTAs/SM is +45 % for BN=64 and +19 % for BN=128, but -25 % for
     // BN=256 (only 2 stages fit) -> the widest tile keeps one CTA per SM with a 4-stage ring
-    if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, to, p, j.OCx / 256, s);
-    if (BN == 128) return launch_fprop<128, 3, 2>(ta, tb, to, p, j.OCx / 128, s);
-    return launch_fprop<64, 4, 2>(ta, tb, to, p, j.OCx / 64, s);
+    if (BN == 256) return launch_fprop<256, 4, 1>(ta, tb, to, p, m_tiles, parts, s);
+    if (BN == 128) return launch_fprop<128, 3, 2>(ta, tb, to, p, m_tiles, parts, s);
+    return launch_fprop<64, 4, 2>(ta, tb, to, p, m_tiles, parts, s);
 }
 
 template <int BN, int BKP, int STAGES>
