@@ -39,9 +39,16 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"],
-                    source="MEASURED_PEAKS.json")
-    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+        out = dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"],
+                   source="MEASURED_PEAKS.json")
+    else:
+        out = dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+    # dense TF32 measured the same way (tools/measure_tf32_peak.py, cuBLAS 8192^3): the conv kernels run kind::tf32
+    t32 = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    if os.path.exists(t32):
+        t = json.load(open(t32))
+        out.update(tf32_burst=t["tf32_tflops"], tf32_sustained=t["tf32_tflops_sustained"])
+    return out
 
 
 class ClockSampler:
@@ -91,7 +98,7 @@ class ClockSampler:
 def signature(name, a):
     """Kernel + shape key for the per-launch roofline (conv geometry / GEMM dims / element count)."""
     try:
-        if name == "xsb_conv2d_fwd":
+        if name in ("xsb_conv2d_fwd", "xsb_conv2d_fwd_stats"):
             N, H, W, C, OC, KH, KW, sh, sw, pad = a[4:14]
         elif name in ("xsb_conv2d_dgrad", "xsb_conv2d_wgrad"):
             N, H, W, C, OC, KH, KW, sh, sw, pad = a[3:13]
@@ -101,7 +108,7 @@ def signature(name, a):
             return f"{name}[R{a[5]} C{a[6]}]"
         elif name in ("xsb_bn_apply",):
             return f"{name}[R{a[6]} C{a[7]} relu{a[8]}]"
-        elif name in ("xsb_bn_bwd", "xsb_bn_train_fwd"):
+        elif name in ("xsb_bn_bwd", "xsb_bn_train_fwd", "xsb_bn_bwd_dxsum"):
             return f"{name}[R{a[8]} C{a[9]}]"
         elif name == "xsb_colsum":
             return f"{name}[R{a[2]} C{a[3]}]"
@@ -327,7 +334,9 @@ def run_ours(args, wl):
         # kind::tf32 runs at half the bf16 rate; the FFMA (fp32) mode is still reported against the tensor peak
         peak = pk["tc_sustained"]
         roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
-                    frac_of_tf32_nominal=achieved / (peak / 2.0) if args.math == "tf32" else None)
+                    frac_of_tf32_nominal=achieved / (peak / 2.0) if args.math == "tf32" else None,
+                    tf32_measured_peak=pk.get("tf32_sustained"),
+                    frac_of_tf32_measured=(achieved / pk["tf32_sustained"]) if (args.math == "tf32" and pk.get("tf32_sustained")) else None)
     else:
         achieved = td["amount"] / (td["ms"] * 1e-3) / 1e9
         roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic)

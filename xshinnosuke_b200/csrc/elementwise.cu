@@ -214,6 +214,48 @@ __global__ void transpose_batched(const float* __restrict__ src, float* dst, int
     }
 }
 
+// nchw -> nhwc for images with C <= 4 channels (the network input): a 32-row tile would be 3/32 full. One thread
+// takes 4 consecutive pixels: C coalesced 128-bit plane reads, C 128-bit writes of the 4*C interleaved floats.
+template <int C, bool kAcc>
+__global__ void nchw_to_nhwc_smallc_k(const float4* __restrict__ src, float4* dst, int64_t hw4, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (image, pixel quad)
+    if (t >= total) return;
+    const int64_t img = t / hw4, q = t - img * hw4;
+    float v[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float4 f = ldg_stream(src + (img * C + c) * hw4 + q);
+        v[c][0] = f.x; v[c][1] = f.y; v[c][2] = f.z; v[c][3] = f.w;
+    }
+    float o[4 * C];
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[px * C + c] = v[c][px];
+    float4* d = dst + t * C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        float4 r = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        if (kAcc) {
+            const float4 e = d[j];
+            r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+        }
+        d[j] = r;
+    }
+}
+
+template <int C>
+static void launch_smallc(const float* src, float* dst, int N, int64_t hw, int accumulate, cudaStream_t s) {
+    const int64_t hw4 = hw / 4, total = (int64_t)N * hw4;
+    const unsigned blocks = (unsigned)ceil_div64(total, 256);
+    if (accumulate)
+        nchw_to_nhwc_smallc_k<C, true><<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(src),
+                                                              reinterpret_cast<float4*>(dst), hw4, total);
+    else
+        nchw_to_nhwc_smallc_k<C, false><<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(src),
+                                                               reinterpret_cast<float4*>(dst), hw4, total);
+}
+
 // ---- y[o,i] = scale * sum_r x[o,r,i] ; dx[o,r,i] (+)= scale * dy[o,i] -------------------------
 __global__ void reduce_axis_k(const float* __restrict__ x, float* __restrict__ y, int64_t outer, int64_t red,
                               int64_t inner, float scale) {
@@ -345,6 +387,14 @@ int xsb_fill(float* dst, float value, int64_t n, void* stream) {
 int xsb_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int accumulate, void* stream) {
     const int rows = C, cols = H * W;
     if (N <= 0 || rows <= 0 || cols <= 0) return XSB_OK;
+    if (C >= 2 && C <= 4 && cols % 4 == 0 && aligned16(src) && aligned16(dst)) {
+        cudaStream_t s = xsb_stream(stream);
+        if (C == 2) launch_smallc<2>(src, dst, N, cols, accumulate, s);
+        else if (C == 3) launch_smallc<3>(src, dst, N, cols, accumulate, s);
+        else launch_smallc<4>(src, dst, N, cols, accumulate, s);
+        XSB_LAUNCH_CHECK();
+        return XSB_OK;
+    }
     XSB_CHECK_ARG(N <= 65535, "batch %d exceeds grid.z", N);
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, N), block(32, 8);
     if (accumulate)

@@ -17,7 +17,7 @@ def _pool_out(H, W, k, sh, sw, pad):
 
 
 def cost(name, a):
-    if name == "xsb_conv2d_fwd":
+    if name in ("xsb_conv2d_fwd", "xsb_conv2d_fwd_stats"):
         return "flop", _conv_flops(a, 4)
     if name in ("xsb_conv2d_dgrad", "xsb_conv2d_wgrad"):
         return "flop", _conv_flops(a, 3)
@@ -62,8 +62,10 @@ def cost(name, a):
         return "byte", 8.0 * a[6] * a[7] + (a[6] * a[7] / 8.0 if a[8] else 0.0)
     if name == "xsb_add_relu":
         return "byte", 12.0 * a[4] + a[4] / 8.0
-    if name == "xsb_bn_bwd":
+    if name in ("xsb_bn_bwd", "xsb_bn_bwd_dxsum"):
         return "byte", (20.0 if a[5] else 8.0) * a[8] * a[9]
+    if name == "xsb_bn_finalize":
+        return "byte", 12.0 * a[1] * a[3]      # P partials x {n, mean, M2} x C
     if name == "xsb_colsum":
         return "byte", 4.0 * a[2] * a[3]
     if name == "xsb_sgd_step":
