@@ -32,13 +32,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-enum { DATA = 1, BULK = 2, STG = 4, LDTM = 8 };
+enum { DATA = 1, BULK = 2, STG = 4, LDTM = 8, COMMIT8 = 16, WAIT8 = 32, ACC6 = 64, COMMIT4 = 128, NOFENCE = 256, NOWAIT = 512, WAIT16 = 1024, LDSPOLL = 2048, DUAL = 4096 };
 
 template <int N, int FLAGS>
 __global__ void __launch_bounds__(192, 1) rate_k(long long* out, int iters, const float* gsrc, float* gdst) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t bar, cbar[2];
+    __shared__ uint64_t bar, bar2, cbar[2];
     __shared__ uint32_t slot;
     __shared__ volatile int stop;
     for (int i = threadIdx.x; i < (96 * 1024) / 4; i += blockDim.x) {
@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(192, 1) rate_k(long long* out, int iters, cons
     if (threadIdx.x == 0) {
         stop = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&cbar[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&cbar[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -62,23 +63,42 @@ __global__ void __launch_bounds__(192, 1) rate_k(long long* out, int iters, cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = slot;
-    if (warp == 1) {
+    if (warp == 1 || ((FLAGS & DUAL) && warp == 2)) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(N);
             const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32 * 1024);
             long long t0 = clock64();
+            __shared__ uint64_t dummy[2];
+            if ((FLAGS & (COMMIT8 | COMMIT4 | WAIT8)) && warp == 2) { for (volatile int z = 0; z < 2000; ++z) {} }
+            if ((FLAGS & (COMMIT8 | COMMIT4 | WAIT8)) && warp == 1) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy[0])) : "memory");
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy[1])) : "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&dummy[1])) : "memory");   // phase 0 of [1] complete
+            }
             for (int i = 0; i < iters; ++i) {
                 const int st = i & 1;
                 const uint64_t da = make_desc(a0 + st * 16384, 16, 1024);
                 const uint64_t db = make_desc(b0 + st * 32768, 16, 1024);
+                if ((FLAGS & WAIT8) && ((FLAGS & WAIT16) ? (i & 3) == 0 : (i & 1) == 0)) {
+                    if (FLAGS & LDSPOLL) {
+                        uint32_t v;
+                        do {
+                            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&dummy[1])) : "memory");
+                        } while (v == 0xFFFFFFFFu);
+                    } else if (!(FLAGS & NOWAIT)) mbar_wait(&dummy[1], 0);     // already complete: pure try_wait latency
+                    if (!(FLAGS & NOFENCE)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t acc = (FLAGS & ACC6) ? tmem + (uint32_t)(((i >> 1) % 6) * 64) : tmem;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1);
+                for (int k = 0; k < 4; ++k) umma(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1);
+                if (((FLAGS & COMMIT8) && (i & 1) == 1) || (FLAGS & COMMIT4))
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[0])) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
-            mbar_wait(&bar, 0);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(warp == 1 ? &bar : &bar2)) : "memory");
+            mbar_wait(warp == 1 ? &bar : &bar2, 0);
             long long t1 = clock64();
-            stop = 1;
-            if (blockIdx.x == 0) out[0] = t1 - t0;
+            if (warp == 1) stop = 1;
+            if (blockIdx.x == 0 && warp == 1) out[0] = t1 - t0;
         }
     } else if (warp == 0) {
         if ((FLAGS & BULK) && lane == 0) {
@@ -100,7 +120,7 @@ __global__ void __launch_bounds__(192, 1) rate_k(long long* out, int iters, cons
             if (it >= 1) mbar_wait(&cbar[(it - 1) & 1], ((it - 1) >> 1) & 1);
             if (it >= 2) mbar_wait(&cbar[(it - 2) & 1], ((it - 2) >> 1) & 1);
         }
-    } else {
+    } else if (!((FLAGS & DUAL) && warp == 2)) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         float* orow = gdst + ((size_t)blockIdx.x * 4096 + row) * 64;
@@ -163,6 +183,18 @@ void sweep() {
     run<N, DATA | STG>("data + strided STG.128");
     run<N, DATA | LDTM>("data + tcgen05.ld");
     run<N, DATA | BULK | STG | LDTM>("data + bulk + STG + ld");
+    run<N, DATA | COMMIT8>("commit every 8 MMAs");
+    run<N, DATA | COMMIT4>("commit every 4 MMAs");
+    run<N, DATA | COMMIT8 | WAIT8>("try_wait + commit every 8");
+    run<N, DATA | COMMIT8 | WAIT8 | ACC6>("try_wait + commit /8, 6 accumulators");
+    run<N, DATA | COMMIT8 | WAIT8 | ACC6 | BULK>("same + bulk copies");
+    run<N, DATA | COMMIT8 | WAIT8 | NOFENCE>("try_wait (no fence) + commit /8");
+    run<N, DATA | COMMIT8 | WAIT8 | NOWAIT>("fence only + commit /8");
+    run<N, DATA | COMMIT8 | WAIT8 | WAIT16>("try_wait+fence every 16, commit /8");
+    run<N, DATA | WAIT8 | NOFENCE>("try_wait every 8, no commit");
+    run<N, DATA | COMMIT8 | WAIT8 | LDSPOLL>("ld.shared poll + fence + commit /8");
+    run<N, DATA | COMMIT8 | WAIT8 | DUAL>("DUAL issuers: try_wait+commit /8 each");
+    run<N, DATA | COMMIT4 | WAIT8 | DUAL>("DUAL issuers: try_wait/8 commit/4");
 }
 
 int main() {
@@ -171,6 +203,5 @@ int main() {
     cudaMalloc(&g_dst, (size_t)148 * 4096 * 64 * 4);
     sweep<64>();
     sweep<128>();
-    sweep<256>();
     return 0;
 }

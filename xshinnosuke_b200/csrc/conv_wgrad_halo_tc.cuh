@@ -1,0 +1,250 @@
+// Persistent tcgen05 weight-gradient kernel for stride-1 convolutions (XSB_MATH_TF32):
+//   dW[oc, kh, kw, c] (+)= sum_{n,oh,ow} dY[n,oh,ow,oc] * x[n, oh+kh-pad, ow+kw-pad, c]        (xs/nn/grad_fn.py:186-194)
+//
+// conv_wgrad_tc_k gives every 128-row block of (tap, c) its own CTAs: each re-reads dY and fetches the im2col patch
+// of its taps -- 22 FLOP per L2->SM byte at C = OC = 64, i.e. pinned to the ~12 TB/s L2->SM fabric. Here
+//  * one CTA owns ALL filter rows of `cbp` channel blocks x KW filter columns x BN output channels: cbp*KW
+//    accumulators of 128 x BN in TMEM (<= 512 columns), so a dY tile is loaded once for every (tap, c) it meets;
+//  * the pixel (K) dimension walks 8 x 8 output tiles; for filter column kw and channel block cb ONE TMA halo block
+//    {32 ch, 8 w, 8+KH-1 rows} lands as rows of 128 B (pixel-major = MN-major A operand, SWIZZLE_128B_ATOM_32B);
+//    tile row r / filter row kh is the 1024-byte group at (r + kh)*1024, so the four 32-row M blocks of one MMA are
+//    the filter rows kh = 0..3 (descriptor LBO = 1024 B; rows of a non-existent kh land in accumulator lanes nobody
+//    reads) and the K = 8 pixels of tile row r start at r*1024: KH x less patch traffic than im2col, no re-read of dY;
+//  * CTAs are persistent over a contiguous range of tiles (split-K across CTAs), accumulate in TMEM over the whole
+//    range and leave with ONE TMA reduce-add of a {32 c, 32 oc} box per warp, accumulator and 32 output channels.
+// grid = (CTAs per pass, passes); pass = (channel-block group, BN-wide output-channel tile).
+#pragma once
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int WH_TW = 8, WH_TH = 8;     // output tile = 64 pixels = 8 MMAs of K = 8
+
+struct WgradHaloParams {
+    int N, OH, OW;
+    int tiles_w, tiles_h, n_tiles;
+    int KH, KW, pad, cblocks;
+    int cbp;              // channel blocks per pass
+    int n_oc_tiles;       // OC / BN
+    int sa_slots, sb_slots, a_slot_bytes;
+    int C;                // input channels (column stride of the dW map)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                  const __grid_constant__ CUtensorMap tmW, const WgradHaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int B_BOX = WH_TW * WH_TH * A_ROW_BYTES;     // 64 pixels x 32 oc = 8 KB
+    constexpr int B_BYTES = (BN / 32) * B_BOX;
+    constexpr int MAXS = 16;
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + p.sa_slots * p.a_slot_bytes;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + p.sb_slots * B_BYTES);
+    uint64_t* emptyA = fullA + MAXS;
+    uint64_t* fullB = emptyA + MAXS;
+    uint64_t* emptyB = fullB + 4;
+    uint64_t* tmem_full = emptyB + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int SA = p.sa_slots, SB = p.sb_slots;
+    const int pass = blockIdx.y;
+    const int oc0 = (pass % p.n_oc_tiles) * BN;
+    const int cb0 = (pass / p.n_oc_tiles) * p.cbp;
+    int cbn = p.cblocks - cb0;                 // channel blocks of this pass
+    if (cbn > p.cbp) cbn = p.cbp;
+    const int n_acc = cbn * p.KW;
+    // contiguous tile range of this CTA
+    const int t_begin = (int)((int64_t)blockIdx.x * p.n_tiles / gridDim.x);
+    const int t_end = (int)((int64_t)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmDy);
+        prefetch_tmap(&tmW);
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(&fullA[i], 1);
+            mbar_init(&emptyA[i], 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(&fullB[i], 1);
+            mbar_init(&emptyB[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int a_box_bytes = (WH_TH + p.KH - 1) * WH_TW * A_ROW_BYTES;   // bytes the halo load writes (slot has 1 row more)
+
+    if (warp == 0) {
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0;
+        int n_img = t_begin / tiles_per_img, rem = t_begin - n_img * tiles_per_img;
+        int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int w0 = tw * WH_TW, h0 = th * WH_TH;
+            mbar_wait(&emptyB[sb], phb ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&fullB[sb], B_BYTES);
+#pragma unroll
+                for (int b = 0; b < BN / 32; ++b)
+                    tma_load_4d(sB + sb * B_BYTES + b * B_BOX, &tmDy, &fullB[sb], oc0 + b * 32, w0, h0, n_img);
+            }
+            if (++sb == SB) { sb = 0; phb ^= 1; }
+            for (int cb = cb0; cb < cb0 + cbn; ++cb)
+                for (int kw = 0; kw < p.KW; ++kw) {
+                    mbar_wait(&emptyA[sa], pha ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&fullA[sa], a_box_bytes);
+                        tma_load_4d(sA + sa * p.a_slot_bytes, &tmX, &fullA[sa], cb * 32, w0 + kw - p.pad, h0 - p.pad, n_img);
+                    }
+                    if (++sa == SA) { sa = 0; pha ^= 1; }
+                }
+            if (++tw == p.tiles_w) {
+                tw = 0;
+                if (++th == p.tiles_h) { th = 0; ++n_img; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+        const uint32_t hi = desc_hi(512, kLayoutSW128Base32B);
+        const uint32_t a_lo0 = desc_lo(smem_u32(sA), 1024), b_lo0 = desc_lo(smem_u32(sB), B_BOX);
+        const uint32_t a_enc = (uint32_t)p.a_slot_bytes >> 4;
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0, a_lo = a_lo0, b_lo = b_lo0;
+        uint32_t fresh = 0;     // 0 while this CTA's accumulators have not been written yet
+        for (int t = t_begin; t < t_end; ++t) {
+            mbar_wait(&fullB[sb], phb);
+            for (int a = 0; a < n_acc; ++a) {
+                mbar_wait(&fullA[sa], pha);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+#pragma unroll
+                    for (int r = 0; r < WH_TH; ++r)   // tile row r: K = 8 pixels = 1024 bytes of both operands
+                        umma_tf32_split(tacc, a_lo + (uint32_t)(r * 64), hi, b_lo + (uint32_t)(r * 64), hi, idesc,
+                                        r ? 1u : fresh);
+                    umma_commit(&emptyA[sa]);
+                    if (a == n_acc - 1) umma_commit(&emptyB[sb]);
+                }
+                __syncwarp();
+                a_lo += a_enc;
+                if (++sa == SA) { sa = 0; pha ^= 1; a_lo = a_lo0; }
+            }
+            fresh = 1;
+            b_lo += (uint32_t)(B_BYTES >> 4);
+            if (++sb == SB) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+        }
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
+    } else {
+        // warp q reads TMEM lanes 32q..32q+31 = filter row kh = q, channel lane; lanes of kh >= KH hold garbage
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (t_end > t_begin && q < p.KH) {
+            float* stage = reinterpret_cast<float*>(sA + q * 4096);    // the rings are idle: [32 oc][32 c] per warp
+            for (int a = 0; a < n_acc; ++a) {
+                const int cb = cb0 + a / p.KW, kw = a - (a / p.KW) * p.KW;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), v);
+                    tmem_wait_ld();
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stage[j * 32 + lane] = __uint_as_float(v[j]);   // row = oc, column = c
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tmW, stage, (q * p.KW + kw) * p.C + cb * 32, oc0 + c0);
+                        bulk_commit();
+                    }
+                }
+            }
+            if (lane == 0) bulk_wait_all<0>();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dw must hold the value to accumulate onto (zeros for "="): every CTA reduce-adds its partial sums.
+// Returns XSB_ERR_UNSUPPORTED outside the envelope (caller runs conv_wgrad_tc_k).
+static int wgrad_halo(const float* dy, const float* x, float* dw, const ConvGeom& g, cudaStream_t s) {
+    if (g.sh != 1 || g.sw != 1 || g.C % 32 != 0 || g.OC % 64 != 0 || g.KH > 4 || g.KH < 2 || g.KW > 8) return XSB_ERR_UNSUPPORTED;
+    const int BN = g.OC % 128 == 0 ? 128 : 64;
+    const int cblocks = g.C / 32;
+    int cbp = 512 / (g.KW * BN);               // accumulators of one pass: cbp * KW * BN <= 512 TMEM columns
+    if (cbp < 1) return XSB_ERR_UNSUPPORTED;
+    if (cbp > cblocks) cbp = cblocks;
+    const int cb_groups = (cblocks + cbp - 1) / cbp;
+    const int n_oc_tiles = g.OC / BN;
+    const int passes = cb_groups * n_oc_tiles;
+    const int S = xsb_sm_count_cached();
+    if (passes > S) return XSB_ERR_UNSUPPORTED;
+    const int tiles_w = (g.OW + WH_TW - 1) / WH_TW, tiles_h = (g.OH + WH_TH - 1) / WH_TH;
+    // tiles mostly outside the image (small feature maps) waste the MMAs: leave those to the im2col kernel
+    if ((int64_t)g.OH * g.OW * 10 < (int64_t)tiles_w * tiles_h * WH_TW * WH_TH * 7) return XSB_ERR_UNSUPPORTED;
+    const int n_tiles = g.N * tiles_w * tiles_h;
+    int ctas = S / passes;
+    if (ctas > n_tiles) ctas = n_tiles;
+    if (ctas < 1) return XSB_ERR_UNSUPPORTED;
+    if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
+    const int a_rows = WH_TH + g.KH - 1;
+    const int a_slot_bytes = (WH_TH + 4) * WH_TW * A_ROW_BYTES;   // room for the rows the (unused) M blocks kh < 4 touch
+    const int b_bytes = (BN / 32) * WH_TW * WH_TH * A_ROW_BYTES;
+    const int sb_slots = 3;
+    int sa_slots = (227 * 1024 - 1024 - 512 - sb_slots * b_bytes) / a_slot_bytes;
+    if (sa_slots > 16) sa_slots = 16;
+    if (sa_slots < 4) return XSB_ERR_UNSUPPORTED;
+    CUtensorMap tx, tdy, tw;
+    cuuint64_t xd[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t xs_[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.W * g.C * 4, (cuuint64_t)g.H * g.W * g.C * 4};
+    cuuint32_t xb[4] = {32, WH_TW, (cuuint32_t)a_rows, 1};
+    cuuint64_t dd[4] = {(cuuint64_t)g.OC, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+    cuuint64_t ds[3] = {(cuuint64_t)g.OC * 4, (cuuint64_t)g.OW * g.OC * 4, (cuuint64_t)g.OH * g.OW * g.OC * 4};
+    cuuint32_t db[4] = {32, WH_TW, WH_TH, 1};
+    if (!make_map_tiled(&tx, x, 4, xd, xs_, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map_tiled(&tdy, dy, 4, dd, ds, db, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map_2d(&tw, dw, (uint64_t)g.OC, (uint64_t)g.KH * g.KW * g.C, 32, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return XSB_ERR_UNSUPPORTED;
+    WgradHaloParams p{g.N, g.OH, g.OW, tiles_w, tiles_h, n_tiles, g.KH, g.KW, g.pad, cblocks, cbp, n_oc_tiles,
+                      sa_slots, sb_slots, a_slot_bytes, g.C};
+    const int smem = 1024 + sa_slots * a_slot_bytes + sb_slots * b_bytes + 512;
+    dim3 grid(ctas, passes);
+    if (BN == 64) {
+        static bool configured = false;
+        if (!configured) {
+            XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_k<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured = true;
+        }
+        conv_wgrad_halo_k<64><<<grid, kThreads, smem, s>>>(tx, tdy, tw, p);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_k<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured = true;
+        }
+        conv_wgrad_halo_k<128><<<grid, kThreads, smem, s>>>(tx, tdy, tw, p);
+    }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+}  // namespace tc
