@@ -280,6 +280,44 @@ def test_conv_bn_relu_fused_statistics_tf32(n, c, h, oc, k, s, p):
         xs.set_math_mode("fp32")
 
 
+@pytest.mark.parametrize("n,c,h,oc,k,s,p", [(4, 128, 14, 256, 3, 1, 1), (24, 256, 7, 512, 3, 1, 1), (100, 128, 14, 256, 3, 1, 1),
+                                          (9, 64, 28, 128, 3, 1, 1), (5, 128, 9, 256, 1, 1, 0)])
+def test_conv_cta_pair_kernels_tf32(n, c, h, oc, k, s, p):
+    """The cta_group::2 forward kernels (two CTAs, M = 256 MMAs issued by the leader, B split across the pair; opt-in):
+    fwd, stride-1 dgrad and the fused BN statistics against the float64 oracle, incl. odd tile counts (the last pair's
+    second CTA has no tile), column parts and the split tail wave."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.nn import functional as F
+    xs.set_math_mode("tf32")
+    lib.xsb_tc_config(0, 1)
+    try:
+        rs = np.random.RandomState(3 * n + c + h)
+        x = rs.randn(n, c, h, h).astype(np.float32)
+        w = (rs.randn(oc, c, k, k) * 0.1).astype(np.float32)
+        b = rs.randn(1, oc).astype(np.float32)
+        gm, bt = (rs.rand(oc) + 0.5).astype(np.float32), rs.randn(oc).astype(np.float32)
+        tx, tw, tb = xs.tensor(x, requires_grad=True), nn.Parameter(w), nn.Parameter(b)
+        mm, mv = xs.tensor(np.zeros(oc, dtype=np.float32)), xs.tensor(np.ones(oc, dtype=np.float32))
+        yc = F.conv2d(tx, tw, tb, (s, s), p)
+        yb = F.batch_norm(yc, nn.Parameter(gm), nn.Parameter(bt), mm, mv, 1, True, 1e-6, 0.99)
+        conv_out = yc.eval.astype(np.float64)
+        yr, col = X.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), p)
+        assert X.rel_err(conv_out, yr) <= TOL_TC
+        assert X.rel_err(mm.eval, 0.01 * conv_out.mean(axis=(0, 2, 3))) <= 1e-5
+        assert X.rel_err(mv.eval, 0.99 + 0.01 * conv_out.var(axis=(0, 2, 3))) <= 1e-5
+        g = rs.randn(*yr.shape).astype(np.float32)
+        y2 = F.conv2d(tx, tw, tb, (s, s), p)
+        y2.backward(gradients=g)
+        dx, dw, db = X.conv2d_bwd(g.astype(np.float64), x.shape, w.astype(np.float64), col, (s, s), p)
+        assert X.rel_err(tx.grad.eval, dx) <= TOL_TC and X.rel_err(tw.grad.eval, dw) <= TOL_TC
+    finally:
+        lib.xsb_tc_config(0, 0)
+        xs.set_math_mode("fp32")
+
+
 def test_resnet18_tf32_mode(golden):
     """Whole ResNet-18 step in tf32 mode: logits of the first forward within 2e-3 of the reference."""
     import xshinnosuke_b200 as xs

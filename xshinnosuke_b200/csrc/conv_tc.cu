@@ -41,6 +41,71 @@ struct FpropParams {
     short part_n0[16], part_cols[16];
 };
 
+// Non-strided epilogue shared by the 1-CTA and 2-CTA im2col kernels. Every MMA has completed, so the operand ring is
+// idle: its first 16 KB become four SWIZZLE_128B staging blocks (one per epilogue warp); a warp's 32 rows x 32 columns
+// leave as ONE TMA store / reduce-add of a {32 ch, 32 pixel} box of out[M, ldo] (rows >= M are clipped by the tensor
+// map); optional BatchNorm partial statistics are gathered from the staged block.
+template <int BN>
+__device__ __forceinline__ void epilogue_store_tma(const FpropParams& p, const CUtensorMap* tmOp, uint32_t tmem_base,
+                                                   uint8_t* sA, int q, int lane, int m_tile, int m0, int n0, int ncols) {
+    const CUtensorMap& tmO = *tmOp;
+    const int row = q * 32 + lane;
+        uint8_t* stage = sA + q * 4096;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_wait_ld();
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                    o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+                }
+            }
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            stage_rows_sw128(stage, lane, o);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m0 + q * 32 < p.M) {
+                if (p.accumulate)
+                    tma_reduce_add_2d(&tmO, stage, n0 + c0, m0 + q * 32);
+                else
+                    tma_store_2d(&tmO, stage, n0 + c0, m0 + q * 32);
+                bulk_commit();
+            }
+            if (p.stats) {   // this warp's 32 rows of columns c0..c0+31 -> (n, mean, M2) per column
+                const int left = p.M - (m0 + q * 32);
+                const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? ((1u << left) - 1u) : 0u);
+                const Moments mo = stage_col_moments(stage, lane, vm);
+                float* sStat = reinterpret_cast<float*>(sA + 16384) + q * 3 * BN + c0 + lane;
+                sStat[0] = mo.n;
+                sStat[BN] = mo.mean;
+                sStat[2 * BN] = mo.m2;
+            }
+        }
+        if (lane == 0) bulk_wait_all<0>();
+        if (p.stats) {   // merge the four warps, one partial per CTA and column
+            epilogue_bar();
+            const float* sStat = reinterpret_cast<const float*>(sA + 16384);
+            for (int col = row; col < ncols; col += 128) {
+                Moments acc{0.f, 0.f, 0.f};
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4)
+                    acc = merge_moments(acc, Moments{sStat[w4 * 3 * BN + col], sStat[(w4 * 3 + 1) * BN + col],
+                                                     sStat[(w4 * 3 + 2) * BN + col]});
+                float* dst = p.stats + (int64_t)m_tile * 3 * p.ldo + n0 + col;
+                dst[0] = acc.n;
+                dst[p.ldo] = acc.mean;
+                dst[2 * p.ldo] = acc.m2;
+            }
+        }
+}
+
 template <int BN, int STAGES, int OCC>
 __global__ void __launch_bounds__(kThreads, OCC)
 conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -129,63 +194,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row = q * 32 + lane;
         const int m = m0 + row;
         if (!p.o_strided) {
-            // every MMA has completed, so the operand ring is idle: its first 16 KB become four SWIZZLE_128B staging
-            // blocks (one per epilogue warp); a warp's 32 rows x 32 columns leave as ONE TMA store / reduce-add of a
-            // {32 ch, 32 pixel} box of out[M, ldo] (rows >= M are clipped by the tensor map)
-            uint8_t* stage = sA + q * 4096;
-#pragma unroll 1
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                tmem_wait_ld();
-                float o[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-                        o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
-                    }
-                }
-                if (lane == 0) bulk_wait_read<0>();
-                __syncwarp();
-                stage_rows_sw128(stage, lane, o);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0 && m0 + q * 32 < p.M) {
-                    if (p.accumulate)
-                        tma_reduce_add_2d(&tmO, stage, n0 + c0, m0 + q * 32);
-                    else
-                        tma_store_2d(&tmO, stage, n0 + c0, m0 + q * 32);
-                    bulk_commit();
-                }
-                if (p.stats) {   // this warp's 32 rows of columns c0..c0+31 -> (n, mean, M2) per column
-                    const int left = p.M - (m0 + q * 32);
-                    const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? ((1u << left) - 1u) : 0u);
-                    const Moments mo = stage_col_moments(stage, lane, vm);
-                    float* sStat = reinterpret_cast<float*>(sA + 16384) + q * 3 * BN + c0 + lane;
-                    sStat[0] = mo.n;
-                    sStat[BN] = mo.mean;
-                    sStat[2 * BN] = mo.m2;
-                }
-            }
-            if (lane == 0) bulk_wait_all<0>();
-            if (p.stats) {   // merge the four warps, one partial per CTA and column
-                epilogue_bar();
-                const float* sStat = reinterpret_cast<const float*>(sA + 16384);
-                for (int col = row; col < ncols; col += 128) {
-                    Moments acc{0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int w4 = 0; w4 < 4; ++w4)
-                        acc = merge_moments(acc, Moments{sStat[w4 * 3 * BN + col], sStat[(w4 * 3 + 1) * BN + col],
-                                                         sStat[(w4 * 3 + 2) * BN + col]});
-                    float* dst = p.stats + (int64_t)m_tile * 3 * p.ldo + n0 + col;
-                    dst[0] = acc.n;
-                    dst[p.ldo] = acc.mean;
-                    dst[2 * p.ldo] = acc.m2;
-                }
-            }
+            epilogue_store_tma<BN>(p, &tmO, tmem_base, sA, q, lane, m_tile, m0, n0, ncols);
         } else {
             const int hw = p.OH * p.OW;
             const int n_img = m / hw, rem = m - n_img * hw;
@@ -222,6 +231,113 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ fprop, CTA pairs
+// Same implicit GEMM on a cluster of two CTAs (adjacent m-tiles): each CTA loads its own A tile and HALF of the B
+// tile (rows [rank*BN/2, +BN/2) of the column part), the leader issues M = 256 MMAs, accumulator rows 0..127 land in
+// the leader's TMEM and 128..255 in the peer's; each CTA runs its own epilogue. Per SM and k-block: 16 + BN/2*128 B of
+// fills and 32 + BN/8 operand wavefronts per MMA instead of 16 KB + BN*128 B and 32 + BN/4.
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_fprop_tc2_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const FpropParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int A_BYTES = BM * A_ROW_BYTES;
+    constexpr int BH_BYTES = (BN / 2) * A_ROW_BYTES;
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * BH_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cblocks = p.C / 32;
+    const int num_kb = p.KH * p.KW * cblocks;
+    const int m_tile = p.m_tile0 + blockIdx.x;
+    const int m0 = m_tile * BM, n0 = p.part_n0[blockIdx.y], ncols = p.part_cols[blockIdx.y];   // ncols: multiple of 32
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        prefetch_tmap(&tmO);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    if (warp == 1) {
+        tmem_alloc2(tmem_slot, TMEM_COLS);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();        // both CTAs' barriers are initialised before any remote complete_tx / commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        const int hw = p.OH * p.OW;
+        const int m0l = m0 < p.M ? m0 : 0;                // odd tile count: the last pair's second CTA loads tile 0 again
+        const int n_img = m0l / hw, rem = m0l - n_img * hw;
+        const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+        const int w0 = ow0 * p.sw - p.pad_w, h0 = oh0 * p.sh - p.pad_h;
+        const int nb = n0 + (int)rank * (ncols / 2);      // this CTA's half of the B rows
+        int s = 0, kb = 0;
+        uint32_t ph = 0;
+        for (int kh = 0; kh < p.KH; ++kh)
+            for (int kw = 0; kw < p.KW; ++kw)
+                for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&full[s], 2 * (A_BYTES + BH_BYTES));
+                        tma2_load_im2col(sA + s * A_BYTES, &tmA, &full[s], cb * 32, w0, h0, n_img, (uint16_t)kw, (uint16_t)kh);
+                        tma2_load_2d(sB + s * BH_BYTES, &tmB, &full[s], kb * 32, nb);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc2(ncols);
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = make_desc(a_base + s * A_BYTES, 16, 1024);
+                    const uint64_t db = make_desc(b_base + s * BH_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma2_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma2_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            if (elect_one()) umma2_commit(tmem_full);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (m0 < p.M) epilogue_store_tma<BN>(p, &tmO, tmem_base, sA, q, lane, m_tile, m0, n0, ncols);
+        tc_fence_before();
+    }
+    __syncthreads();
+    cluster_sync_all();        // the peer's shared memory / TMEM stay alive until both CTAs are done
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, TMEM_COLS);
     }
 }
 
@@ -618,6 +734,7 @@ static bool make_map_im2col(CUtensorMap* m, const float* base, int N, int H, int
 }
 
 static uint64_t g_tc_launches = 0, g_ffma_fallbacks = 0;
+static int g_pair_mode = -1;     // -1: read XSB_TC_PAIR on first use
 
 // XSB_TC_OCC=1|2 (env, read once): CTAs per SM for the fprop kernel. 2 (default) halves the smem ring of each CTA
 // so that one CTA's epilogue overlaps the other's mainloop.
@@ -641,6 +758,21 @@ static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const CUtens
     }
     dim3 grid(m_tiles, n_parts);
     conv_fprop_tc_k<BN, STAGES, OCC><<<grid, kThreads, smem, s>>>(a, b, o, p);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_fprop2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const FpropParams& p, int m_tiles,
+                         int n_parts, cudaStream_t s) {
+    constexpr int smem = STAGES * (BM * A_ROW_BYTES + (BN / 2) * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        XSB_CUDA(cudaFuncSetAttribute(conv_fprop_tc2_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(2 * ((m_tiles + 1) / 2), n_parts);     // clusters of 2 along x
+    conv_fprop_tc2_k<BN, STAGES><<<grid, kThreads, smem, s>>>(a, b, o, p);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }
@@ -705,7 +837,58 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
         if (bn == 96) return launch_fprop<96, 6, 1>(ta, tbp, to, p, count, parts, s);
         return launch_fprop<64, 8, 1>(ta, tbp, to, p, count, parts, s);
     };
+    // CTA-pair variant of launch_parts (cta_group::2): `count` m-tiles as ceil(count/2) clusters
+    auto launch_parts2 = [&](int m_tile0, int count, int parts) -> int {
+        const int w32 = j.OCx / 32, base = w32 / parts, extra = w32 % parts;
+        int n0 = 0, widest = 0;
+        for (int i = 0; i < parts; ++i) {
+            const int cols = (base + (i < extra ? 1 : 0)) * 32;
+            p.part_n0[i] = (short)n0;
+            p.part_cols[i] = (short)cols;
+            n0 += cols;
+            if (cols > widest) widest = cols;
+        }
+        p.m_tile0 = m_tile0;
+        const int bn = widest <= 64 ? 64 : widest <= 128 ? 128 : widest <= 192 ? 192 : 256;
+        CUtensorMap tbp;
+        if (!make_map_2d(&tbp, j.flt, (uint64_t)j.OCx, (uint64_t)j.KH * j.KW * j.Cx, (uint32_t)(bn / 2))) {
+            xsb_set_error("cuTensorMapEncode failed (fprop filter box %d)", bn / 2);
+            return XSB_ERR_CUDA;
+        }
+        if (bn == 256) return launch_fprop2<256, 6>(ta, tbp, to, p, count, parts, s);
+        if (bn == 192) return launch_fprop2<192, 7>(ta, tbp, to, p, count, parts, s);
+        if (bn == 128) return launch_fprop2<128, 8>(ta, tbp, to, p, count, parts, s);
+        return launch_fprop2<64, 8>(ta, tbp, to, p, count, parts, s);
+    };
     const int S = xsb_sm_count_cached();
+    // CTA pairs (cta_group::2) halve the B fills and operand reads per SM; measured on R224 they tie the 1-CTA kernels on
+    // layer3 (53 vs 54 us), and lose where pairs leave SMs idle (layer4: 50 clusters on 74 pair slots) or where the 1-CTA
+    // kernel runs two CTAs per SM (layer2): opt-in (XSB_TC_PAIR=1 / xsb_tc_config(0, 1)), exercised by the parity suite.
+    if (g_pair_mode < 0) {
+        const char* e = getenv("XSB_TC_PAIR");
+        g_pair_mode = e ? atoi(e) : 0;
+    }
+    if (g_pair_mode > 0 && !j.o_strided && BN >= 128 && m_tiles >= 2) {
+        const int SP = S / 2, pairs = (m_tiles + 1) / 2, n_tiles = j.OCx / BN;
+        const int64_t units = (int64_t)pairs * n_tiles;
+        int max_parts = j.OCx / 32;
+        if (max_parts > 16) max_parts = 16;
+        if (units < SP) {
+            int parts = SP / pairs;
+            if (parts > max_parts) parts = max_parts;
+            if (parts > n_tiles) return launch_parts2(0, m_tiles, parts);
+        } else if (n_tiles == 1 && units % SP != 0 && (units % SP) * 10 < (int64_t)SP * 7) {
+            const int main_tiles = (int)(units / SP) * SP * 2, tail = m_tiles - main_tiles;
+            int parts = SP / ((tail + 1) / 2);
+            if (parts > max_parts) parts = max_parts;
+            if (parts > 1 && tail > 0) {
+                const int rc = launch_parts2(0, main_tiles, 1);
+                if (rc != XSB_OK) return rc;
+                return launch_parts2(main_tiles, tail, parts);
+            }
+        }
+        return launch_parts2(0, m_tiles, n_tiles);
+    }
     static const int wave_aware = [] { const char* e = getenv("XSB_TC_WAVES"); return (e && e[0] == '0') ? 0 : 1; }();
     if (BN == 256 && wave_aware) {
         // One CTA per SM: tile counts that are not a multiple of the SM count leave SMs idle (98 tiles on 148 SMs =
@@ -1048,6 +1231,15 @@ int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
 }
 
 extern "C" {
+// kernel-selection switches (tests / A-B measurements): key 0 = CTA-pair (cta_group::2) forward kernels on/off
+int xsb_tc_config(int key, int value) {
+    if (key == 0) {
+        tc::g_pair_mode = value ? 1 : 0;
+        return XSB_OK;
+    }
+    xsb_set_error("xsb_tc_config: unknown key %d", key);
+    return XSB_ERR_ARG;
+}
 // counters: [0] GEMM-shaped calls served by tensor-core kernels, [1] GEMM-shaped calls that ran the fp32 FFMA kernel in TF32 mode
 int xsb_tc_stats(uint64_t* out2) {
     out2[0] = tc::g_tc_launches;

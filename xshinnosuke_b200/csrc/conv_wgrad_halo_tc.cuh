@@ -193,6 +193,9 @@ static int wgrad_halo(const float* dy, const float* x, float* dw, const ConvGeom
     int cbp = 512 / (g.KW * BN);               // accumulators of one pass: cbp * KW * BN <= 512 TMEM columns
     if (cbp < 1) return XSB_ERR_UNSUPPORTED;
     if (cbp > cblocks) cbp = cblocks;
+    // measured (R224): with one pass (all channel blocks' accumulators resident, C = OC = 64) this beats the im2col
+    // kernel (102 vs 108 us); with several passes every pass re-reads dY and it loses (84-95 vs 69 us): single pass only
+    if (cbp < cblocks) return XSB_ERR_UNSUPPORTED;
     const int cb_groups = (cblocks + cbp - 1) / cbp;
     const int n_oc_tiles = g.OC / BN;
     const int passes = cb_groups * n_oc_tiles;

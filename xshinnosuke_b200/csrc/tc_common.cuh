@@ -87,6 +87,69 @@ __device__ __forceinline__ void tma_load_im2col(void* dst, const CUtensorMap* ma
         : "memory");
 }
 
+// ---- CTA pair (cta_group::2): both CTAs load, the even ("leader") CTA issues M = 256 MMAs that read A (own 128 rows)
+// and HALF of B from each CTA's shared memory -- per SM that halves the B operand reads and the B fill traffic, the two
+// things that saturate the 128 B/clk shared-memory port of a 1-CTA tf32 kernel.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// loads whose complete_tx goes to the LEADER's mbarrier (same smem offset, peer bit cleared)
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                 int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+        "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// D=f32, A=B=tf32, K-major, M = 256 (two CTAs x 128 rows), N = n
+__host__ __device__ constexpr uint32_t make_idesc2(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
 // ---- TMA stores (shared -> global), bulk-group completion
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -241,6 +304,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// zero 32 columns of this warp's 32 TMEM lanes (accumulators are always accumulated INTO: see kThreads2)
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
@@ -269,6 +343,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
 }
 
 constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+// Dual-issuer kernels: warp 6 is a SECOND MMA issuer. A thread that issues tcgen05.mma cannot run ahead of a
+// result-returning instruction (mbarrier try_wait, ld): measured ~160 clk of idle tensor pipe per barrier wait for a
+// single issuer (tools/mma_rate2.cu), i.e. 30-45 % at N = 64..128 with 4-12 MMAs per pipeline stage. Two issuers on
+// different SM sub-partitions take alternate stages, so one's wait hides under the other's MMAs (measured: pipe-bound).
+// Their MMAs into one accumulator commute only if none of them overwrites: accumulators are zeroed by the epilogue
+// warps (tcgen05.st) and every MMA accumulates.
+constexpr int kThreads2 = 224;
 constexpr int BM = 128;
 constexpr int A_ROW_BYTES = 128;  // 32 fp32 = one SWIZZLE_128B row
 
