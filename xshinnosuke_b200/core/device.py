@@ -111,13 +111,17 @@ class DevArray:
     1 ("+=") afterwards -- which is how `zero_grad` costs no memset and no read-modify-write
     (the reference allocates and fills zeros: xs/utils/common.py:29-32, xs/core/base.py:312-316).
     """
-    __slots__ = ("buf", "shape", "dtype", "cl", "_pz", "_root")
+    __slots__ = ("buf", "shape", "dtype", "cl", "_pz", "_root", "lazy_mask")
 
     def __init__(self, buf, shape, dtype="float32", cl=None, pending_zero=False, _share=None):
         self.buf = buf
         self.shape = tuple(int(s) for s in shape)
         self.dtype = dtype
         self.cl = (len(self.shape) == 4 and dtype == "float32") if cl is None else cl
+        # lazy_mask: `buf` ALIASES another gradient and the logical contents are buf with the elements whose bit is set
+        # in this ReLU bit mask zeroed (AddBackward hands dZ to a BatchNorm branch this way; the BN backward kernels apply
+        # the mask on the fly, anyone else materialises a masked copy first)
+        self.lazy_mask = None
         if _share is None:
             # one cell shared by an array and all its views: [pending_zero, pending_op]
             self._pz = [bool(pending_zero), None]
@@ -207,9 +211,18 @@ class DevArray:
     def ndim(self):
         return len(self.shape)
 
+    def _materialize_mask(self):
+        mask, src = self.lazy_mask, self.buf
+        self.lazy_mask = None
+        self.buf = rt.empty(max(self.size, 1))
+        lib.xsb_relu_bwd_mask(src.data_ptr(), mask.data_ptr(), self.buf.data_ptr(), self.size, 0, rt.stream())
+        rt.launches += 1
+
     @property
     def ptr(self):
         """Pointer for a kernel that will READ (or read-modify-write) the contents."""
+        if self.lazy_mask is not None:
+            self._materialize_mask()
         if self._pz[1] is not None:
             self.flush()
         if self.pending_zero:
@@ -219,6 +232,9 @@ class DevArray:
     @property
     def wptr(self):
         """Pointer for a kernel that fully OVERWRITES the contents."""
+        if self.lazy_mask is not None:       # never write through an alias
+            self.lazy_mask = None
+            self.buf = rt.empty(max(self.size, 1))
         self._pz[1] = None
         self.pending_zero = False
         return self.buf.data_ptr()
@@ -231,6 +247,8 @@ class DevArray:
         return 1
 
     def peek_ptr(self):
+        if self.lazy_mask is not None:
+            self._materialize_mask()
         if self._pz[1] is not None:
             self.flush()
         return self.buf.data_ptr()
@@ -245,6 +263,8 @@ class DevArray:
     # ---- host transfer
     def to_numpy(self):
         rt.ensure()
+        if self.lazy_mask is not None:
+            self._materialize_mask()
         self.flush()
         if self.pending_zero:
             return np.zeros(self.shape, dtype=np.float32 if self.dtype == "float32" else np.int64)
@@ -280,6 +300,8 @@ class DevArray:
         return DevArray(self.buf[: max(n * per, 1)], (n,) + self.shape[1:], self.dtype, self.cl, _share=self)
 
     def clone(self):
+        if self.lazy_mask is not None:
+            self._materialize_mask()
         self.flush()
         if self.pending_zero:
             return DevArray.empty(self.shape, self.dtype, pending_zero=True)

@@ -332,6 +332,51 @@ bn_apply_k(const float* __restrict__ x, float* __restrict__ y, const float* __re
     }
 }
 
+// persistent forward apply (C = 4 * 2^k <= 1024): the thread's four channels are fixed, their scale / shift live in
+// registers -- y = x * a + b with a = gamma * invstd, b = beta - mean * a (one FMA per element), optional ReLU + bit mask
+template <bool kRelu>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_persist_k(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
+                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   int64_t nvec, int CV, uint8_t* __restrict__ mask) {
+    constexpr int U = 4;
+    const int tid = threadIdx.x;
+    const int c = (tid & (CV - 1)) * 4;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const int64_t stride = (int64_t)gridDim.x * (kThreads * U);
+    // block-uniform trip count: the mask nibbles are paired with a full-warp shuffle
+    for (int64_t bbase = (int64_t)blockIdx.x * (kThreads * U); bbase < nvec; bbase += stride) {
+        const int64_t base = bbase + tid;
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads;
+            if (i < nvec) v[u] = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nvec) {   // same operation order as bn_apply_k: ((x - mean) * invstd) * gamma + beta
+                o.x = fmaf((v[u].x - mu.x) * is.x, ga.x, be.x);
+                o.y = fmaf((v[u].y - mu.y) * is.y, ga.y, be.y);
+                o.z = fmaf((v[u].z - mu.z) * is.z, ga.z, be.z);
+                o.w = fmaf((v[u].w - mu.w) * is.w, ga.w, be.w);
+            }
+            if (kRelu) {
+                unsigned nib = (o.x < 0.f ? 1u : 0u) | (o.y < 0.f ? 2u : 0u) | (o.z < 0.f ? 4u : 0u) | (o.w < 0.f ? 8u : 0u);
+                const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
+                if ((tid & 1) == 0 && i < nvec) mask[i >> 1] = (uint8_t)(nib | (hi << 4));
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (i < nvec) stg_stream(reinterpret_cast<float4*>(y) + i, o);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ backward sums (and plain column sums)
 // kXhat: also accumulate sum(dy * xhat). ws: [counters][nb][C] s_dy | [nb][C] s_dyxhat
 // finalize writes dgamma/dbeta (+)= and coef[0..C)=sum_dy/M, coef[C..2C)=sum_dyxhat/M, coef[2C..3C)=gamma*invstd
@@ -730,10 +775,10 @@ __global__ void bn_finalize_k(const float* __restrict__ part, int P, int C, floa
     const int c = blockIdx.x * 32 + tx;
     float an = 0.f, amean = 0.f, am2 = 0.f;
     if (c < C) {
-        for (int p0 = ty; p0 < P; p0 += TY * 4) {
-            float pn[4], pm[4], p2[4];
+        for (int p0 = ty; p0 < P; p0 += TY * 8) {
+            float pn[8], pm[8], p2[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int p = p0 + u * TY;
                 pn[u] = 0.f; pm[u] = 0.f; p2[u] = 0.f;
                 if (p < P) {
@@ -742,7 +787,7 @@ __global__ void bn_finalize_k(const float* __restrict__ part, int P, int C, floa
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const Moments m = merge(Moments{an, amean, am2}, Moments{pn[u], pm[u], p2[u]});
                 an = m.n; amean = m.mean; am2 = m.m2;
             }
@@ -790,8 +835,21 @@ static int launch_bn_apply(const float* x, float* y, const float* mean, const fl
     const int64_t nvec = R * CV;
     const int cv_mask = (CV & (CV - 1)) == 0 ? CV - 1 : -1;
     const unsigned blocks = (unsigned)ceil_div64(nvec, (int64_t)kThreads * 4);
+    if (relu) XSB_CHECK_ARG(v4 && nvec % 2 == 0 && relu_mask, "bn_apply: fused ReLU needs C %% 4 == 0, an even vector count and a mask");
+    if (v4 && CV <= kThreads && (CV & (CV - 1)) == 0 && aligned16(mean) && aligned16(invstd) && aligned16(gamma) &&
+        aligned16(beta)) {
+        int64_t pb = ceil_div64(nvec, (int64_t)kThreads * 4 * 2);
+        const int64_t cap = (int64_t)xsb_sm_count_cached() * 8;
+        if (pb > cap) pb = cap;
+        if (pb < 1) pb = 1;
+        if (relu)
+            bn_apply_persist_k<true><<<(unsigned)pb, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, relu_mask);
+        else
+            bn_apply_persist_k<false><<<(unsigned)pb, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, nullptr);
+        XSB_LAUNCH_CHECK();
+        return XSB_OK;
+    }
     if (relu) {
-        XSB_CHECK_ARG(v4 && nvec % 2 == 0 && relu_mask, "bn_apply: fused ReLU needs C %% 4 == 0, an even vector count and a mask");
         bn_apply_k<4, true><<<blocks, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, cv_mask, relu_mask);
     } else if (v4) {
         bn_apply_k<4, false><<<blocks, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, cv_mask, nullptr);
@@ -853,7 +911,7 @@ int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const
 int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* running_mean, float* running_var,
                     float* save_mean, float* save_invstd, float eps, float momentum, void* stream) {
     XSB_CHECK_ARG(P > 0 && R > 0 && C > 0, "bn_finalize: empty input");
-    const int TY = P > 256 ? 32 : 8;
+    const int TY = P > 32 ? 32 : 8;
     bn_finalize_k<<<(C + 31) / 32, dim3(32, TY), 0, xsb_stream(stream)>>>(partials, P, C, (float)R, save_mean, save_invstd,
                                                                           running_mean, running_var, eps, momentum);
     XSB_LAUNCH_CHECK();

@@ -69,6 +69,15 @@ def AddBackward(outputs: Tensor, relu_mask=None):
         if all(_grad_arr(t).cl == dy.cl for t in targets):
             for t in targets:
                 g = _grad_arr(t)
+                if (t.grad_fn is BatchNormBackward and t.is_dynamic and len(t.out_bounds) == 1 and g.pending_zero
+                        and not t.cache.get("inplace") and dy.lazy_mask is None and tuple(g.shape) == tuple(dy.shape)):
+                    # the branch ends in a BatchNorm whose only consumer is this add: hand it dZ itself plus the
+                    # mask -- its backward kernels mask on the fly, no masked copy is written and read back
+                    alias = DevArray(dy.buf, g.shape, g.dtype, cl=g.cl)
+                    dy.ptr  # noqa: B018 -- dZ itself must be materialised before it is aliased
+                    alias.lazy_mask = relu_mask
+                    t.grad._arr = alias
+                    continue
                 lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), g.peek_ptr(), g.size, g.take_acc(), rt.stream())
                 rt.launches += 1
             return
@@ -244,8 +253,14 @@ def BatchNormBackward(outputs: Tensor, relu_mask=None):
     inputs, gamma, beta = outputs.in_bounds
     dy = outputs.grad.arr
     x = inputs.arr
+    if dy.lazy_mask is not None and relu_mask is None and (x.ndim != 4 or (x.cl and dy.cl)):
+        relu_mask, dy_ptr = dy.lazy_mask, dy.buf.data_ptr()     # masked alias of the add's dZ (see AddBackward)
+    else:
+        dy_ptr = None
     if x.ndim == 4:
         x, dy = x.as_cl(), dy.as_cl()
+    if dy_ptr is None:
+        dy_ptr = dy.ptr
     C = gamma.arr.size
     R = x.size // C
     gx = _grad_arr(inputs) if inputs.requires_grad else None
@@ -262,7 +277,7 @@ def BatchNormBackward(outputs: Tensor, relu_mask=None):
     if cb is not None:
         was_zero = cb.pending_zero
         done = ctypes.c_int(0)
-        lib.xsb_bn_bwd_dxsum(dy.ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
+        lib.xsb_bn_bwd_dxsum(dy_ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
                              gx.peek_ptr(), gg.peek_ptr() if gg is not None else None,
                              gb.peek_ptr() if gb is not None else None, R, C, gx.take_acc(),
                              gg.take_acc() if gg is not None else 0, gb.take_acc() if gb is not None else 0,
@@ -276,7 +291,7 @@ def BatchNormBackward(outputs: Tensor, relu_mask=None):
         _done(gamma)
         _done(beta)
         return
-    lib.xsb_bn_bwd(dy.ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
+    lib.xsb_bn_bwd(dy_ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
                    gx.peek_ptr() if gx is not None else None, gg.peek_ptr() if gg is not None else None,
                    gb.peek_ptr() if gb is not None else None, R, C,
                    gx.take_acc() if gx is not None else 0, gg.take_acc() if gg is not None else 0,
