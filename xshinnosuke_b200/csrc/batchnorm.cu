@@ -24,7 +24,9 @@ constexpr int kMaxRowBlocks = 4 * 148;   // total CTAs (row blocks x column chun
 constexpr int kMaxLX = 32;
 constexpr int kRowsPerThread = 32;
 constexpr int kMergeBatch = 8;           // partials fetched per round trip in the last-block merge
-constexpr int kCounterSlots = 64;  // ws[0..63]: one "blocks done" ticket counter per column chunk
+constexpr int kCounterSlots = 64;  // ws[0..63]: one "blocks done" ticket counter per column chunk (slot 63: BN-backward ticket)
+constexpr int kSumsFloats = 2048;  // ws[64..64+2048): sum(dy) | sum(dy*xhat) of the persistent BN backward (self-cleaning)
+constexpr int kScratchBase = kCounterSlots + kSumsFloats;   // per-block partials of the generic kernels start here
 
 struct Geom {
     int V;        // channels per thread (4 or 1)
@@ -125,7 +127,7 @@ bn_stats_k(const float* __restrict__ x, int64_t R, int C, int LX, int LY, int ro
     const bool active = (ty < LY) && (cv < CV);
     const int nb = gridDim.x;
     unsigned* counters = reinterpret_cast<unsigned*>(ws);
-    float* p_mean = ws + kCounterSlots;
+    float* p_mean = ws + kScratchBase;
     float* p_m2 = p_mean + (int64_t)nb * C;
 
     float K[V], s1[V], s2[V];
@@ -396,7 +398,7 @@ col_sums_k(const float* __restrict__ dy, const float* __restrict__ x, const floa
     const bool active = (ty < LY) && (cv < CV);
     const int nb = gridDim.x;
     unsigned* counters = reinterpret_cast<unsigned*>(ws);
-    float* p_a = ws + kCounterSlots;
+    float* p_a = ws + kScratchBase;
     float* p_b = p_a + (int64_t)nb * C;
 
     float sa[V], sb[V], mu[V], is[V];
@@ -604,12 +606,15 @@ constexpr int kPersistBlocksPerSM = 4;
 template <bool kXhat>
 __global__ void __launch_bounds__(kThreads)
 col_sums_atomic_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                  const float* __restrict__ invstd, int64_t nvec, int CV, float* sums, const uint8_t* __restrict__ rmask) {
+                  const float* __restrict__ invstd, int64_t nvec, int CV, float* sums, const uint8_t* __restrict__ rmask,
+                  float* zero_me) {
     __shared__ float4 s_a[kThreads], s_b[kThreads];
     constexpr int U = kXhat ? 4 : 8;
     const int tid = threadIdx.x;
     const int c = (tid & (CV - 1)) * 4;     // CV divides kThreads: the channel group depends on the thread only
     const int C = CV * 4;
+    if (zero_me && blockIdx.x == 0)         // the apply kernel that follows accumulates the bias gradient into it ("=")
+        for (int ch = tid; ch < C; ch += kThreads) zero_me[ch] = 0.f;
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu;
     if (kXhat) {
         mu = __ldg(reinterpret_cast<const float4*>(mean + c));
@@ -689,8 +694,9 @@ __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x, float* dx, const float* __restrict__ mean,
                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ sums,
                        float invM, int64_t nvec, int CV, const uint8_t* __restrict__ rmask, float* dgamma, float* dbeta,
-                       int acc_gamma, int acc_beta, float* dxsum) {
+                       int acc_gamma, int acc_beta, float* dxsum, float* sums_rw, unsigned* ticket) {
     __shared__ float4 s_a[kThreads];
+    __shared__ unsigned s_last;
     constexpr int U = 4;
     const int tid = threadIdx.x;
     const int c = (tid & (CV - 1)) * 4;
@@ -763,6 +769,15 @@ bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x
             atomicAdd(dxsum + c, a.x); atomicAdd(dxsum + c + 1, a.y); atomicAdd(dxsum + c + 2, a.z); atomicAdd(dxsum + c + 3, a.w);
         }
     }
+    // every block read `sums` before its loop; the LAST block to get here zeroes them for the next BatchNorm backward
+    // (self-cleaning scratch: no memset node per call)
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        for (int ch = tid; ch < 2 * C; ch += kThreads) sums_rw[ch] = 0.f;
+        if (tid == 0) *ticket = 0u;
+    }
 }
 
 // ------------------------------------------------------------------ statistics from conv-epilogue partials
@@ -825,7 +840,7 @@ extern "C" {
 // zero-initialised once (the ticket counters at its head are self-cleaning afterwards).
 int64_t xsb_bn_workspace_floats(int64_t R, int C) {
     (void)R;
-    return kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks + 3 * (int64_t)C;
+    return kScratchBase + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks + 3 * (int64_t)C;
 }
 
 static int launch_bn_apply(const float* x, float* y, const float* mean, const float* invstd, const float* gamma,
@@ -867,7 +882,7 @@ int xsb_bn_stats(const float* x, float* running_mean, float* running_var, float*
     cudaStream_t s = xsb_stream(stream);
     const bool v4 = use_vec4(C, x);
     const Geom g = make_geom(R, C, v4);
-    XSB_CHECK_ARG(g.chunks <= kCounterSlots, "bn: C=%d too large", C);
+    XSB_CHECK_ARG(g.chunks < kCounterSlots, "bn: C=%d too large", C);
     dim3 grid(g.nb, g.chunks);
     if (v4)
         bn_stats_k<4><<<grid, kThreads, 0, s>>>(x, R, C, g.LX, g.LY, g.rows_per_block, ws, save_mean, save_invstd,
@@ -901,7 +916,7 @@ int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const
                     const float* moving_var, float* y, int64_t R, int C, float eps, float* ws, void* stream) {
     XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
     cudaStream_t s = xsb_stream(stream);
-    float* invstd = ws + kCounterSlots;   // partial-sum area of the scratch buffer; free between launches
+    float* invstd = ws + kScratchBase;   // partial-sum area of the scratch buffer; free between launches
     invstd_k<<<(C + 255) / 256, 256, 0, s>>>(moving_var, invstd, C, eps);
     XSB_LAUNCH_CHECK();
     return launch_bn_apply(x, y, moving_mean, invstd, gamma, beta, R, C, nullptr, false, s);
@@ -951,33 +966,35 @@ static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, cons
     const int CV4 = C / 4;
     if (v4 && dx && C % 4 == 0 && CV4 <= kThreads && (CV4 & (CV4 - 1)) == 0 && aligned16(save_mean) &&
         aligned16(save_invstd) && aligned16(gamma)) {
-        float* sums = ws + kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks;   // the coef area: 3C floats
-        XSB_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), s));
-        if (dxsum && !acc_dxsum) XSB_CUDA(cudaMemsetAsync(dxsum, 0, (size_t)C * sizeof(float), s));
+        // scratch: sums[2C] at a FIXED offset (independent of C) so that the zeros one call leaves are the zeros the
+        // next call finds; the buffer is zero-initialised once by the caller, afterwards the apply kernel cleans up
+        float* sums = ws + kCounterSlots;
+        unsigned* ticket = reinterpret_cast<unsigned*>(ws) + (kCounterSlots - 1);
         const int64_t nvec = R * CV4;
         // >= 4 grid-stride iterations per thread: a block ends with 2C (+C) atomics, keep them few on small tensors
         int64_t blocks = ceil_div64(nvec, (int64_t)kThreads * 4 * 4);
         const int64_t cap = (int64_t)xsb_sm_count_cached() * kPersistBlocksPerSM;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        col_sums_atomic_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, nvec, CV4, sums, relu_mask);
+        col_sums_atomic_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, nvec, CV4, sums, relu_mask,
+                                                                      (dxsum && !acc_dxsum) ? dxsum : nullptr);
         XSB_LAUNCH_CHECK();
         const float invM = 1.0f / (float)R;
         if (acc_dx)
             bn_bwd_apply_persist_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
                                                                               nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
-                                                                              acc_dbeta, dxsum);
+                                                                              acc_dbeta, dxsum, sums, ticket);
         else
             bn_bwd_apply_persist_k<false><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
                                                                                nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
-                                                                               acc_dbeta, dxsum);
+                                                                               acc_dbeta, dxsum, sums, ticket);
         XSB_LAUNCH_CHECK();
         if (dxsum && dxsum_done) *dxsum_done = 1;
         return XSB_OK;
     }
     const Geom g = make_geom(R, C, v4, 2 * 148);   // two streamed arrays per thread: fewer, fatter CTAs measured faster
-    XSB_CHECK_ARG(g.chunks <= kCounterSlots, "bn: C=%d too large", C);
-    float* coef = ws + kCounterSlots + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks;
+    XSB_CHECK_ARG(g.chunks < kCounterSlots, "bn: C=%d too large", C);
+    float* coef = ws + kScratchBase + (int64_t)kMaxRowBlocks * C * 3 + kMaxRowBlocks;
     dim3 grid(g.nb, g.chunks);
     if (v4)
         col_sums_k<4, true><<<grid, kThreads, 0, s>>>(dy, x, save_mean, save_invstd, gamma, R, C, g.LX, g.LY,
@@ -1014,7 +1031,7 @@ int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, flo
     cudaStream_t s = xsb_stream(stream);
     const bool v4 = use_vec4(C, x);
     const Geom g = make_geom(R, C, v4);
-    XSB_CHECK_ARG(g.chunks <= kCounterSlots, "colsum: C=%d too large", C);
+    XSB_CHECK_ARG(g.chunks < kCounterSlots, "colsum: C=%d too large", C);
     dim3 grid(g.nb, g.chunks);
     if (v4)
         col_sums_k<4, false><<<grid, kThreads, 0, s>>>(x, nullptr, nullptr, nullptr, nullptr, R, C, g.LX, g.LY,
