@@ -70,6 +70,13 @@ int xsb_broadcast_axis(const float* dy, float* dx, int64_t outer, int64_t red, i
  *      argmax = ky*k+kx in (n,oh,ow,c) order) and xs/nn/grad_fn.py:206-235. ---- */
 int xsb_maxpool2d_fwd(const float* x, float* y, uint8_t* argmax /* nullable */, int N, int H, int W, int C, int k,
                       int sh, int sw, int pad, void* stream);
+/* BatchNormalization -> ReLU(inplace) -> MaxPooling2D fused forward: y = maxpool(max(0, bn(x))) with argmax and the
+ * ReLU bit mask, without writing the intermediate tensor (xs/nn/functional.py:726-737 + activators.py:37-50 + 445-491).
+ * Returns XSB_ERR_UNSUPPORTED, launching nothing, when the geometry / channel count is outside the kernel's envelope. */
+int xsb_bn_relu_maxpool_fwd(const float* x, const float* mean, const float* invstd, const float* gamma,
+                            const float* beta, float* y, uint8_t* argmax /* nullable */,
+                            uint8_t* relu_mask /* nullable */, int N, int H, int W, int C, int k, int sh, int sw, int pad,
+                            void* stream);
 int xsb_maxpool2d_bwd(const float* dy, const uint8_t* argmax, float* dx, int N, int H, int W, int C, int k, int sh,
                       int sw, int pad, int accumulate, void* stream);
 

@@ -175,6 +175,17 @@ class FakeLib:
             o = np.maximum(o, 0)
         f32(y, R * C).reshape(R, C)[...] = o
 
+    def _bn_relu_maxpool_fwd(self, x, mean, invstd, gamma, beta, y, amax, rmask, N, H, W, C, k, sh, sw, pad, s):
+        # contract: maxpool(max(0, bn(x))) with argmax + the ReLU bit mask, the intermediate is never stored
+        R = N * H * W
+        z = torch.empty(R * C, dtype=torch.float32)
+        m = torch.empty((R * C + 7) // 8, dtype=torch.uint8)
+        self._bn_apply(x, z.data_ptr(), mean, invstd, gamma, beta, R, C, 1, m.data_ptr(), s)
+        if rmask:
+            u8(rmask, (R * C + 7) // 8)[...] = m.numpy()
+        self._maxpool2d_fwd(z.data_ptr(), y, amax, N, H, W, C, k, sh, sw, pad, s)
+        return 0
+
     def _add_relu(self, a, b, y, mask, n, s):
         t = f32(a, n) + f32(b, n)
         u8(mask, (n + 7) // 8)[...] = np.packbits(t < 0, bitorder="little")

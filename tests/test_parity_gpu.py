@@ -318,6 +318,52 @@ def test_conv_cta_pair_kernels_tf32(n, c, h, oc, k, s, p):
         xs.set_math_mode("fp32")
 
 
+@pytest.mark.parametrize("n,c,h,k,s,p", [(4, 64, 20, 3, 2, 1), (3, 8, 17, 3, 2, 1), (2, 16, 12, 2, 2, 0), (2, 64, 9, 3, 1, 1)])
+def test_bn_relu_maxpool_fused_equals_unfused(n, c, h, k, s, p):
+    """BatchNormalization -> ReLU(inplace) -> MaxPooling2D: the fused kernel (pool straight from the BN input, the
+    rectified tensor never materialised) must give bit-identical pooled values, arg-max, ReLU mask effect and input
+    gradient as the three separate kernels; the unfused chain itself is pinned to the oracle by the other tests."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.layers import BatchNormalization, MaxPooling2D, ReLU
+    rs = np.random.RandomState(n + c + h)
+    x = rs.randn(n, c, h, h).astype(np.float32)
+    g = None
+    res = []
+    for fuse in (True, False):
+        xs.runtime.fuse_bn_relu_pool = fuse     # opt-in fusion (off by default: measured no faster)
+        np.random.seed(0)
+        bn, relu, pool = BatchNormalization(), ReLU(True), MaxPooling2D(k, s, p)
+        calls = []
+        orig = lib.xsb_bn_relu_maxpool_fwd
+        lib.xsb_bn_relu_maxpool_fwd = lambda *a: (calls.append(1), orig(*a))[1]
+        try:
+            tx = xs.tensor(x, requires_grad=True)
+            z = relu(bn(tx))
+            y = pool(z)
+            yv = y.eval
+            am = np.asarray(y.cache["pool_argmax"])
+            if g is None:
+                g = rs.randn(*yv.shape).astype(np.float32)
+            y.backward(gradients=g)
+            res.append((yv, am, tx.grad.eval, bn.parameters()[0].grad.eval, len(calls)))
+        finally:
+            lib.xsb_bn_relu_maxpool_fwd = orig
+            xs.runtime.fuse_bn_relu_pool = False
+    (y1, a1, dx1, dg1, c1), (y0, a0, dx0, dg0, c0) = res
+    assert c1 == 1 and c0 == 0
+    assert np.array_equal(y1, y0) and np.array_equal(a1, a0)
+    # (the BatchNorm backward sums use atomics: summation order, hence the last bits, vary from run to run)
+    assert X.rel_err(dx1, dx0) <= 1e-6 and X.rel_err(dg1, dg0) <= 1e-6
+    # and against the oracle (fp32 path, 1e-5; arg-max exact)
+    xh = x.astype(np.float64)
+    zr, xhat, sv, _, _ = X.batch_norm_fwd(xh, np.ones(c), np.zeros(c), np.zeros(c), np.ones(c), 1, 1e-6, 0.99)
+    pr, amr = X.max_pool2d_fwd(X.relu_fwd(zr), k, (s, s), p)
+    assert X.rel_err(y1, pr) <= 1e-5
+
+
 def test_resnet18_tf32_mode(golden):
     """Whole ResNet-18 step in tf32 mode: logits of the first forward within 2e-3 of the reference."""
     import xshinnosuke_b200 as xs

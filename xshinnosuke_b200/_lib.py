@@ -12,6 +12,9 @@ ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(ROOT, "include", "xsb200.h")
 LIB_PATH = os.path.join(_HERE, "libxsb200.so")
 
+# fused entry points that answer XSB_ERR_UNSUPPORTED (3) for shapes outside their envelope instead of failing
+_MAY_DECLINE = {"xsb_bn_relu_maxpool_fwd"}
+
 MATH_FP32 = 0
 MATH_TF32 = 1
 
@@ -80,6 +83,8 @@ class _Lib:
         if self.protos[name][0] is ctypes.c_int and name not in ("xsb_version", "xsb_device_sm_count"):
             def checked(*args, _fn=fn, _name=name):
                 rc = _fn(*args)
+                if rc == 3 and _name in _MAY_DECLINE:
+                    return rc           # XSB_ERR_UNSUPPORTED, nothing launched: the caller runs the unfused kernels
                 if rc != 0:
                     raise RuntimeError(f"{_name} failed (code {rc}): {dll.xsb_last_error().decode()}")
                 return rc

@@ -39,6 +39,9 @@ class Runtime:
         self._ws_big = None
         self._ws_stats = None
         self.launches = 0          # kernel-launching C-ABI calls issued (bench.py reports it)
+        # BatchNorm -> ReLU -> MaxPool as one kernel (xsb_bn_relu_maxpool_fwd). Measured on the R224 stem: 288 us against
+        # 124 + 131 us for the two bandwidth kernels it replaces (the tiled kernel is latency-bound) -> off by default
+        self.fuse_bn_relu_pool = False
 
     def ensure(self):
         if self.ready:

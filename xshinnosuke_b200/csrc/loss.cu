@@ -23,10 +23,10 @@ __device__ double block_sum_d(double v, double* smem) {
 }
 
 // one warp per row (looping); probs[N,C] written; loss[0] = | -sum_i log p[i, y_i] / denom |
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(1024)
 softmax_xent_fwd_k(const float* __restrict__ z, const int64_t* __restrict__ labels, float* __restrict__ probs,
                    float* __restrict__ loss, int N, int C, float inv_denom) {
-    __shared__ double s_part[kThreads / 32];
+    __shared__ double s_part[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double acc = 0.0;
     for (int row = wid; row < N; row += nw) {
@@ -90,7 +90,9 @@ int xsb_softmax_xent_fwd(const float* logits, const int64_t* labels, float* prob
                          int reduction, void* stream) {
     XSB_CHECK_ARG(N > 0 && C > 0, "xent: empty input");
     const float inv = reduction == 0 ? 1.0f / (float)N : 1.0f;
-    softmax_xent_fwd_k<<<1, kThreads, 0, xsb_stream(stream)>>>(logits, labels, probs, loss, N, C, inv);
+    // one CTA (deterministic row order in the final sum), one warp per row: 32 warps for the usual N >= 32
+    const int threads = N >= 32 ? 1024 : N >= 16 ? 512 : kThreads;
+    softmax_xent_fwd_k<<<1, threads, 0, xsb_stream(stream)>>>(logits, labels, probs, loss, N, C, inv);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

@@ -201,28 +201,143 @@ maxpool_bwd_s2_k(const float* __restrict__ dy, const uint8_t* __restrict__ amax,
     }
 }
 
-// avg pool (padding == 0 only: the reference's padded variant is broken)
-__global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int OH,
-                              int OW, int k, int sh, int sw) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (unsigned)OW * C) return;
-    const int c = (int)(t % (unsigned)C);
-    const int ow = (int)(t / (unsigned)C);
-    const int oh = blockIdx.y;
+// BatchNorm apply + ReLU (+ its bit mask) + max-pool with argmax in ONE pass over the conv output x: the normalised,
+// rectified tensor z = max(0, gamma*(x-mean)*invstd + beta) -- which only the pool would read -- is never written.
+// A block owns a TOH x TOW tile of outputs (all C <= 64 channels): phase 1 normalises the input tile + halo once into
+// shared memory (zero padding stays zero) and writes the mask bits of the pixels the tile owns; phase 2 pools from
+// shared memory. Same arithmetic, tap order and tie rule as bn_apply_k followed by maxpool_fwd_k.
+constexpr int FP_TOH = 4, FP_TOW = 8;
+
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool_fwd_k(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                      uint8_t* __restrict__ amax, uint8_t* __restrict__ rmask, int N, int H, int W, int C, int OH, int OW,
+                      int k, int sh, int sw, int pad) {
+    extern __shared__ float4 s_z[];                 // [rows][cols][CV]
+    const int CV = C / 4;
+    const int rows = (FP_TOH - 1) * sh + k, cols = (FP_TOW - 1) * sw + k;
+    const int oh0 = blockIdx.y * FP_TOH, ow0 = blockIdx.x * FP_TOW;
     const int n = blockIdx.z;
-    float acc = 0.f;
-    for (int ky = 0; ky < k; ++ky)
-        for (int kx = 0; kx < k; ++kx)
-            acc += __ldg(x + (((int64_t)n * H + oh * sh + ky) * W + ow * sw + kx) * C + c);
-    y[(((int64_t)n * OH + oh) * OW + ow) * C + c] = acc / (float)(k * k);
+    const int h_base = oh0 * sh - pad, w_base = ow0 * sw - pad;
+    const int tid = threadIdx.x;
+    const int total = rows * cols * CV;
+    // 256 % CV == 0 (checked by the launcher): the thread's channel group is fixed, pixel index advances by 256/CV
+    const int cv = tid % CV, ppi = 256 / CV;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + cv);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cv);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cv);
+    const int trips = (total + 255) / 256;          // block-uniform: the nibble pairing uses a full-warp shuffle
+    constexpr int UB = 4;                           // loads in flight per thread
+    for (int it0 = 0; it0 < trips; it0 += UB) {
+        float4 q[UB];
+        int hh[UB], ww[UB];
+        bool ins[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int pix = (it0 + u) * ppi + tid / CV;           // pixel of the tile (row-major rows x cols)
+            const int r = pix / cols, cidx = pix - r * cols;
+            hh[u] = h_base + r;
+            ww[u] = w_base + cidx;
+            ins[u] = (it0 + u) < trips && pix < rows * cols && hh[u] >= 0 && hh[u] < H && ww[u] >= 0 && ww[u] < W;
+            q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ins[u]) q[u] = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)n * H + hh[u]) * W + ww[u]) * C) + cv);
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            if (it0 + u >= trips) break;            // block-uniform
+            const int i = (it0 + u) * 256 + tid;
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned nib = 0;
+            if (ins[u]) {
+                z.x = fmaf((q[u].x - mu.x) * is.x, ga.x, be.x);
+                z.y = fmaf((q[u].y - mu.y) * is.y, ga.y, be.y);
+                z.z = fmaf((q[u].z - mu.z) * is.z, ga.z, be.z);
+                z.w = fmaf((q[u].w - mu.w) * is.w, ga.w, be.w);
+                nib = (z.x < 0.f ? 1u : 0u) | (z.y < 0.f ? 2u : 0u) | (z.z < 0.f ? 4u : 0u) | (z.w < 0.f ? 8u : 0u);
+                z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f);
+            }
+            if (i < total) s_z[i] = z;
+            if (rmask) {
+                const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
+                // the tile owns pixel (h, w) when window (h / sh, w / sw) is one of its outputs
+                const int oh = hh[u] / sh, ow = ww[u] / sw;
+                const bool own = ins[u] && oh >= oh0 && oh < oh0 + FP_TOH && ow >= ow0 && ow < ow0 + FP_TOW;
+                if (own && (cv & 1) == 0) {
+                    const int64_t e0 = ((((int64_t)n * H + hh[u]) * W + ww[u]) * C) + (int64_t)cv * 4;
+                    rmask[e0 >> 3] = (uint8_t)(nib | (hi << 4));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int outs = FP_TOH * FP_TOW * CV;
+    for (int o = tid; o < outs; o += 256) {
+        const int cv = o % CV;
+        const int t2 = o / CV;
+        const int tow = t2 % FP_TOW, toh = t2 / FP_TOW;
+        const int oh = oh0 + toh, ow = ow0 + tow;
+        if (oh >= OH || ow >= OW) continue;
+        float best[4] = {0.f, 0.f, 0.f, 0.f};
+        int arg[4] = {0, 0, 0, 0};
+        bool first = true;
+        for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx) {
+                const float4 q = s_z[((toh * sh + ky) * cols + tow * sw + kx) * CV + cv];
+                const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (first || v[i] > best[i]) { best[i] = v[i]; arg[i] = ky * k + kx; }
+                first = false;
+            }
+        const int64_t off = (((int64_t)n * OH + oh) * OW + ow) * C + (int64_t)cv * 4;
+        *reinterpret_cast<float4*>(y + off) = make_float4(best[0], best[1], best[2], best[3]);
+        if (amax)
+            *reinterpret_cast<uchar4*>(amax + off) =
+                make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
+    }
 }
 
+// avg pool (padding == 0 only: the reference's padded variant is broken). V channels per thread.
+template <int V>
+__global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int OH,
+                              int OW, int k, int sh, int sw) {
+    const unsigned CV = C / V;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)OW * CV) return;
+    const int c = (int)(t % CV) * V;
+    const int ow = (int)(t / CV);
+    const int oh = blockIdx.y;
+    const int n = blockIdx.z;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx) {
+            const float* p = x + (((int64_t)n * H + oh * sh + ky) * W + ow * sw + kx) * C + c;
+            if (V == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                acc[0] += q.x; acc[1 % V] += q.y; acc[2 % V] += q.z; acc[3 % V] += q.w;
+            } else {
+                acc[0] += __ldg(p);
+            }
+        }
+    const float inv = 1.0f / (float)(k * k);
+    float* o = y + (((int64_t)n * OH + oh) * OW + ow) * C + c;
+    if (V == 4)
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0] * inv, acc[1 % V] * inv, acc[2 % V] * inv, acc[3 % V] * inv);
+    else
+        o[0] = acc[0] * inv;
+}
+
+template <int V>
 __global__ void avgpool_bwd_k(const float* __restrict__ dy, float* dx, int N, int H, int W, int C, int OH, int OW,
                               int k, int sh, int sw, int acc_flag) {
+    const unsigned CV = C / V;
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (unsigned)W * C) return;
-    const int c = (int)(t % (unsigned)C);
-    const int w = (int)(t / (unsigned)C);
+    if (t >= (unsigned)W * CV) return;
+    const int c = (int)(t % CV) * V;
+    const int w = (int)(t / CV);
     const int h = blockIdx.y;
     const int n = blockIdx.z;
     int oh_lo = h - k + 1;
@@ -233,12 +348,32 @@ __global__ void avgpool_bwd_k(const float* __restrict__ dy, float* dx, int N, in
     ow_lo = ow_lo <= 0 ? 0 : (ow_lo + sw - 1) / sw;
     int ow_hi = w / sw;
     if (ow_hi > OW - 1) ow_hi = OW - 1;
-    float acc = 0.f;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
     for (int oh = oh_lo; oh <= oh_hi; ++oh)
-        for (int ow = ow_lo; ow <= ow_hi; ++ow) acc += __ldg(dy + (((int64_t)n * OH + oh) * OW + ow) * C + c);
-    acc /= (float)(k * k);
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+            const float* p = dy + (((int64_t)n * OH + oh) * OW + ow) * C + c;
+            if (V == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                acc[0] += q.x; acc[1 % V] += q.y; acc[2 % V] += q.z; acc[3 % V] += q.w;
+            } else {
+                acc[0] += __ldg(p);
+            }
+        }
+    const float inv = 1.0f / (float)(k * k);
     float* p = dx + (((int64_t)n * H + h) * W + w) * C + c;
-    *p = acc_flag ? *p + acc : acc;
+    if (V == 4) {
+        float4 r = make_float4(acc[0] * inv, acc[1 % V] * inv, acc[2 % V] * inv, acc[3 % V] * inv);
+        if (acc_flag) {
+            const float4 d = *reinterpret_cast<const float4*>(p);
+            r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+        }
+        *reinterpret_cast<float4*>(p) = r;
+    } else {
+        const float r = acc[0] * inv;
+        p[0] = acc_flag ? p[0] + r : r;
+    }
 }
 
 }  // namespace
@@ -262,6 +397,30 @@ int xsb_maxpool2d_fwd(const float* x, float* y, uint8_t* argmax, int N, int H, i
         dim3 grid((unsigned)ceil_div64((int64_t)OW * C, 256), OH, N);
         maxpool_fwd_k<1><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
     }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// Fused BatchNorm apply + ReLU + max-pool forward (see bn_relu_maxpool_fwd_k). Returns XSB_ERR_UNSUPPORTED (nothing
+// launched) when the geometry does not let every input pixel be owned by exactly one window or C % 8 != 0: the caller
+// then runs xsb_bn_apply (relu) and xsb_maxpool2d_fwd.
+int xsb_bn_relu_maxpool_fwd(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                            float* y, uint8_t* argmax, uint8_t* relu_mask, int N, int H, int W, int C, int k, int sh,
+                            int sw, int pad, void* stream) {
+    XSB_CHECK_ARG(k >= 1 && k <= 15 && sh >= 1 && sw >= 1 && pad >= 0, "maxpool: bad k/stride/pad %d %d %d %d", k, sh,
+                  sw, pad);
+    const int OH = (H + 2 * pad - k) / sh + 1, OW = (W + 2 * pad - k) / sw + 1;
+    XSB_CHECK_ARG(OH > 0 && OW > 0, "maxpool: empty output");
+    const bool covered = pad + sh - 1 < k && pad + sw - 1 < k && (H + sh - 1) / sh <= OH && (W + sw - 1) / sw <= OW;
+    if (!covered || C % 8 != 0 || !aligned16(x) || !aligned16(y) || !aligned16(mean) || !aligned16(invstd) ||
+        !aligned16(gamma) || !aligned16(beta) || (argmax && ((uintptr_t)argmax & 3u) != 0) || N > 65535 || OH > 65535)
+        return XSB_ERR_UNSUPPORTED;
+    const int rows = (FP_TOH - 1) * sh + k, cols = (FP_TOW - 1) * sw + k;
+    const size_t smem = (size_t)rows * cols * C * sizeof(float);
+    if (smem > 48 * 1024 || (OH + FP_TOH - 1) / FP_TOH > 65535 || 256 % (C / 4) != 0) return XSB_ERR_UNSUPPORTED;
+    dim3 grid((OW + FP_TOW - 1) / FP_TOW, (OH + FP_TOH - 1) / FP_TOH, N);
+    bn_relu_maxpool_fwd_k<<<grid, 256, smem, xsb_stream(stream)>>>(x, mean, invstd, gamma, beta, y, argmax, relu_mask, N, H, W,
+                                                                   C, OH, OW, k, sh, sw, pad);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }
@@ -300,8 +459,13 @@ int xsb_avgpool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int 
     const int OH = (H - k) / sh + 1, OW = (W - k) / sw + 1;
     XSB_CHECK_ARG(OH > 0 && OW > 0, "avgpool: empty output");
     XSB_CHECK_ARG(N <= 65535 && OH <= 65535, "avgpool: N/OH exceed grid limits");
-    dim3 grid((unsigned)ceil_div64((int64_t)OW * C, 256), OH, N);
-    avgpool_fwd_k<<<grid, 256, 0, xsb_stream(stream)>>>(x, y, N, H, W, C, OH, OW, k, sh, sw);
+    if (C % 4 == 0 && aligned16(x) && aligned16(y)) {
+        dim3 grid((unsigned)ceil_div64((int64_t)OW * (C / 4), 128), OH, N);
+        avgpool_fwd_k<4><<<grid, 128, 0, xsb_stream(stream)>>>(x, y, N, H, W, C, OH, OW, k, sh, sw);
+    } else {
+        dim3 grid((unsigned)ceil_div64((int64_t)OW * C, 256), OH, N);
+        avgpool_fwd_k<1><<<grid, 256, 0, xsb_stream(stream)>>>(x, y, N, H, W, C, OH, OW, k, sh, sw);
+    }
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }
@@ -311,8 +475,13 @@ int xsb_avgpool2d_bwd(const float* dy, float* dx, int N, int H, int W, int C, in
     const int OH = (H - k) / sh + 1, OW = (W - k) / sw + 1;
     XSB_CHECK_ARG(OH > 0 && OW > 0, "avgpool: empty output");
     XSB_CHECK_ARG(N <= 65535 && H <= 65535, "avgpool: N/H exceed grid limits");
-    dim3 grid((unsigned)ceil_div64((int64_t)W * C, 256), H, N);
-    avgpool_bwd_k<<<grid, 256, 0, xsb_stream(stream)>>>(dy, dx, N, H, W, C, OH, OW, k, sh, sw, accumulate);
+    if (C % 4 == 0 && aligned16(dy) && aligned16(dx)) {
+        dim3 grid((unsigned)ceil_div64((int64_t)W * (C / 4), 128), H, N);
+        avgpool_bwd_k<4><<<grid, 128, 0, xsb_stream(stream)>>>(dy, dx, N, H, W, C, OH, OW, k, sh, sw, accumulate);
+    } else {
+        dim3 grid((unsigned)ceil_div64((int64_t)W * C, 256), H, N);
+        avgpool_bwd_k<1><<<grid, 256, 0, xsb_stream(stream)>>>(dy, dx, N, H, W, C, OH, OW, k, sh, sw, accumulate);
+    }
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

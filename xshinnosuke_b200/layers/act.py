@@ -41,7 +41,17 @@ class ReLU(Layer):
                 if GLOBAL.INPUTS is None:
                     GLOBAL.INPUTS = x
                 arr.pending_op = None
-                producer(mask)
+                bn = getattr(producer, "bn", None) if rt.fuse_bn_relu_pool else None
+                if bn is not None:
+                    # BatchNorm -> ReLU: stay deferred one more op -- a max-pool that follows runs BN apply + ReLU + mask
+                    # + pool as ONE kernel (F.max_pool2d); anything else launches the fused BN+ReLU kernel on first touch
+                    def run2(m=None, _p=producer, _mask=mask):
+                        _p(_mask)
+                    run2.fusable_relu = False
+                    run2.bn_relu = dict(bn, mask=mask)
+                    arr.pending_op = run2
+                else:
+                    producer(mask)
             else:
                 F.relu(x, True, None, _mask=mask)
             if track:

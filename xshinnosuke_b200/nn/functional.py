@@ -302,8 +302,18 @@ def max_pool2d(inputs: Tensor, kernel_size: int = 2, stride=None, padding: int =
     y.cl = True
     need_grad = GLOBAL.COMPUTE_GRAD and inputs.requires_grad
     amax = rt.empty(max(y.size, 1), "uint8") if need_grad else None
-    lib.xsb_maxpool2d_fwd(x.ptr, y.wptr, amax.data_ptr() if amax is not None else None, n, h, w, c, k, sh, sw,
-                          padding, rt.stream())
+    aptr = amax.data_ptr() if amax is not None else None
+    # the input is a not-yet-materialised BatchNorm -> in-place ReLU result: pool straight from the conv output
+    # (BN apply + ReLU + mask + pool in one pass, the rectified tensor is never written unless someone else reads it)
+    fused = False
+    br = getattr(x.pending_op, "bn_relu", None) if x is inputs.arr else None
+    if br is not None and br["x"].cl:
+        rc = lib.xsb_bn_relu_maxpool_fwd(br["x"].ptr, br["mean"].peek_ptr(), br["invstd"].peek_ptr(), br["gamma"].ptr,
+                                         br["beta"].ptr, y.wptr, aptr, br["mask"].data_ptr(), n, h, w, c, k, sh, sw, padding,
+                                         rt.stream())
+        fused = rc == 0
+    if not fused:
+        lib.xsb_maxpool2d_fwd(x.ptr, y.wptr, aptr, n, h, w, c, k, sh, sw, padding, rt.stream())
     rt.launches += 1
     cache = {"mode": "im2col", "stride": (sh, sw), "padding": padding, "kernel_size": k}
     if need_grad:
@@ -383,6 +393,7 @@ def batch_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, moving_mean: Tensor,
                          0 if mask is None else 1, None if mask is None else mask.data_ptr(), rt.stream())
         rt.launches += 1
     run.fusable_relu = C % 4 == 0 and (R * (C // 4)) % 2 == 0 and x.cl == y.cl
+    run.bn = dict(x=x, mean=save_mean, invstd=save_invstd, gamma=gamma.arr, beta=beta.arr, R=R, C=C)
     y.pending_op = run
     rg = inputs.requires_grad or gamma.requires_grad or beta.requires_grad
     axis_field = tuple(i for i in range(x.ndim) if i != (axis % x.ndim))

@@ -42,6 +42,11 @@ def cost(name, a):
         N, H, W, C, k, sh, sw, pad = a[3:11]
         OH, OW = _pool_out(H, W, k, sh, sw, pad)
         return "byte", 4.0 * (N * H * W * C + N * OH * OW * C) + (N * OH * OW * C if a[2] else 0)
+    if name == "xsb_bn_relu_maxpool_fwd":
+        N, H, W, C, k, sh, sw, pad = a[8:16]
+        OH, OW = _pool_out(H, W, k, sh, sw, pad)
+        return "byte", 4.0 * (N * H * W * C + N * OH * OW * C) + (N * OH * OW * C if a[6] else 0) + \
+            (N * H * W * C / 8.0 if a[7] else 0.0)
     if name == "xsb_maxpool2d_bwd":
         N, H, W, C, k, sh, sw, pad = a[3:11]
         OH, OW = _pool_out(H, W, k, sh, sw, pad)
