@@ -1,21 +1,26 @@
 // tcgen05 tensor-core implicit-GEMM convolution for sm_100a (XSB_MATH_TF32).
 //
 //  * operands stay fp32 in HBM (channels-last activations, [OC,KH,KW,C] filters) and are fed to
-//    `tcgen05.mma.cta_group::1.kind::tf32` directly: no conversion pass, no im2col buffer;
+//    `tcgen05.mma.kind::tf32` directly: no conversion pass, no im2col buffer;
 //  * A tiles are fetched by TMA in IM2COL mode (cp.async.bulk.tensor.4d...im2col): one instruction
-//    gathers {32 channels x P pixels} for one filter tap, zero padding and the conv stride handled
+//    gathers {32 channels x 128 pixels} for one filter tap, zero padding and the conv stride handled
 //    by the tensor map; B tiles by tiled 2-D TMA; both land in SWIZZLE_128B shared memory;
-//  * accumulators live in TMEM (fp32), read back with tcgen05.ld in the epilogue warps;
-//  * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 =
-//    epilogue; smem ring of STAGES stages guarded by full/empty mbarriers, tcgen05.commit frees stages.
+//  * accumulators live in TMEM (fp32); the epilogue warps read them with tcgen05.ld, add the bias, stage 32 x 32
+//    blocks in swizzled shared memory (the idle operand ring) and leave through TMA stores / TMA reduce-adds,
+//    gathering BatchNorm partial statistics on the way (epilogue_store_tma);
+//  * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 = epilogue; the
+//    role loops run warp-uniformly and issue under elect.sync (tc_common.cuh: why); smem ring of STAGES stages
+//    guarded by full/empty mbarriers, tcgen05.commit frees stages.
 //
 //  fprop : D[pixel, oc]   = sum_{tap,c} patch[pixel,(tap,c)] * w[oc,(tap,c)]   A,B K-major
-//  dgrad : the same kernel on dY (zero-inserted for strided convs) with the flipped/transposed filter
-//          wt[c,kh',kw',oc], pad' = K-1-pad
+//          conv_fprop_tc_k (one CTA per 128 x N tile, N = a column part of <= 256), conv_fprop_tc2_k (CTA pairs,
+//          cta_group::2, opt-in), conv_halo_tc_k (conv_halo_tc.cuh: filter-resident, persistent; stem and 64->64 3x3)
+//  dgrad : stride-1 convolutions of dY, one per parity class of dX, with gathered sub-filters (tc_conv_dgrad)
 //  wgrad : D[(tap,c), oc] = sum_pixel patch[pixel,(tap,c)] * dY[pixel,oc]      A,B MN-major, split-K
+//          conv_wgrad_tc_k, stem_wgrad_tc_k, conv_wgrad_halo_k (conv_wgrad_halo_tc.cuh)
 //
 // Reference arithmetic: xs/nn/functional.py:405-442, xs/nn/grad_fn.py:186-203 (see gemm_conv.cu).
-// Shapes outside the envelope (C or OC not multiples of 32/64, strided dgrad) return
+// Shapes outside the envelope (C not a multiple of 32 and > 4, OC not a multiple of 64) return
 // XSB_ERR_UNSUPPORTED from the xsb_tc_* probes and the caller runs the fp32 FFMA kernel instead.
 #include "conv_halo_tc.cuh"
 #include "conv_wgrad_halo_tc.cuh"
