@@ -979,6 +979,22 @@ static bool stem_map_x(CUtensorMap* m, const float* xp, const ConvGeom& g, const
     return make_map_tiled(m, xp, 5, dims, strides, box, swz);
 }
 
+// The padded image lives at the TAIL of the workspace (every other user -- dgrad sub-filters, split-K partials -- grows
+// from its head), so the copy made by the stem's forward is still there when its wgrad runs later in the same step:
+// the tag remembers which input it holds. A forward always re-pads (the batch behind a pointer changes between steps).
+struct StemXpTag {
+    const float* x; const float* ws; int N, H, W, C, pad, Hp, Wp;
+};
+static StemXpTag g_xp_tag = {nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0};
+static float* stem_xp_ptr(float* ws, int64_t ws_floats, const StemPlan& pl) {
+    return ws + ((ws_floats - pl.xp_floats) & ~(int64_t)255);
+}
+static bool stem_xp_valid(const float* x, const float* ws, const ConvGeom& g, const StemPlan& pl) {
+    const StemXpTag& t = g_xp_tag;
+    return t.x == x && t.ws == ws && t.N == g.N && t.H == g.H && t.W == g.W && t.C == g.C && t.pad == g.pad &&
+           t.Hp == pl.Hp && t.Wp == pl.Wp;
+}
+
 static int stem_prepare(const float* x, const ConvGeom& g, const StemPlan& pl, float* xp, cudaStream_t s) {
     const int64_t total = (int64_t)g.N * pl.Hp * pl.Wp;
     stem_pad_c4_k<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(x, reinterpret_cast<float4*>(xp), g.N, g.H, g.W, g.C,
@@ -996,8 +1012,9 @@ static int stem_fwd(const float* x, const float* w, const float* bias, float* y,
     const int stages = halo_stages(g.KH, g.OC, rows * 1024);
     if (stages == 0 || rows > 256) return XSB_ERR_UNSUPPORTED;
     if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
-    float* xp = ws;
-    float* wq = ws + pl.xp_floats;
+    if (ws_floats < 2 * pl.xp_floats + pl.wq_floats + 512) return XSB_ERR_UNSUPPORTED;
+    float* xp = stem_xp_ptr(ws, ws_floats, pl);
+    float* wq = ws;
     CUtensorMap ta, tb;
     // rows of 32 floats starting every sw pixels: {32, OW, Hp, N} with OVERLAPPING dim-1 stride
     cuuint64_t dims[4] = {32, (cuuint64_t)g.OW, (cuuint64_t)pl.Hp, (cuuint64_t)g.N};
@@ -1008,6 +1025,7 @@ static int stem_fwd(const float* x, const float* w, const float* bias, float* y,
         return XSB_ERR_UNSUPPORTED;   // driver rejected the overlapping-stride map: FFMA kernel takes the call
     int rc = stem_prepare(x, g, pl, xp, s);
     if (rc != XSB_OK) return rc;
+    g_xp_tag = StemXpTag{x, ws, g.N, g.H, g.W, g.C, g.pad, pl.Hp, pl.Wp};
     stem_pack_filter_k<<<(g.OC * g.KH * 32 + 255) / 256, 256, 0, s>>>(w, wq, g.OC, g.KH, g.KW, g.C);
     XSB_LAUNCH_CHECK();
     HaloParams p{};
@@ -1023,9 +1041,9 @@ static int stem_fwd(const float* x, const float* w, const float* bias, float* y,
 static int stem_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
                       int64_t ws_floats, cudaStream_t s) {
     const StemPlan pl = stem_plan(g);
-    if (!ws || ws_floats < pl.xp_floats) return XSB_ERR_UNSUPPORTED;
+    if (!ws || ws_floats < 2 * pl.xp_floats + 512) return XSB_ERR_UNSUPPORTED;
     if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
-    float* xp = ws;
+    float* xp = stem_xp_ptr(ws, ws_floats, pl);
     CUtensorMap tx, tdy;
     cuuint64_t ddims[4] = {(cuuint64_t)g.OC, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
     cuuint64_t dstr[3] = {(cuuint64_t)g.OC * 4, (cuuint64_t)g.OW * g.OC * 4, (cuuint64_t)g.OH * g.OW * g.OC * 4};
@@ -1033,8 +1051,19 @@ static int stem_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
     if (!stem_map_x(&tx, xp, g, pl, STEM_TW, STEM_WTH, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
         !make_map_tiled(&tdy, dy, 4, ddims, dstr, dbox, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
         return XSB_ERR_UNSUPPORTED;
-    int rc = stem_prepare(x, g, pl, xp, s);
-    if (rc != XSB_OK) return rc;
+    int rc = XSB_OK;
+    if (stem_xp_valid(x, ws, g, pl)) {
+        g_xp_tag.x = nullptr;            // one forward, one wgrad: the next wgrad on this pointer pads again
+    } else {
+        rc = stem_prepare(x, g, pl, xp, s);
+        if (rc != XSB_OK) return rc;
+    }
+    static const int stem_halo = [] { const char* e = getenv("XSB_TC_WGRAD_HALO"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (stem_halo) {   // persistent halo kernel: every filter row from one load, dY read once
+        if (!accumulate) XSB_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.OC * g.KH * g.KW * g.C * sizeof(float), s));
+        rc = wgrad_halo_stem(dy, xp, dw, g, pl.Hp, pl.Wp, s);
+        if (rc != XSB_ERR_UNSUPPORTED) return rc;
+    }
     constexpr int STAGES = 4, BN = 64;
     const int tiles_w = (g.OW + STEM_TW - 1) / STEM_TW, tiles_h = (g.OH + STEM_WTH - 1) / STEM_WTH;
     const int total_kb = g.N * tiles_w * tiles_h;

@@ -28,9 +28,19 @@ struct WgradHaloParams {
     int n_oc_tiles;       // OC / BN
     int sa_slots, sb_slots, a_slot_bytes;
     int C;                // input channels (column stride of the dW map)
+    // generalisation for the stem (C <= 4 pre-padded to 4 channels, filter columns folded into the 32-float row):
+    int sh;               // conv stride along h: tile row r / filter row kh is the group at (r*sh + kh)*1024
+    int groups;           // ceil(KH / 4) accumulators per load: M blocks kh = 4g .. 4g+3
+    int KWl;              // halo loads per channel block (KW, or 1 when the row already holds all filter columns)
+    int pad_h, pad_w;     // subtracted from the TMA coordinates (0 for a pre-padded image)
+    int stem;             // epilogue: rows are (kh, kw*4 + c) -> scattered red.add into dw_raw[oc][kh][kw][c]
+    int KW_real, C_real;
+    float* dw_raw;
 };
 
-template <int BN>
+// SH = conv stride along h, G = accumulators (groups of four filter rows) per load: compile-time so that the issue
+// loop is immediates only (N = 64 MMAs are issue-sensitive)
+template <int BN, int SH, int G>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
                   const __grid_constant__ CUtensorMap tmW, const WgradHaloParams p) {
@@ -55,7 +65,8 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int cb0 = (pass / p.n_oc_tiles) * p.cbp;
     int cbn = p.cblocks - cb0;                 // channel blocks of this pass
     if (cbn > p.cbp) cbn = p.cbp;
-    const int n_acc = cbn * p.KW;
+    const int n_loads = cbn * p.KWl;
+    const int n_acc = n_loads * G;
     // contiguous tile range of this CTA
     const int t_begin = (int)((int64_t)blockIdx.x * p.n_tiles / gridDim.x);
     const int t_end = (int)((int64_t)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
@@ -84,7 +95,7 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
-    const int a_box_bytes = (WH_TH + p.KH - 1) * WH_TW * A_ROW_BYTES;   // bytes the halo load writes (slot has 1 row more)
+    const int a_box_bytes = ((WH_TH - 1) * SH + p.KH) * WH_TW * A_ROW_BYTES;   // bytes the halo load writes
 
     if (warp == 0) {
         int sa = 0, sb = 0;
@@ -102,11 +113,12 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
             if (++sb == SB) { sb = 0; phb ^= 1; }
             for (int cb = cb0; cb < cb0 + cbn; ++cb)
-                for (int kw = 0; kw < p.KW; ++kw) {
+                for (int kw = 0; kw < p.KWl; ++kw) {
                     mbar_wait(&emptyA[sa], pha ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&fullA[sa], a_box_bytes);
-                        tma_load_4d(sA + sa * p.a_slot_bytes, &tmX, &fullA[sa], cb * 32, w0 + kw - p.pad, h0 - p.pad, n_img);
+                        tma_load_4d(sA + sa * p.a_slot_bytes, &tmX, &fullA[sa], cb * 32, w0 + kw - p.pad_w,
+                                    h0 * SH - p.pad_h, n_img);
                     }
                     if (++sa == SA) { sa = 0; pha ^= 1; }
                 }
@@ -125,17 +137,20 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint32_t fresh = 0;     // 0 while this CTA's accumulators have not been written yet
         for (int t = t_begin; t < t_end; ++t) {
             mbar_wait(&fullB[sb], phb);
-            for (int a = 0; a < n_acc; ++a) {
+            for (int a = 0; a < n_loads; ++a) {
                 mbar_wait(&fullA[sa], pha);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
 #pragma unroll
-                    for (int r = 0; r < WH_TH; ++r)   // tile row r: K = 8 pixels = 1024 bytes of both operands
-                        umma_tf32_split(tacc, a_lo + (uint32_t)(r * 64), hi, b_lo + (uint32_t)(r * 64), hi, idesc,
-                                        r ? 1u : fresh);
+                    for (int g = 0; g < G; ++g) {
+                        const uint32_t tacc = tmem_base + (uint32_t)((a * G + g) * BN);
+#pragma unroll
+                        for (int r = 0; r < WH_TH; ++r)   // tile row r: K = 8 pixels = 1024 bytes of both operands
+                            umma_tf32_split(tacc, a_lo + (uint32_t)((g * 4 + r * SH) * 64), hi, b_lo + (uint32_t)(r * 64), hi,
+                                            idesc, r ? 1u : fresh);
+                    }
                     umma_commit(&emptyA[sa]);
-                    if (a == n_acc - 1) umma_commit(&emptyB[sb]);
+                    if (a == n_loads - 1) umma_commit(&emptyB[sb]);
                 }
                 __syncwarp();
                 a_lo += a_enc;
@@ -152,7 +167,26 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        if (t_end > t_begin && q < p.KH) {
+        if (t_end > t_begin && p.stem) {
+            // rows of accumulator g: (kh = 4g + q, lane = kw*4 + c); scattered element-wise reduction into dW[oc][kh][kw][c]
+            const int kw = lane >> 2, c = lane & 3;
+            for (int g = 0; g < G; ++g) {
+                const int kh = 4 * g + q;
+                const bool valid = kh < p.KH && kw < p.KW_real && c < p.C_real;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN + c0), v);
+                    tmem_wait_ld();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            atomicAdd(p.dw_raw + (((int64_t)(oc0 + c0 + j) * p.KH + kh) * p.KW_real + kw) * p.C_real + c,
+                                      __uint_as_float(v[j]));
+                    }
+                }
+            }
+        } else if (t_end > t_begin && q < p.KH) {
             float* stage = reinterpret_cast<float*>(sA + q * 4096);    // the rings are idle: [32 oc][32 c] per warp
             for (int a = 0; a < n_acc; ++a) {
                 const int cb = cb0 + a / p.KW, kw = a - (a / p.KW) * p.KW;
@@ -228,24 +262,76 @@ static int wgrad_halo(const float* dy, const float* x, float* dw, const ConvGeom
         !make_map_2d(&tw, dw, (uint64_t)g.OC, (uint64_t)g.KH * g.KW * g.C, 32, CU_TENSOR_MAP_SWIZZLE_NONE))
         return XSB_ERR_UNSUPPORTED;
     WgradHaloParams p{g.N, g.OH, g.OW, tiles_w, tiles_h, n_tiles, g.KH, g.KW, g.pad, cblocks, cbp, n_oc_tiles,
-                      sa_slots, sb_slots, a_slot_bytes, g.C};
+                      sa_slots, sb_slots, a_slot_bytes, g.C, 1, 1, g.KW, g.pad, g.pad, 0, g.KW, g.C, dw};
     const int smem = 1024 + sa_slots * a_slot_bytes + sb_slots * b_bytes + 512;
     dim3 grid(ctas, passes);
     if (BN == 64) {
         static bool configured = false;
         if (!configured) {
-            XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_k<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_k<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             configured = true;
         }
-        conv_wgrad_halo_k<64><<<grid, kThreads, smem, s>>>(tx, tdy, tw, p);
+        conv_wgrad_halo_k<64, 1, 1><<<grid, kThreads, smem, s>>>(tx, tdy, tw, p);
     } else {
         static bool configured = false;
         if (!configured) {
-            XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_k<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_k<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             configured = true;
         }
-        conv_wgrad_halo_k<128><<<grid, kThreads, smem, s>>>(tx, tdy, tw, p);
+        conv_wgrad_halo_k<128, 1, 1><<<grid, kThreads, smem, s>>>(tx, tdy, tw, p);
     }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// Stem (C <= 4): xp is the zero-bordered 4-channel copy of the input ([N, Hp, Wp, 4], see stem_pad_c4_k); a row of the
+// A operand is the 32 floats (8 pixels x 4 channels) starting at pixel (oh*sh + kh, ow*sw): the tensor map walks
+// OVERLAPPING rows {32 floats, OW (stride sw pixels), Hp, N}. dw must already hold the value to accumulate onto.
+static int wgrad_halo_stem(const float* dy, const float* xp, float* dw, const ConvGeom& g, int Hp, int Wp, cudaStream_t s) {
+    if (g.OC != 64 || g.KH > 8 || g.KW > 8 || g.C > 4) return XSB_ERR_UNSUPPORTED;
+    constexpr int BN = 64;
+    const int groups = (g.KH + 3) / 4;
+    const int tiles_w = (g.OW + WH_TW - 1) / WH_TW, tiles_h = (g.OH + WH_TH - 1) / WH_TH;
+    if ((int64_t)g.OH * g.OW * 10 < (int64_t)tiles_w * tiles_h * WH_TW * WH_TH * 7) return XSB_ERR_UNSUPPORTED;
+    const int n_tiles = g.N * tiles_w * tiles_h;
+    int ctas = xsb_sm_count_cached();
+    if (ctas > n_tiles) ctas = n_tiles;
+    if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
+    const int a_rows = (WH_TH - 1) * g.sh + g.KH;                 // rows the halo load brings
+    const int a_slot_rows = (WH_TH - 1) * g.sh + 4 * groups;      // rows the M blocks kh < 4*groups may touch
+    if (a_rows > 256) return XSB_ERR_UNSUPPORTED;
+    const int a_slot_bytes = a_slot_rows * WH_TW * A_ROW_BYTES;
+    const int b_bytes = (BN / 32) * WH_TW * WH_TH * A_ROW_BYTES;
+    const int sb_slots = 3;
+    int sa_slots = (227 * 1024 - 1024 - 512 - sb_slots * b_bytes) / a_slot_bytes;
+    if (sa_slots > 16) sa_slots = 16;
+    if (sa_slots < 3) return XSB_ERR_UNSUPPORTED;
+    CUtensorMap tx, tdy, tw;
+    cuuint64_t xd[4] = {32, (cuuint64_t)g.OW, (cuuint64_t)Hp, (cuuint64_t)g.N};
+    cuuint64_t xs_[3] = {(cuuint64_t)g.sw * 16, (cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16};
+    cuuint32_t xb[4] = {32, WH_TW, (cuuint32_t)a_rows, 1};
+    cuuint64_t dd[4] = {(cuuint64_t)g.OC, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+    cuuint64_t ds[3] = {(cuuint64_t)g.OC * 4, (cuuint64_t)g.OW * g.OC * 4, (cuuint64_t)g.OH * g.OW * g.OC * 4};
+    cuuint32_t db[4] = {32, WH_TW, WH_TH, 1};
+    if (!make_map_tiled(&tx, xp, 4, xd, xs_, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map_tiled(&tdy, dy, 4, dd, ds, db, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return XSB_ERR_UNSUPPORTED;
+    tw = tdy;   // unused by the stem epilogue
+    WgradHaloParams p{g.N, g.OH, g.OW, tiles_w, tiles_h, n_tiles, g.KH, 1, 0, 1, 1, 1,
+                      sa_slots, sb_slots, a_slot_bytes, 4, g.sh, groups, 1, 0, 0, 1, g.KW, g.C, dw};
+    const int smem = 1024 + sa_slots * a_slot_bytes + sb_slots * b_bytes + 512;
+    auto go = [&](auto kern) -> int {
+        XSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        kern<<<dim3(ctas, 1), kThreads, smem, s>>>(tx, tdy, tw, p);
+        return XSB_OK;
+    };
+    int rc;
+    if (g.sh == 1 && groups == 1) rc = go(conv_wgrad_halo_k<64, 1, 1>);
+    else if (g.sh == 1 && groups == 2) rc = go(conv_wgrad_halo_k<64, 1, 2>);
+    else if (g.sh == 2 && groups == 1) rc = go(conv_wgrad_halo_k<64, 2, 1>);
+    else if (g.sh == 2 && groups == 2) rc = go(conv_wgrad_halo_k<64, 2, 2>);
+    else return XSB_ERR_UNSUPPORTED;
+    if (rc != XSB_OK) return rc;
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }
