@@ -488,6 +488,27 @@ def test_graphed_step_feeds_prefetched_host_batches():
     np.testing.assert_allclose(losses_g, losses_e[2:], rtol=1e-5)
 
 
+def test_static_fit_replayed_as_cuda_graph(golden):
+    """Model.fit(..., cuda_graph=True) captures the static graph's train step after two eager batches
+    and replays it; the loss trajectory equals the reference's (golden `fit/*`, same tolerance as the eager path),
+    including the MLP recipe whose last batch of every epoch is partial (runs eagerly between replays)."""
+    import parity_suite as S
+    np.random.seed(0)
+    xd = np.random.rand(96, 1, 28, 28)
+    yd = np.random.randint(0, 10, (96,))
+    np.random.seed(1)
+    model = S.readme_cnn(lr=0.01)
+    prof = model.fit(xd, yd, batch_size=32, epochs=2, verbose=0, shuffle=False, cuda_graph=True)
+    np.testing.assert_allclose(prof.data["train_loss"], golden.case("fit/cnn")["losses"], rtol=2e-4)
+    np.random.seed(0)
+    xd = np.random.rand(80, 784)
+    yd = np.random.randint(0, 10, (80,))
+    np.random.seed(1)
+    mlp = S.readme_mlp(lr=0.05)
+    prof = mlp.fit(xd, yd, batch_size=32, epochs=2, verbose=0, shuffle=False, cuda_graph=True)
+    np.testing.assert_allclose(prof.data["train_loss"], golden.case("fit/mlp")["losses"], rtol=2e-4)
+
+
 def test_dataloader_prefetch_matches_plain():
     """the pinned / side-stream prefetching loader yields exactly the reference's batches
     (same order incl. the per-epoch reseeding), and rank shards are contiguous slices."""

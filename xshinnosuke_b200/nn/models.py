@@ -74,7 +74,11 @@ class _Model(_Base):
         raise NotImplementedError
 
     def fit(self, x, y, batch_size=None, epochs=1, verbose=1, shuffle=True, validation_data=None,
-            validation_split=0.0, initial_epoch=0):
+            validation_split=0.0, initial_epoch=0, cuda_graph=False):
+        """xs/nn/models.py:61-129. `cuda_graph=True` (no reference counterpart): the static graph's
+        train step -- zero_grad, forward into the preallocated `out=` buffers, loss, backward, optimizer step -- is
+        captured into ONE CUDA graph after the first two full batches (which run eagerly: every batch is exactly one
+        update either way) and replayed for every further full-size batch; a partial last batch runs eagerly."""
         x, y = np.asarray(x), np.asarray(y)
         names = ["train_loss", "train_acc"]
         if validation_data is None and 0.0 < validation_split < 1.0:
@@ -86,6 +90,20 @@ class _Model(_Base):
             train_x, train_y = x, y
         loader = DataLoader(DataSet(train_x, train_y), batch_size, shuffle)
         v_acc = v_loss = 0.0
+        from ..core.device import rt
+        use_graph = bool(cuda_graph) and validation_data is None and batch_size is not None and \
+            rt.device is not None and rt.device.type == "cuda"
+        gx = gy = graphed = None
+        n_full = 0
+
+        def train_step_static():
+            self.train()
+            self.optimizer.zero_grad()
+            pred_ = self.forward(gx)
+            loss_ = self.loss.forward(pred_, gy)
+            self.backward(loss_)
+            self.optimizer.step()
+            return pred_, loss_
         with SummaryProfile(*names, verbose=verbose) as profile:
             for epoch in range(initial_epoch, epochs):
                 t0 = time.time()
@@ -93,14 +111,33 @@ class _Model(_Base):
                     print("\033[1;31m Epoch[%d/%d]\033[0m" % (epoch + 1, epochs))
                 bar = ProgressBar(max_iter=len(train_x), verbose=verbose)
                 for idx, (batch_x, batch_y) in enumerate(loader):
-                    if idx == 0 or idx == len(loader) - 1:
-                        self.init_graph_out_tensor(batch_x, batch_y)
-                    self.train()
-                    self.optimizer.zero_grad()
-                    pred = self.forward(batch_x)
-                    loss = self.loss.forward(pred, batch_y)
-                    self.backward(loss)
-                    self.optimizer.step()
+                    full = use_graph and batch_x.shape[0] == batch_size
+                    if full:
+                        # fixed input tensors: every full batch is copied into them on the device
+                        if gx is None:
+                            gx, gy = Tensor(batch_x.arr.clone()), Tensor(batch_y.arr.clone())
+                        else:
+                            for dst, src in ((gx, batch_x), (gy, batch_y)):
+                                src.arr.ptr  # noqa: B018 -- materialise
+                                dst.arr.wptr  # noqa: B018
+                                dst.arr.buf[: max(dst.arr.size, 1)].copy_(src.arr.buf[: max(src.arr.size, 1)])
+                        if graphed is None or idx == 0:
+                            self.init_graph_out_tensor(gx, gy)
+                        if graphed is None and n_full >= 2:
+                            from ..utils.graph import GraphedStep
+                            graphed = GraphedStep(train_step_static, warmup=0)   # capture only, executes nothing
+                        pred, loss = graphed() if graphed is not None else train_step_static()
+                        n_full += 1
+                        batch_y = gy
+                    else:
+                        if idx == 0 or idx == len(loader) - 1 or use_graph:
+                            self.init_graph_out_tensor(batch_x, batch_y)
+                        self.train()
+                        self.optimizer.zero_grad()
+                        pred = self.forward(batch_x)
+                        loss = self.loss.forward(pred, batch_y)
+                        self.backward(loss)
+                        self.optimizer.step()
                     train_acc = self.loss.calc_acc(pred, batch_y)
                     loss_value = loss.item()
                     profile.step("train_acc", train_acc)

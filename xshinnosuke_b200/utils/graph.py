@@ -45,12 +45,15 @@ class GraphedStep:
         self._slots = None
         self._next_slot = 0
         self._side_in = None
-        side = t.cuda.Stream(device=rt.device)
-        side.wait_stream(t.cuda.current_stream())
-        with t.cuda.stream(side):          # warm-up off the default stream: builds flat buffers, scratch, attributes
-            for _ in range(max(warmup, 1)):
-                step_fn()
-        t.cuda.current_stream().wait_stream(side)
+        if warmup > 0:
+            side = t.cuda.Stream(device=rt.device)
+            side.wait_stream(t.cuda.current_stream())
+            with t.cuda.stream(side):      # warm-up off the default stream: builds flat buffers, scratch, attributes
+                for _ in range(warmup):
+                    step_fn()
+            t.cuda.current_stream().wait_stream(side)
+        # warmup == 0: the caller has already run this very step eagerly (Model.fit captures after its first batches,
+        # every one of which is a real update) -- capture only
         t.cuda.synchronize()
         GLOBAL.INPUTS = GLOBAL.OUTPUTS = GLOBAL.GRAPH = None
         self.graph = t.cuda.CUDAGraph()
