@@ -61,6 +61,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--layers", default="")
     ap.add_argument("--json", default="")
+    ap.add_argument("--cpu-ref", action="store_true",
+                    help="also time the reference's NumPy algorithm (oracle/, float64 im2col + np.dot + col2im) for conv "
+                         "fwd / bwd and BN on a 2-image slice of each layer, on the host cores (context, SURVEY 8d)")
     a = ap.parse_args()
     rt.ensure()
     xs.set_math_mode(a.math)
@@ -84,6 +87,30 @@ def main():
                          peak_kind=pk, note=note))
         print(f"{op:12s} {layer:10s} {sec * 1e6:9.1f} us  {ach:9.1f} {unit:8s} {100 * ach / peak:5.1f}% of {pk} {note}", flush=True)
 
+    def cpu_ref(lname, C, H, OC, k, s_, p_):
+        """The oracle (test infrastructure) as the CPU yardstick: per-op GFLOP/s / GB/s of the reference's algorithm."""
+        import time
+        from oracle import xs_numpy as X
+        n = 2
+        rs = np.random.RandomState(0)
+        xh = rs.randn(n, C, H, H)
+        wh = rs.randn(OC, C, k, k) * 0.1
+        bh = rs.randn(1, OC)
+        t0 = time.perf_counter()
+        yh, col = X.conv2d_fwd(xh, wh, bh, (s_, s_), p_)
+        t1 = time.perf_counter()
+        X.conv2d_bwd(np.ones_like(yh), xh.shape, wh, col, (s_, s_), p_)
+        t2 = time.perf_counter()
+        fl = 2.0 * yh.size * C * k * k
+        X.batch_norm_fwd(yh, np.ones(OC), np.zeros(OC), np.zeros(OC), np.ones(OC), 1, 1e-6, 0.99)
+        t3 = time.perf_counter()
+        row = dict(op="cpu_ref", layer=lname, images=n, conv_fwd_gflops=fl / (t1 - t0) / 1e9,
+                   conv_bwd_gflops=2 * fl / (t2 - t1) / 1e9, bn_fwd_gbs=3 * 8.0 * yh.size / (t3 - t2) / 1e9,
+                   threads=os.cpu_count())
+        rows.append(row)
+        print(f"cpu_ref      {lname:10s} NumPy f64, {n} images: conv fwd {row['conv_fwd_gflops']:7.1f} GFLOP/s, "
+              f"conv bwd {row['conv_bwd_gflops']:7.1f} GFLOP/s, BN fwd {row['bn_fwd_gbs']:6.2f} GB/s", flush=True)
+
     sel = [l for l in LAYERS[a.shapes] if not a.layers or l[0] in a.layers.split(",")]
     for (lname, C, H, OC, k, s, p) in sel:
         OH = (H - k + 2 * p) // s + 1
@@ -91,6 +118,8 @@ def main():
         y, dy = dev(N, OH, OH, OC), dev(N, OH, OH, OC)
         dx, dw = dev(N, H, H, C), dev(OC, k, k, C)
         g = (N, H, H, C, OC, k, k, s, s, p)
+        if a.cpu_ref:
+            cpu_ref(lname, C, H, OC, k, s, p)
         if "conv_fwd" in ops:
             args = (x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr()) + g + (mode, ws, wsn, st)
             report("conv_fwd", lname, "xsb_conv2d_fwd", args, timed(lambda: lib.xsb_conv2d_fwd(*args), a.iters))
