@@ -364,6 +364,43 @@ def test_bn_relu_maxpool_fused_equals_unfused(n, c, h, k, s, p):
     assert X.rel_err(y1, pr) <= 1e-5
 
 
+@pytest.mark.parametrize("n,c,h,w,oc,k,s,p", [
+    (3, 64, 12, 20, 64, 3, 1, 1), (2, 64, 32, 24, 64, 3, 1, 1), (2, 64, 19, 28, 128, 3, 2, 1), (2, 3, 30, 44, 64, 7, 2, 3),
+    (2, 128, 9, 14, 256, 3, 1, 1), (1, 64, 16, 40, 64, 3, 1, 1), (2, 64, 21, 13, 128, 1, 2, 0), (2, 4, 17, 33, 64, 5, 2, 2)])
+def test_conv_non_square_images_tf32(n, c, h, w, oc, k, s, p):
+    """H != W (every kernel takes the two extents separately: im2col, halo fwd / dgrad / wgrad, parity-class dgrad,
+    stem): fwd, dX, dW and the fused BN statistics against the float64 oracle."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    xs.set_math_mode("tf32")
+    try:
+        rs = np.random.RandomState(n + c + h + w)
+        x = rs.randn(n, c, h, w).astype(np.float32)
+        wt = (rs.randn(oc, c, k, k) * 0.1).astype(np.float32)
+        b = rs.randn(1, oc).astype(np.float32)
+        tx, tw, tb = xs.tensor(x, requires_grad=c >= 32), nn.Parameter(wt), nn.Parameter(b)
+        mm, mv = xs.tensor(np.zeros(oc, dtype=np.float32)), xs.tensor(np.ones(oc, dtype=np.float32))
+        yc = F.conv2d(tx, tw, tb, (s, s), p)
+        yb = F.batch_norm(yc, nn.Parameter(np.ones(oc, dtype=np.float32)), nn.Parameter(np.zeros(oc, dtype=np.float32)), mm, mv,
+                          1, True, 1e-6, 0.99)
+        conv_out = yc.eval.astype(np.float64)
+        yr, col = X.conv2d_fwd(x.astype(np.float64), wt.astype(np.float64), b.astype(np.float64), (s, s), p)
+        assert conv_out.shape == yr.shape and X.rel_err(conv_out, yr) <= TOL_TC
+        assert X.rel_err(mm.eval, 0.01 * conv_out.mean(axis=(0, 2, 3))) <= 1e-5
+        assert X.rel_err(mv.eval, 0.99 + 0.01 * conv_out.var(axis=(0, 2, 3))) <= 1e-5
+        g = rs.randn(*yr.shape).astype(np.float32)
+        y2 = F.conv2d(tx, tw, tb, (s, s), p)
+        y2.backward(gradients=g)
+        dx, dw, db = X.conv2d_bwd(g.astype(np.float64), x.shape, wt.astype(np.float64), col, (s, s), p, need_dx=c >= 32)
+        assert X.rel_err(tw.grad.eval, dw) <= TOL_TC
+        if c >= 32:
+            assert X.rel_err(tx.grad.eval, dx) <= TOL_TC
+    finally:
+        xs.set_math_mode("fp32")
+
+
 def test_resnet18_tf32_mode(golden):
     """Whole ResNet-18 step in tf32 mode: logits of the first forward within 2e-3 of the reference."""
     import xshinnosuke_b200 as xs
