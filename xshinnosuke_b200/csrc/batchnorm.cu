@@ -782,7 +782,7 @@ bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x
 
 // ------------------------------------------------------------------ statistics from conv-epilogue partials
 // part[p][{n, mean, M2}][C], p < P  ->  save_mean / save_invstd and the running-statistics update. block (32, TY).
-__global__ void bn_finalize_k(const float* __restrict__ part, int P, int C, float R, float* __restrict__ save_mean,
+__global__ void __launch_bounds__(1024) bn_finalize_k(const float* __restrict__ part, int P, int C, float R, float* __restrict__ save_mean,
                               float* __restrict__ save_invstd, float* running_mean, float* running_var, float eps,
                               float momentum) {
     __shared__ float s_n[32][33], s_mean[32][33], s_m2[32][33];
