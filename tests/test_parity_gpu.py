@@ -218,6 +218,46 @@ def test_conv_tf32_tensor_cores(n, c, h, oc, k, s, p, n_tc):
         xs.set_math_mode("fp32")
 
 
+@pytest.mark.parametrize("m,n,k,on_tc", [
+    (128, 500, 784, True),      # BASELINE configs[1]: Dense(784 -> 500), batch 128 (K tail of 16, N tail of 116)
+    (128, 100, 4608, True),     # ResNet-18 head (split-K)
+    (128, 10, 500, False),      # Dense(10): 40-byte rows cannot be a TMA source -> FFMA kernel
+    (77, 36, 40, True), (300, 260, 200, True), (1, 16, 8, True), (130, 132, 36, True)])
+def test_dense_gemm_tf32_tensor_cores(m, n, k, on_tc):
+    """xsb_gemm in tf32 mode = the tcgen05 kernel for all three Dense products (y = x.W + b, dX = dY.W^T, dW = x^T.dY,
+    each with and without "+="), ragged M / N / K served by TMA zero fill and clipped stores; float64 NumPy is the
+    oracle (xs/nn/functional.py:81-120, xs/nn/grad_fn.py:73-99)."""
+    from xshinnosuke_b200._lib import MATH_TF32, lib
+    from xshinnosuke_b200.core.device import DevArray, rt
+    from oracle import xs_numpy as X
+    rs = np.random.RandomState(m + n + k)
+    x, w = rs.randn(m, k).astype(np.float32), (rs.randn(k, n) * 0.1).astype(np.float32)
+    b, dy = rs.randn(n).astype(np.float32), rs.randn(m, n).astype(np.float32)
+    c0y, c0x, c0w = rs.randn(m, n).astype(np.float32), rs.randn(m, k).astype(np.float32), rs.randn(k, n).astype(np.float32)
+    dx_, dw_, db_, ddy = DevArray.from_numpy(x), DevArray.from_numpy(w), DevArray.from_numpy(b), DevArray.from_numpy(dy)
+    x64, w64, dy64 = x.astype(np.float64), w.astype(np.float64), dy.astype(np.float64)
+
+    def run(a, bm, c_init, bias, M, N, K, ta, tb, acc):
+        out = DevArray.from_numpy(c_init.copy())
+        lib.xsb_gemm(a.ptr, bm.ptr, out.wptr, bias.ptr if bias is not None else None, M, N, K, ta, tb, acc, MATH_TF32,
+                     rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream())
+        return out.to_numpy()
+
+    s0 = _tc_stats()
+    for acc in (0, 1):
+        y = run(dx_, dw_, c0y, db_, m, n, k, 0, 0, acc)
+        assert X.rel_err(y, x64 @ w64 + b + acc * c0y) <= TOL_TC
+        gx = run(ddy, dw_, c0x, None, m, k, n, 0, 1, acc)
+        assert X.rel_err(gx, dy64 @ w64.T + acc * c0x) <= TOL_TC
+        gw = run(dx_, ddy, c0w, None, k, n, m, 1, 0, acc)
+        assert X.rel_err(gw, x64.T @ dy64 + acc * c0w) <= TOL_TC
+    s1 = _tc_stats()
+    if on_tc:
+        assert s1[0] - s0[0] == 6 and s1[1] == s0[1]
+    else:
+        assert s1[0] - s0[0] < 6 and (s1[0] - s0[0]) + (s1[1] - s0[1]) == 6
+
+
 @pytest.mark.parametrize("n,c,h,oc,k,s,p", [
     (4, 64, 14, 64, 3, 1, 1), (8, 64, 28, 128, 3, 2, 1), (2, 256, 7, 512, 3, 1, 1), (3, 3, 56, 64, 7, 2, 3),
     (5, 64, 32, 64, 3, 1, 1), (4, 64, 30, 64, 3, 1, 2), (2, 128, 9, 256, 1, 2, 0), (150, 64, 16, 64, 3, 1, 1),

@@ -24,6 +24,7 @@
 // XSB_ERR_UNSUPPORTED from the xsb_tc_* probes and the caller runs the fp32 FFMA kernel instead.
 #include "conv_halo_tc.cuh"
 #include "conv_wgrad_halo_tc.cuh"
+#include "gemm_tc.cuh"
 
 namespace tc {
 
@@ -1101,9 +1102,14 @@ static bool fprop_ok(int Cx, int OCx, const void* a, const void* b, const void* 
     return Cx % 32 == 0 && OCx % 64 == 0 && aligned16(a) && aligned16(b) && aligned16(c);
 }
 
-int xsb_tc_gemm(const float*, const float*, float*, const float*, int, int, int, int, int, int, float*, int64_t,
-                cudaStream_t) {
-    return XSB_ERR_UNSUPPORTED;   // Dense layers of the hot path are < 1 % of the FLOPs: FFMA kernel
+// Dense products (gemm_tc.cuh). XSB_TC_GEMM=0 (env, read once) keeps them on the FFMA kernel for A/B measurements.
+int xsb_tc_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA, int transB,
+                int accumulate, float*, int64_t, cudaStream_t s) {
+    static const int on = [] { const char* e = getenv("XSB_TC_GEMM"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (!on) return XSB_ERR_UNSUPPORTED;
+    const int rc = gemm_tf32(A, B, C, bias, M, N, K, transA, transB, accumulate, s);
+    if (rc == XSB_OK) ++g_tc_launches;
+    return rc;
 }
 
 // XSB_TC_HALO=0 (env, read once) routes everything through the im2col kernel (A/B measurements)
