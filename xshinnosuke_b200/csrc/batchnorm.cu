@@ -785,9 +785,10 @@ bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x
 __global__ void __launch_bounds__(1024) bn_finalize_k(const float* __restrict__ part, int P, int C, float R, float* __restrict__ save_mean,
                               float* __restrict__ save_invstd, float* running_mean, float* running_var, float eps,
                               float momentum) {
-    __shared__ float s_n[32][33], s_mean[32][33], s_m2[32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
-    const int c = blockIdx.x * 32 + tx;
+    __shared__ float s_n[1152], s_mean[1152], s_m2[1152];     // [TY][TX + 1], (TX, TY) = (32, <= 32) or (8, 128)
+    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    const int c = blockIdx.x * TX + tx;
+    const int me = ty * (TX + 1) + tx;
     float an = 0.f, amean = 0.f, am2 = 0.f;
     if (c < C) {
         for (int p0 = ty; p0 < P; p0 += TY * 8) {
@@ -808,19 +809,19 @@ __global__ void __launch_bounds__(1024) bn_finalize_k(const float* __restrict__ 
             }
         }
     }
-    s_n[ty][tx] = an; s_mean[ty][tx] = amean; s_m2[ty][tx] = am2;
+    s_n[me] = an; s_mean[me] = amean; s_m2[me] = am2;
     __syncthreads();
     for (int st = TY / 2; st > 0; st >>= 1) {
         if (ty < st) {
-            const Moments m = merge(Moments{s_n[ty][tx], s_mean[ty][tx], s_m2[ty][tx]},
-                                    Moments{s_n[ty + st][tx], s_mean[ty + st][tx], s_m2[ty + st][tx]});
-            s_n[ty][tx] = m.n; s_mean[ty][tx] = m.mean; s_m2[ty][tx] = m.m2;
+            const int other = me + st * (TX + 1);
+            const Moments m = merge(Moments{s_n[me], s_mean[me], s_m2[me]}, Moments{s_n[other], s_mean[other], s_m2[other]});
+            s_n[me] = m.n; s_mean[me] = m.mean; s_m2[me] = m.m2;
         }
         __syncthreads();
     }
     if (ty == 0 && c < C) {
-        const float mean = s_mean[0][tx];
-        const float var = s_m2[0][tx] / R;
+        const float mean = s_mean[tx];
+        const float var = s_m2[tx] / R;
         save_mean[c] = mean;
         save_invstd[c] = 1.0f / sqrtf(var + eps);
         if (running_mean) running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * mean;
@@ -926,9 +927,12 @@ int xsb_bn_eval_fwd(const float* x, const float* gamma, const float* beta, const
 int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* running_mean, float* running_var,
                     float* save_mean, float* save_invstd, float eps, float momentum, void* stream) {
     XSB_CHECK_ARG(P > 0 && R > 0 && C > 0, "bn_finalize: empty input");
-    const int TY = P > 32 ? 32 : 8;
-    bn_finalize_k<<<(C + 31) / 32, dim3(32, TY), 0, xsb_stream(stream)>>>(partials, P, C, (float)R, save_mean, save_invstd,
-                                                                          running_mean, running_var, eps, momentum);
+    // many partials (one per 128-row tile of a large layer): 8 channels x 128 partial rows per block, so that C / 8 blocks
+    // share the serial Chan merges; few partials (persistent producers): 32 channels per block
+    const bool tall = P > 64;
+    const int TX = tall ? 8 : 32, TY = tall ? 128 : (P > 32 ? 32 : 8);
+    bn_finalize_k<<<(C + TX - 1) / TX, dim3(TX, TY), 0, xsb_stream(stream)>>>(partials, P, C, (float)R, save_mean, save_invstd,
+                                                                              running_mean, running_var, eps, momentum);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }
