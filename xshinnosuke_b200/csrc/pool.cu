@@ -15,7 +15,8 @@
 namespace {
 
 // V = channels per thread (4 -> float4, 1 -> scalar). Grids are (ceil(W*CV/256), rows, N): no 64-bit div.
-template <int V>
+// KT > 0: window size known at compile time (unrolled taps, branch-free interior path)
+template <int V, int KT = 0>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W,
               int C, int OH, int OW, int k, int sh, int sw, int pad) {
@@ -31,8 +32,40 @@ maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, uint8_t* __res
     int arg[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { best[i] = 0.f; arg[i] = 0; }
+    if (KT > 0 && V == 4) {
+        constexpr int T = KT > 0 ? KT : 1;
+        float4 q[T * T];
+        const float4* img = reinterpret_cast<const float4*>(x) + (int64_t)n * H * W * CV;
+        if (h0 >= 0 && w0 >= 0 && h0 + T <= H && w0 + T <= W) {
+            // interior window (all but the first/last output row and column): no clamps, no padding selects --
+            // the kernel is issue-bound (368 instructions per output vector with them, 74 % SM busy in ncu)
+            const float4* p0 = img + (unsigned)((h0 * W + w0) * (int)CV + cv);
+            const unsigned row = (unsigned)W * CV;
+#pragma unroll
+            for (int ky = 0; ky < T; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < T; ++kx) q[ky * T + kx] = __ldg(p0 + (ky * row + kx * CV));
+        } else {
+#pragma unroll
+            for (int ky = 0; ky < T; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < T; ++kx) {
+                    const int h = h0 + ky, w = w0 + kx;
+                    q[ky * T + kx] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero padding takes part in the max
+                    if (h >= 0 && h < H && w >= 0 && w < W) q[ky * T + kx] = __ldg(img + (unsigned)((h * W + w) * (int)CV + cv));
+                }
+        }
+        best[0] = q[0].x; best[1 % V] = q[0].y; best[2 % V] = q[0].z; best[3 % V] = q[0].w;
+#pragma unroll
+        for (int t2 = 1; t2 < T * T; ++t2) {      // same tap order and tie rule (first maximum wins) as the generic loop
+            const float v4[4] = {q[t2].x, q[t2].y, q[t2].z, q[t2].w};
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (v4[i] > best[i]) { best[i] = v4[i]; arg[i] = t2; }
+        }
+    }
     bool first = true;
-    for (int ky = 0; ky < k; ++ky) {
+    for (int ky = 0; ky < ((KT > 0 && V == 4) ? 0 : k); ++ky) {
         const int h = h0 + ky;
         for (int kx = 0; kx < k; ++kx) {
             const int w = w0 + kx;
@@ -126,7 +159,7 @@ maxpool_bwd_k(const float* __restrict__ dy, const uint8_t* __restrict__ amax, fl
 // (rows 2i..2i+1, cols 2j..2j+1). Only the <= ceil((k+1)/2)^2 windows touching the quad are visited and each
 // window's (argmax, dy) is loaded ONCE for the four pixels instead of once per pixel (the generic kernel is
 // LSU-bound: ncu shows SM 77 % busy at 18 % DRAM).
-template <bool kAcc>
+template <bool kAcc, bool kSmall = false, bool kK3P1 = false>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_s2_k(const float* __restrict__ dy, const uint8_t* __restrict__ amax, float* dx, int N, int H, int W, int C,
                  int OH, int OW, int k, int pad) {
@@ -155,13 +188,24 @@ maxpool_bwd_s2_k(const float* __restrict__ dy, const uint8_t* __restrict__ amax,
         for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[a][b][i] = 0.f;
-    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
-        const int ry = h0 + pad - 2 * oh;          // window-relative row of pixel h0 (h0+1 -> ry+1)
-        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-            const int rx = w0 + pad - 2 * ow;
-            const int64_t o = (((int64_t)n * OH + oh) * OW + ow) * C + (int64_t)cv * 4;
-            const uchar4 am = __ldg(reinterpret_cast<const uchar4*>(amax + o));
+    // kSmall (k <= 3): at most 2 x 2 windows touch the quad -- fixed trip counts, so the (argmax, dy) loads of all four
+    // windows are in flight together; windows past oh_hi / ow_hi contribute a slot that matches nothing
+    const int noh = kSmall ? 2 : oh_hi - oh_lo + 1, now = kSmall ? 2 : ow_hi - ow_lo + 1;
+#pragma unroll
+    for (int dh = 0; dh < (kSmall ? 2 : noh); ++dh) {
+        const int oh = oh_lo + dh;
+        // window-relative row of pixel h0 (h0+1 -> ry+1); k = 3, pad = 1: oh_lo = qi, so ry is the constant 1 - 2*dh and
+        // 9 of the 16 (window, quad pixel) pairs remain
+        const int ry = kK3P1 ? 1 - 2 * dh : h0 + pad - 2 * oh;
+#pragma unroll
+        for (int dw = 0; dw < (kSmall ? 2 : now); ++dw) {
+            const int ow = ow_lo + dw;
+            const int rx = kK3P1 ? 1 - 2 * dw : w0 + pad - 2 * ow;
+            const bool live = oh <= oh_hi && ow <= ow_hi;
+            const int64_t o = (((int64_t)n * OH + (live ? oh : 0)) * OW + (live ? ow : 0)) * C + (int64_t)cv * 4;
+            uchar4 am = __ldg(reinterpret_cast<const uchar4*>(amax + o));
             const float4 g = __ldg(reinterpret_cast<const float4*>(dy + o));
+            if (!live) am = make_uchar4(255, 255, 255, 255);
             const int a4[4] = {am.x, am.y, am.z, am.w};
             const float g4[4] = {g.x, g.y, g.z, g.w};
             // window slot of each quad pixel (-1: the pixel is outside this window): compares, no divisions
@@ -170,8 +214,8 @@ maxpool_bwd_s2_k(const float* __restrict__ dy, const uint8_t* __restrict__ amax,
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    const int yy = ry + a, xx = rx + b;
-                    slot[a][b] = (yy >= 0 && yy < k && xx >= 0 && xx < k) ? yy * k + xx : -1;
+                    const int yy = ry + a, xx = rx + b, kk = kK3P1 ? 3 : k;
+                    slot[a][b] = (yy >= 0 && yy < kk && xx >= 0 && xx < kk) ? yy * kk + xx : -1;
                 }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -179,7 +223,7 @@ maxpool_bwd_s2_k(const float* __restrict__ dy, const uint8_t* __restrict__ amax,
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b)
-                        if (a4[i] == slot[a][b]) acc[a][b][i] += g4[i];
+                        if (slot[a][b] >= 0 && a4[i] == slot[a][b]) acc[a][b][i] += g4[i];
         }
     }
 #pragma unroll
@@ -392,7 +436,12 @@ int xsb_maxpool2d_fwd(const float* x, float* y, uint8_t* argmax, int N, int H, i
     XSB_CHECK_ARG(N <= 65535 && OH <= 65535, "maxpool: N/OH exceed grid limits");
     if (v4) {
         dim3 grid((unsigned)ceil_div64((int64_t)OW * (C / 4), 256), OH, N);
-        maxpool_fwd_k<4><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
+        if (k == 3)
+            maxpool_fwd_k<4, 3><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
+        else if (k == 2)
+            maxpool_fwd_k<4, 2><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
+        else
+            maxpool_fwd_k<4><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
     } else {
         dim3 grid((unsigned)ceil_div64((int64_t)OW * C, 256), OH, N);
         maxpool_fwd_k<1><<<grid, 256, 0, s>>>(x, y, argmax, N, H, W, C, OH, OW, k, sh, sw, pad);
@@ -434,7 +483,17 @@ int xsb_maxpool2d_bwd(const float* dy, const uint8_t* argmax, float* dx, int N, 
     XSB_CHECK_ARG(N <= 65535 && H <= 65535, "maxpool: N/H exceed grid limits");
     if (v4 && sh == 2 && sw == 2) {
         dim3 g((unsigned)ceil_div64((int64_t)((W + 1) / 2) * (C / 4), 256), (H + 1) / 2, N);
-        if (accumulate)
+        if (k == 3 && pad == 1) {
+            if (accumulate)
+                maxpool_bwd_s2_k<true, true, true><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, pad);
+            else
+                maxpool_bwd_s2_k<false, true, true><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, pad);
+        } else if (k <= 3) {
+            if (accumulate)
+                maxpool_bwd_s2_k<true, true><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, pad);
+            else
+                maxpool_bwd_s2_k<false, true><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, pad);
+        } else if (accumulate)
             maxpool_bwd_s2_k<true><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, pad);
         else
             maxpool_bwd_s2_k<false><<<g, 256, 0, s>>>(dy, argmax, dx, N, H, W, C, OH, OW, k, pad);
