@@ -51,10 +51,13 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint8_t* smem = align1024(smem_raw);
     uint8_t* sA = smem;
     uint8_t* sB = sA + p.sa_slots * p.a_slot_bytes;
-    uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + p.sb_slots * B_BYTES);
-    uint64_t* emptyA = fullA + MAXS;
-    uint64_t* fullB = emptyA + MAXS;
-    uint64_t* emptyB = fullB + 4;
+    // "full" barriers are per TILE (the dY load and every halo load of a tile arrive on the same one): the MMA thread
+    // consumes one try_wait per tile instead of one per load -- each costs ~160 clk of idle tensor pipe (tc_common.cuh).
+    // "empty" barriers stay per slot, so the producer refills slot by slot.
+    constexpr int TS = 4;
+    uint64_t* fullT = reinterpret_cast<uint64_t*>(sB + p.sb_slots * B_BYTES);
+    uint64_t* emptyA = fullT + TS;
+    uint64_t* emptyB = emptyA + MAXS;
     uint64_t* tmem_full = emptyB + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
@@ -75,14 +78,9 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         prefetch_tmap(&tmX);
         prefetch_tmap(&tmDy);
         prefetch_tmap(&tmW);
-        for (int i = 0; i < SA; ++i) {
-            mbar_init(&fullA[i], 1);
-            mbar_init(&emptyA[i], 1);
-        }
-        for (int i = 0; i < SB; ++i) {
-            mbar_init(&fullB[i], 1);
-            mbar_init(&emptyB[i], 1);
-        }
+        for (int i = 0; i < TS; ++i) mbar_init(&fullT[i], (uint32_t)n_loads + 1);   // one arrive.expect_tx per load
+        for (int i = 0; i < SA; ++i) mbar_init(&emptyA[i], 1);
+        for (int i = 0; i < SB; ++i) mbar_init(&emptyB[i], 1);
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
@@ -98,26 +96,28 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int a_box_bytes = ((WH_TH - 1) * SH + p.KH) * WH_TW * A_ROW_BYTES;   // bytes the halo load writes
 
     if (warp == 0) {
-        int sa = 0, sb = 0;
+        int sa = 0, sb = 0, ts = 0;
         uint32_t pha = 0, phb = 0;
         int n_img = t_begin / tiles_per_img, rem = t_begin - n_img * tiles_per_img;
         int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         for (int t = t_begin; t < t_end; ++t) {
             const int w0 = tw * WH_TW, h0 = th * WH_TH;
             mbar_wait(&emptyB[sb], phb ^ 1);
+            uint64_t* full = &fullT[ts];
+            ts = (ts + 1) & (TS - 1);
             if (elect_one()) {
-                mbar_expect_tx(&fullB[sb], B_BYTES);
+                mbar_expect_tx(full, B_BYTES);
 #pragma unroll
                 for (int b = 0; b < BN / 32; ++b)
-                    tma_load_4d(sB + sb * B_BYTES + b * B_BOX, &tmDy, &fullB[sb], oc0 + b * 32, w0, h0, n_img);
+                    tma_load_4d(sB + sb * B_BYTES + b * B_BOX, &tmDy, full, oc0 + b * 32, w0, h0, n_img);
             }
             if (++sb == SB) { sb = 0; phb ^= 1; }
             for (int cb = cb0; cb < cb0 + cbn; ++cb)
                 for (int kw = 0; kw < p.KWl; ++kw) {
                     mbar_wait(&emptyA[sa], pha ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(&fullA[sa], a_box_bytes);
-                        tma_load_4d(sA + sa * p.a_slot_bytes, &tmX, &fullA[sa], cb * 32, w0 + kw - p.pad_w,
+                        mbar_expect_tx(full, a_box_bytes);
+                        tma_load_4d(sA + sa * p.a_slot_bytes, &tmX, full, cb * 32, w0 + kw - p.pad_w,
                                     h0 * SH - p.pad_h, n_img);
                     }
                     if (++sa == SA) { sa = 0; pha ^= 1; }
@@ -132,14 +132,14 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t hi = desc_hi(512, kLayoutSW128Base32B);
         const uint32_t a_lo0 = desc_lo(smem_u32(sA), 1024), b_lo0 = desc_lo(smem_u32(sB), B_BOX);
         const uint32_t a_enc = (uint32_t)p.a_slot_bytes >> 4;
-        int sa = 0, sb = 0;
-        uint32_t pha = 0, phb = 0, a_lo = a_lo0, b_lo = b_lo0;
+        int sa = 0, sb = 0, ts = 0;
+        uint32_t pht = 0, a_lo = a_lo0, b_lo = b_lo0;
         uint32_t fresh = 0;     // 0 while this CTA's accumulators have not been written yet
         for (int t = t_begin; t < t_end; ++t) {
-            mbar_wait(&fullB[sb], phb);
+            mbar_wait(&fullT[ts], pht);
+            tc_fence_after();
+            if (++ts == TS) { ts = 0; pht ^= 1; }
             for (int a = 0; a < n_loads; ++a) {
-                mbar_wait(&fullA[sa], pha);
-                tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
@@ -154,11 +154,11 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 }
                 __syncwarp();
                 a_lo += a_enc;
-                if (++sa == SA) { sa = 0; pha ^= 1; a_lo = a_lo0; }
+                if (++sa == SA) { sa = 0; a_lo = a_lo0; }
             }
             fresh = 1;
             b_lo += (uint32_t)(B_BYTES >> 4);
-            if (++sb == SB) { sb = 0; phb ^= 1; b_lo = b_lo0; }
+            if (++sb == SB) { sb = 0; b_lo = b_lo0; }
         }
         if (elect_one()) umma_commit(tmem_full);
         __syncwarp();
@@ -249,7 +249,7 @@ static int wgrad_halo(const float* dy, const float* x, float* dw, const ConvGeom
     const int sb_slots = 3;
     int sa_slots = (227 * 1024 - 1024 - 512 - sb_slots * b_bytes) / a_slot_bytes;
     if (sa_slots > 16) sa_slots = 16;
-    if (sa_slots < 4) return XSB_ERR_UNSUPPORTED;
+    if (sa_slots < 4 || sa_slots < cbp * g.KW) return XSB_ERR_UNSUPPORTED;   // a tile's loads must all fit the ring (one full barrier per tile)
     CUtensorMap tx, tdy, tw;
     cuuint64_t xd[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
     cuuint64_t xs_[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.W * g.C * 4, (cuuint64_t)g.H * g.W * g.C * 4};
