@@ -106,6 +106,42 @@ def check_inplace_relu_layer(tol):
     close(res[1][0], np.maximum(pre, 0), tol, "inplace relu forward")
 
 
+def check_postponed_shortcut_dgrad(tol, c=4, oc=8, hw=9):
+    """A filter smaller than its stride (the ResNet 1x1/2 shortcut) has its dgrad postponed until dX is read
+    (DevArray.defer_add): alone it must still produce dX (zero-filled classes), and next to a 3x3/2 branch the 3x3 must
+    become the "=" writer and the 1x1 the "+=" one -- with the sum equal to the oracle's either way."""
+    from xshinnosuke_b200._lib import lib
+    rs = np.random.RandomState(11)
+    x = rs.randn(2, c, hw, hw).astype(np.float32)
+    w1 = (rs.randn(oc, c, 1, 1) * 0.3).astype(np.float32)
+    w3 = (rs.randn(oc, c, 3, 3) * 0.2).astype(np.float32)
+    x64 = x.astype(np.float64)
+    y1, col1 = X.conv2d_fwd(x64, w1.astype(np.float64), None, (2, 2), 0)
+    y3, col3 = X.conv2d_fwd(x64, w3.astype(np.float64), None, (2, 2), 1)
+    g = rs.randn(*y1.shape).astype(np.float32)
+    assert y1.shape == y3.shape
+    dx1 = X.conv2d_bwd(g.astype(np.float64), x.shape, w1.astype(np.float64), col1, (2, 2), 0)[0]
+    dx3 = X.conv2d_bwd(g.astype(np.float64), x.shape, w3.astype(np.float64), col3, (2, 2), 1)[0]
+    # alone
+    tx, tw = T(x, True), nn.Parameter(w1)
+    y = F.conv2d(tx, tw, None, (2, 2), 0)
+    y.backward(gradients=g)
+    close(tx.grad.eval, dx1, tol, "postponed 1x1/2 dgrad alone")
+    # both branches of a downsampling block: out = conv3x3/2(x) + conv1x1/2(x)
+    order = []
+    orig = lib.xsb_conv2d_dgrad
+    lib.xsb_conv2d_dgrad = lambda *a: (order.append((a[8], a[13])), orig(*a))[1]     # (KH, accumulate)
+    try:
+        tx, ta, tb = T(x, True), nn.Parameter(w3), nn.Parameter(w1)
+        out = F.add(F.conv2d(tx, ta, None, (2, 2), 1), F.conv2d(tx, tb, None, (2, 2), 0))
+        out.backward(gradients=g)
+        got = tx.grad.eval
+    finally:
+        lib.xsb_conv2d_dgrad = orig
+    assert order == [(3, 0), (1, 1)], order
+    close(got, dx1 + dx3, tol, "postponed 1x1/2 dgrad + 3x3/2 dgrad")
+
+
 def check_bn(golden, tol):
     for name in golden.names("bn"):
         c = golden.case(f"bn/{name}")

@@ -32,6 +32,10 @@ def test_relu_add(golden):
     S.check_inplace_relu_layer(TOL)
 
 
+def test_postponed_shortcut_dgrad():
+    S.check_postponed_shortcut_dgrad(TOL)
+
+
 def test_bn(golden):
     S.check_bn(golden, 1e-5)
     S.check_bn_eval(1e-6)

@@ -50,6 +50,18 @@ def test_relu_add(golden):
     S.check_inplace_relu_layer(TOL)
 
 
+def test_postponed_shortcut_dgrad():
+    """fp32 FFMA kernels, then the tcgen05 path (parity-class dgrad: the postponed 1x1/2 skips its zero-fill launches)."""
+    import parity_suite as S
+    import xshinnosuke_b200 as xs
+    S.check_postponed_shortcut_dgrad(TOL)
+    xs.set_math_mode("tf32")
+    try:
+        S.check_postponed_shortcut_dgrad(2e-3, c=64, oc=128, hw=16)
+    finally:
+        xs.set_math_mode("fp32")
+
+
 def test_bn(golden):
     import parity_suite as S
     S.check_bn(golden, TOL)
@@ -208,9 +220,9 @@ def test_conv_tf32_tensor_cores(n, c, h, oc, k, s, p, n_tc):
         assert X.rel_err(y.eval, yr) <= TOL_TC
         g = rs.randn(*yr.shape).astype(np.float32)
         y.backward(gradients=g)
-        s1 = _tc_stats()
         dx, dw, db = X.conv2d_bwd(g.astype(np.float64), x.shape, w.astype(np.float64), col, (s, s), p)
         assert X.rel_err(tx.grad.eval, dx) <= TOL_TC
+        s1 = _tc_stats()       # after dX was read: the dgrad of a filter smaller than its stride is postponed until then
         assert X.rel_err(tw.grad.eval, dw) <= TOL_TC
         assert X.rel_err(tb.grad.eval.reshape(-1), db) <= 1e-5
         assert s1[0] - s0[0] == n_tc and (s1[0] - s0[0]) + (s1[1] - s0[1]) == 3

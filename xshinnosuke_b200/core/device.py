@@ -126,8 +126,8 @@ class DevArray:
         # the mask on the fly, anyone else materialises a masked copy first)
         self.lazy_mask = None
         if _share is None:
-            # one cell shared by an array and all its views: [pending_zero, pending_op]
-            self._pz = [bool(pending_zero), None]
+            # one cell shared by an array and all its views: [pending_zero, pending_op, deferred_add]
+            self._pz = [bool(pending_zero), None, None]
             self._root = None
         else:
             self._pz = _share._pz
@@ -152,11 +152,29 @@ class DevArray:
     def pending_op(self, op):
         self._pz[1] = op
 
-    def flush(self):
+    def _run_pending_op(self):
         op = self._pz[1]
         if op is not None:
             self._pz[1] = None
             op(None)
+
+    def flush(self):
+        self._run_pending_op()
+        add = self._pz[2]
+        if add is not None:
+            self._pz[2] = None
+            add(self.take_acc())
+
+    # deferred_add: an accumulating kernel that is cheap as "+=" and expensive as the first "=" write of a gradient (a
+    # strided 1x1 dgrad reaches a quarter of the pixels: as "=" it must zero-fill the rest). It is postponed until the
+    # gradient is READ; a later writer then finds the array still logically zero, writes "=" without a read-modify-write,
+    # and the postponed kernel only adds where it has something to add. Called as add(accumulate_flag).
+    def defer_add(self, add):
+        """-> True if `add` was taken (the array is logically zero and holds no other postponed kernel)."""
+        if self._pz[0] and self._pz[2] is None and self.lazy_mask is None:
+            self._pz[2] = add
+            return True
+        return False
 
     def _materialize_zero(self):
         root = self if self._root is None else self._root
@@ -226,7 +244,7 @@ class DevArray:
         """Pointer for a kernel that will READ (or read-modify-write) the contents."""
         if self.lazy_mask is not None:
             self._materialize_mask()
-        if self._pz[1] is not None:
+        if self._pz[1] is not None or self._pz[2] is not None:
             self.flush()
         if self.pending_zero:
             self._materialize_zero()
@@ -239,6 +257,7 @@ class DevArray:
             self.lazy_mask = None
             self.buf = rt.empty(max(self.size, 1))
         self._pz[1] = None
+        self._pz[2] = None
         self.pending_zero = False
         return self.buf.data_ptr()
 
@@ -250,10 +269,10 @@ class DevArray:
         return 1
 
     def peek_ptr(self):
+        """Pointer for a kernel that accumulates (paired with take_acc): a postponed add stays postponed."""
         if self.lazy_mask is not None:
             self._materialize_mask()
-        if self._pz[1] is not None:
-            self.flush()
+        self._run_pending_op()
         return self.buf.data_ptr()
 
     @property

@@ -262,6 +262,7 @@ class Tensor(object):
             self._grad = Tensor(DevArray.empty(self._arr.shape, "float32", pending_zero=True))
         else:
             self._grad._arr.pending_zero = True
+            self._grad._arr._pz[2] = None      # a postponed add belongs to the gradient that is being discarded
 
     def sum(self, axis=None, keepdims=False):
         from ..nn import functional as F

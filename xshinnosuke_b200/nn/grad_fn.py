@@ -35,6 +35,7 @@ def _same_layout(src, like):
 def accumulate_into(t, src):
     """t.grad += src (src: DevArray of t's logical shape)."""
     g = _grad_arr(t)
+    src.flush()                          # (a postponed add would otherwise hide behind pending_zero)
     src = _same_layout(src, g)
     if g.take_acc():
         lib.xsb_axpy(g.peek_ptr(), src.ptr, 1.0, g.size, rt.stream())
@@ -212,9 +213,18 @@ def Conv2DBackward(outputs: Tensor):
     if inputs.requires_grad:
         g = _grad_arr(inputs)
         assert g.cl, "conv input gradient must be channels-last"
-        lib.xsb_conv2d_dgrad(dy.ptr, weight.arr.ptr, g.peek_ptr(), n, h, w, c, oc, kh, kw, sh, sw, pad, g.take_acc(),
-                             rt.math_mode, ws, wsn, st)
-        rt.launches += 1
+        dy_ptr, w_ptr = dy.ptr, weight.arr.ptr
+
+        def dgrad(acc, _keep=(dy.buf, weight.arr.buf)):      # the buffers stay alive while the kernel is postponed
+            lib.xsb_conv2d_dgrad(dy_ptr, w_ptr, g.peek_ptr(), n, h, w, c, oc, kh, kw, sh, sw, pad, acc, rt.math_mode, ws,
+                                 wsn, st)
+            rt.launches += 1
+
+        # a filter smaller than its stride (the 1x1/2 shortcut) reaches only some parity classes of dX: postponed until
+        # dX is read, so that the other branch of the block writes "=" and this one only adds (see DevArray.defer_add)
+        if (kh < sh or kw < sw) and g.defer_add(dgrad):
+            return
+        dgrad(g.take_acc())
 
 
 def Maxpool2DBackward(outputs: Tensor):
