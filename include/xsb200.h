@@ -123,7 +123,9 @@ int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* runni
 int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, float* ws, void* stream);
 
 /* ---- Dense. replaces xs/nn/functional.py:81-120 (mm / addmm) and xs/nn/grad_fn.py:73-99.
- *      C[M,N] (+)= op(A).op(B) (+ bias[N]); transA: A stored [K,M]; transB: B stored [N,K]. ---- */
+ *      C[M,N] (+)= op(A).op(B) (+ bias[N]); transA: A stored [K,M]; transB: B stored [N,K].
+ *      math_mode 1 (TF32): tcgen05 kernel when the row pitches of A, B and C are multiples of 16 bytes (the operands are
+ *      TMA sources as stored, W[in,out] is never transposed), the FP32 FFMA kernel otherwise (counted by xsb_tc_stats). ---- */
 int xsb_gemm(const float* A, const float* B, float* C, const float* bias /* nullable */, int M, int N, int K,
              int transA, int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, void* stream);
 
