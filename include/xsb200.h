@@ -150,7 +150,8 @@ int xsb_conv2d_wgrad(const float* dy, const float* x, float* dw, int N, int H, i
 /* counters (no reference counterpart): out2[0] = tcgen05 kernel launches so far, out2[1] = GEMM-shaped calls
  * that ran the fp32 FFMA kernel while in XSB_MATH_TF32 mode (shape outside the tensor-core envelope). */
 int xsb_tc_stats(uint64_t* out2);
-/* kernel-selection switch for tests / A-B measurements: key 0 = CTA-pair (tcgen05 cta_group::2) forward kernels (0/1) */
+/* kernel-selection switches for tests / A-B measurements: key 0 = CTA-pair (tcgen05 cta_group::2) forward kernels (0/1),
+ * key 1 = dgrad reads the forward filter as stored (MN-major operand) instead of a flipped / transposed copy (0/1) */
 int xsb_tc_config(int key, int value);
 
 /* ---- losses. replaces xs/nn/functional.py:984-1010 + xs/nn/td_functional.py:73-78,115-128 +

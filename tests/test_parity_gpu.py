@@ -332,6 +332,35 @@ def test_conv_bn_relu_fused_statistics_tf32(n, c, h, oc, k, s, p):
         xs.set_math_mode("fp32")
 
 
+@pytest.mark.parametrize("n,c,h,oc,k,s,p", [(4, 128, 14, 256, 3, 1, 1), (8, 64, 28, 128, 3, 2, 1), (8, 64, 28, 128, 1, 2, 0),
+                                          (4, 64, 15, 128, 3, 2, 1), (2, 64, 17, 128, 7, 2, 3), (2, 64, 8, 64, 2, 3, 0),
+                                          (24, 256, 7, 512, 3, 1, 1), (3, 96, 9, 64, 5, 1, 2)])
+def test_conv_dgrad_mn_major_filter_tf32(n, c, h, oc, k, s, p):
+    """dgrad with the forward filter read AS STORED (MN-major B operand, xsb_tc_config(1, 1); opt-in): stride-1 flipped
+    taps, every parity class of strided convolutions, column parts -- against the float64 oracle."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.nn import functional as F
+    xs.set_math_mode("tf32")
+    lib.xsb_tc_config(1, 1)
+    try:
+        rs = np.random.RandomState(5 * n + c + h)
+        x = rs.randn(n, c, h, h).astype(np.float32)
+        w = (rs.randn(oc, c, k, k) * 0.1).astype(np.float32)
+        tx, tw = xs.tensor(x, requires_grad=True), nn.Parameter(w)
+        y = F.conv2d(tx, tw, None, (s, s), p)
+        yr, col = X.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), None, (s, s), p)
+        g = rs.randn(*yr.shape).astype(np.float32)
+        y.backward(gradients=g)
+        dx = X.conv2d_bwd(g.astype(np.float64), x.shape, w.astype(np.float64), col, (s, s), p)[0]
+        assert X.rel_err(tx.grad.eval, dx) <= TOL_TC
+    finally:
+        lib.xsb_tc_config(1, 0)
+        xs.set_math_mode("fp32")
+
+
 @pytest.mark.parametrize("n,c,h,oc,k,s,p", [(4, 128, 14, 256, 3, 1, 1), (24, 256, 7, 512, 3, 1, 1), (100, 128, 14, 256, 3, 1, 1),
                                           (9, 64, 28, 128, 3, 1, 1), (5, 128, 9, 256, 1, 1, 0)])
 def test_conv_cta_pair_kernels_tf32(n, c, h, oc, k, s, p):

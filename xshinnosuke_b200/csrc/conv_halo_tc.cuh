@@ -322,6 +322,15 @@ static void halo_attach_stats(HaloParams& p, StatsReq* st) {
     }
 }
 
+// the shape envelope of halo_conv_s1 (no side effects): callers that must prepare the filter first ask this
+static bool halo_s1_accepts(int Cx, int OCx, int KH, int KW, int OH, int OW) {
+    if (Cx % 32 != 0 || (OCx != 64 && OCx != 128) || KH > HALO_MAX_KH) return false;
+    const int rows = HALO_TH - 1 + KH;
+    if (halo_stages(KH * KW * (Cx / 32), OCx, rows * 1024) == 0 || rows > 256) return false;
+    const int tiles_w = (OW + HALO_TW - 1) / HALO_TW, tiles_h = (OH + HALO_TH - 1) / HALO_TH;
+    return (int64_t)OH * OW * 10 >= (int64_t)tiles_w * tiles_h * HALO_TW * HALO_TH * 8;
+}
+
 // Generic stride-1 path: conv of channels-last in[N,H,W,Cx] with flt[OCx, KH*KW*Cx] -> out[N,OH,OW,OCx].
 // Returns XSB_ERR_UNSUPPORTED when the shape is outside the envelope (caller runs the im2col kernel).
 static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const float* flt, int OCx, int KH, int KW, int pad_h,

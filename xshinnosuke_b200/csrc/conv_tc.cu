@@ -45,6 +45,11 @@ struct FpropParams {
     // tile count does not fill the SMs split its N range into as many parts as there are idle SMs
     int m_tile0;
     short part_n0[16], part_cols[16];
+    // b_mn (dgrad): the B operand is read from the forward filter w[oc][kh][kw][c] AS STORED -- rows = oc (the K dimension
+    // of a dgrad), 32 contiguous c per box = an MN-major tile ({32 c, 32 oc} boxes, SWIZZLE_128B_BASE32B). The k-block of
+    // job tap (kh', kw') starts at float column b_col0 - kh'*b_step_h - kw'*b_step_w (the flipped / sub-sampled tap of the
+    // forward filter this parity class meets): no transposed copy of the filter is made.
+    int b_mn, b_col0, b_step_h, b_step_w;
 };
 
 // Non-strided epilogue shared by the 1-CTA and 2-CTA im2col kernels. Every MMA has completed, so the operand ring is
@@ -166,15 +171,24 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int cb = 0; cb < cblocks; ++cb, ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-                        tma_load_im2col(sA + s * A_BYTES, &tmA, &full[s], cb * 32, w0, h0, n_img, (uint16_t)kw, (uint16_t)kh);
-                        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * 32, n0);   // column (tap*C + cb*32) = kb*32
+                        if (p.b_mn) {
+                            const int col = p.b_col0 - kh * p.b_step_h - kw * p.b_step_w + n0;
+                            mbar_expect_tx(&full[s], A_BYTES + (ncols >> 5) * 4096);
+                            tma_load_im2col(sA + s * A_BYTES, &tmA, &full[s], cb * 32, w0, h0, n_img, (uint16_t)kw, (uint16_t)kh);
+                            for (int b = 0; b < (ncols >> 5); ++b)
+                                tma_load_2d(sB + s * B_BYTES + b * 4096, &tmB, &full[s], col + b * 32, cb * 32);
+                        } else {
+                            mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                            tma_load_im2col(sA + s * A_BYTES, &tmA, &full[s], cb * 32, w0, h0, n_img, (uint16_t)kw, (uint16_t)kh);
+                            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * 32, n0);   // column (tap*C + cb*32) = kb*32
+                        }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
     } else if (warp == 1) {
-        const uint32_t idesc = make_idesc(ncols, 0, 0);   // N = this CTA's column count (the B tile holds BN >= N rows)
+        const uint32_t idesc = make_idesc(ncols, 0, p.b_mn ? 1 : 0);   // N = this CTA's column count (the B tile holds BN >= N rows)
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        const uint32_t b_kstep = p.b_mn ? 64u : 2u;     // K = 8 advance: 8 rows of 128 B (MN-major) / 32 B (K-major)
         int s = 0;
         uint32_t ph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -182,10 +196,11 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t da = make_desc(a_base + s * A_BYTES, 16, 1024);
-                const uint64_t db = make_desc(b_base + s * B_BYTES, 16, 1024);
+                const uint64_t db = p.b_mn ? make_desc(b_base + s * B_BYTES, 4096, 512, kLayoutSW128Base32B)
+                                           : make_desc(b_base + s * B_BYTES, 16, 1024);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 = 32 B) per 128-byte row
-                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * b_kstep), idesc, (kb | k) != 0);
                 umma_commit(&empty[s]);
             }
             __syncwarp();
@@ -741,6 +756,7 @@ static bool make_map_im2col(CUtensorMap* m, const float* base, int N, int H, int
 
 static uint64_t g_tc_launches = 0, g_ffma_fallbacks = 0;
 static int g_pair_mode = -1;     // -1: read XSB_TC_PAIR on first use
+static int g_dgrad_mn = -1;      // -1: read XSB_TC_DGRAD_MN on first use
 
 // XSB_TC_OCC=1|2 (env, read once): CTAs per SM for the fprop kernel. 2 (default) halves the smem ring of each CTA
 // so that one CTA's epilogue overlaps the other's mainloop.
@@ -792,6 +808,8 @@ struct FpropJob {
     int o_strided, o_H, o_W, o_sh, o_sw, o_a, o_b;
     float* stats;          // BatchNorm partials (null = off)
     int* n_partials;       // host: receives the number of partials written
+    // b_mn: `flt` is the FORWARD filter [b_rows = oc, b_cols = KH*KW*C floats] read as an MN-major B operand (see FpropParams)
+    int b_mn = 0, b_rows = 0, b_cols = 0, b_col0 = 0, b_step_h = 0, b_step_w = 0;
 };
 
 static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
@@ -804,14 +822,16 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
     const int lo_h = -j.pad_h, lo_w = -j.pad_w;
     const int up_h = lo_h + (j.OH - 1) * j.sh - (j.H - 1), up_w = lo_w + (j.OW - 1) * j.sw - (j.W - 1);
     CUtensorMap ta, tb;
-    if (!make_map_im2col(&ta, j.in, j.N, j.H, j.W, j.Cx, j.sh, j.sw, lo_h, lo_w, up_h, up_w, BM) ||
-        !make_map_2d(&tb, j.flt, (uint64_t)j.OCx, (uint64_t)j.KH * j.KW * j.Cx, (uint32_t)BN)) {
+    const bool ok_b = j.b_mn ? make_map_2d(&tb, j.flt, (uint64_t)j.b_rows, (uint64_t)j.b_cols, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                             : make_map_2d(&tb, j.flt, (uint64_t)j.OCx, (uint64_t)j.KH * j.KW * j.Cx, (uint32_t)BN);
+    if (!make_map_im2col(&ta, j.in, j.N, j.H, j.W, j.Cx, j.sh, j.sw, lo_h, lo_w, up_h, up_w, BM) || !ok_b) {
         xsb_set_error("cuTensorMapEncode failed (fprop N=%d H=%d W=%d C=%d OC=%d k=%dx%d s=%d p=%d,%d)", j.N, j.H, j.W,
                       j.Cx, j.OCx, j.KH, j.KW, j.sh, j.pad_h, j.pad_w);
         return XSB_ERR_CUDA;
     }
     FpropParams p{j.out, j.bias, j.N * j.OH * j.OW, j.OCx, j.Cx, j.KH, j.KW, j.OH, j.OW, j.sh, j.sw, j.pad_h, j.pad_w,
                   j.accumulate, j.o_strided, j.o_H, j.o_W, j.o_sh, j.o_sw, j.o_a, j.o_b, j.o_strided ? nullptr : j.stats};
+    p.b_mn = j.b_mn; p.b_col0 = j.b_col0; p.b_step_h = j.b_step_h; p.b_step_w = j.b_step_w;
     const int m_tiles = (p.M + BM - 1) / BM;
     if (p.stats && j.n_partials) *j.n_partials = m_tiles;
     CUtensorMap to = ta;   // unused by strided-destination launches
@@ -832,8 +852,8 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
         }
         p.m_tile0 = m_tile0;
         const int bn = widest <= 64 ? 64 : widest <= 96 ? 96 : widest <= 128 ? 128 : widest <= 192 ? 192 : 256;
-        CUtensorMap tbp;
-        if (!make_map_2d(&tbp, j.flt, (uint64_t)j.OCx, (uint64_t)j.KH * j.KW * j.Cx, (uint32_t)bn)) {
+        CUtensorMap tbp = tb;     // (the MN-major filter map does not depend on the tile width)
+        if (!j.b_mn && !make_map_2d(&tbp, j.flt, (uint64_t)j.OCx, (uint64_t)j.KH * j.KW * j.Cx, (uint32_t)bn)) {
             xsb_set_error("cuTensorMapEncode failed (fprop filter box %d)", bn);
             return XSB_ERR_CUDA;
         }
@@ -874,7 +894,7 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
         const char* e = getenv("XSB_TC_PAIR");
         g_pair_mode = e ? atoi(e) : 0;
     }
-    if (g_pair_mode > 0 && !j.o_strided && BN >= 128 && m_tiles >= 2) {
+    if (g_pair_mode > 0 && !j.o_strided && !j.b_mn && BN >= 128 && m_tiles >= 2) {
         const int SP = S / 2, pairs = (m_tiles + 1) / 2, n_tiles = j.OCx / BN;
         const int64_t units = (int64_t)pairs * n_tiles;
         int max_parts = j.OCx / 32;
@@ -1185,10 +1205,22 @@ static int tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvG
             tp.pos[t] = ua * cw[b].T + ub;
             tp.ntaps[t] = ch[a].T * cw[b].T;
         }
-    dim3 grid((g.C + 31) / 32, (g.OC + 31) / 32, taps), block(32, 8);
-    gather_subfilters_k<<<grid, block, 0, s>>>(w, ws, g.OC, taps, g.C, tp);
-    XSB_LAUNCH_CHECK();
     const int strided = (g.sh != 1 || g.sw != 1) ? 1 : 0;
+    // The im2col kernel can read the forward filter as stored (MN-major B operand, FpropParams::b_mn) instead of the
+    // flipped / transposed copy gather_subfilters_k makes. Measured on R224 (same box, alternating runs): 5.912 ms/step
+    // against 5.882 with the copy -- N/32 boxes of 4 KB per k-block cost more TMA issue slots than 10 gathers of ~5 us
+    // save -- so it is opt-in (XSB_TC_DGRAD_MN=1 / xsb_tc_config(1, 1)), parity-tested, and the copy stays the default.
+    if (g_dgrad_mn < 0) {
+        const char* e = getenv("XSB_TC_DGRAD_MN");
+        g_dgrad_mn = (e && e[0] == '1') ? 1 : 0;
+    }
+    const bool halo_first = !strided && halo_enabled() && halo_s1_accepts(g.OC, g.C, g.KH, g.KW, g.H, g.W);
+    const bool gathered = halo_first || !g_dgrad_mn;
+    if (gathered) {
+        dim3 grid((g.C + 31) / 32, (g.OC + 31) / 32, taps), block(32, 8);
+        gather_subfilters_k<<<grid, block, 0, s>>>(w, ws, g.OC, taps, g.C, tp);
+        XSB_LAUNCH_CHECK();
+    }
     for (int a = 0; a < g.sh; ++a)
         for (int b = 0; b < g.sw; ++b) {
             const int Ha = ch[a].n, Wb = cw[b].n;
@@ -1202,13 +1234,23 @@ static int tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvG
                 }
                 continue;
             }
-            if (!strided && halo_enabled()) {
+            if (halo_first) {
                 const int rc = halo_conv_s1(dy, g.N, g.OH, g.OW, g.OC, ws, g.C, g.KH, g.KW, ch[0].padp, cw[0].padp, g.H, g.W,
                                             nullptr, dx, accumulate, s);
                 if (rc != XSB_ERR_UNSUPPORTED) return rc;
             }
-            const FpropJob j{dy, g.N, g.OH, g.OW, g.OC, ws + cls_base[a][b], g.C, ch[a].T, cw[b].T, 1, 1, ch[a].padp,
-                             cw[b].padp, Ha, Wb, nullptr, dx, accumulate, strided, g.H, g.W, g.sh, g.sw, a, b, nullptr, nullptr};
+            FpropJob j{dy, g.N, g.OH, g.OW, g.OC, ws + cls_base[a][b], g.C, ch[a].T, cw[b].T, 1, 1, ch[a].padp,
+                       cw[b].padp, Ha, Wb, nullptr, dx, accumulate, strided, g.H, g.W, g.sh, g.sw, a, b, nullptr, nullptr};
+            if (!gathered) {
+                // job tap (ua, ub) of this class = forward tap (r_a + sh*(T_a-1-ua), r_b + sw*(T_b-1-ub))
+                j.flt = w;
+                j.b_mn = 1;
+                j.b_rows = g.OC;
+                j.b_cols = taps * g.C;
+                j.b_col0 = ((ch[a].r + g.sh * (ch[a].T - 1)) * g.KW + (cw[b].r + g.sw * (cw[b].T - 1))) * g.C;
+                j.b_step_h = g.sh * g.KW * g.C;
+                j.b_step_w = g.sw * g.C;
+            }
             const int rc = fprop_dispatch(j, s);
             if (rc != XSB_OK) return rc;
         }
@@ -1271,10 +1313,15 @@ int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom
 }
 
 extern "C" {
-// kernel-selection switches (tests / A-B measurements): key 0 = CTA-pair (cta_group::2) forward kernels on/off
+// kernel-selection switches (tests / A-B measurements): key 0 = CTA-pair (cta_group::2) forward kernels on/off,
+// key 1 = dgrad reads the forward filter as an MN-major operand (no transposed copy) on/off
 int xsb_tc_config(int key, int value) {
     if (key == 0) {
         tc::g_pair_mode = value ? 1 : 0;
+        return XSB_OK;
+    }
+    if (key == 1) {
+        tc::g_dgrad_mn = value ? 1 : 0;
         return XSB_OK;
     }
     xsb_set_error("xsb_tc_config: unknown key %d", key);
