@@ -12,8 +12,8 @@
 //    one load feeds KH k-blocks (KH x less A traffic than im2col);
 //  * accumulators are double-buffered in TMEM: the 4 epilogue warps drain tile i while tile i+1 is multiplied.
 //
-// 64->64 3x3: 6 loads (2 channel blocks x 3 filter columns, the column shift is the TMA start coordinate, zero padding
-// by out-of-bounds fill) x 3 k-blocks. Stem (C <= 4): the image is pre-padded to 4 channels (stem_pad_c4_k) and the
+// 64->64 3x3: 2 loads per tile (one {32 ch, 10 w, 18 rows} halo block per channel block, zero padding by out-of-bounds
+// fill) x 9 k-blocks: filter column kw is the view shifted by kw*128 B (see HaloParams::kwd). Stem (C <= 4): the image is pre-padded to 4 channels (stem_pad_c4_k) and the
 // tensor map walks OVERLAPPING rows {32 floats = 8 pixels x 4 ch, stride sw pixels}: 1 load x KH k-blocks.
 #pragma once
 #include "tc_common.cuh"
@@ -36,6 +36,12 @@ struct HaloParams {
     int h_off;               // TMA row coordinate of output row 0, filter row 0 (= -pad, or 0 for a pre-padded image)
     int stage_bytes, n_stages, n_btiles;
     int accumulate;
+    // kwd > 0: ONE halo load {32 ch, 8 + KW - 1 = kwd columns, rows} per channel block feeds all KW filter columns: the
+    // view of (kh, kw) starts at stage + (kh*kwd + kw)*128 B with SBO = kwd*128 B -- neither is a multiple of the 1024-byte
+    // swizzle period. Measured (parity suite): the MMA unit derives the SWIZZLE_128B phase of every operand row from its
+    // absolute shared-memory address, exactly as TMA wrote it, so any 128-byte-aligned start / SBO is a valid view.
+    // KW x less A traffic than one load per filter column (XSB_TC_HALO_KWD=0 restores that form for A/B runs).
+    int kwd, tx_bytes;
     // BatchNorm partial statistics (null = off): stats[(blockIdx.x*3 + {0:n, 1:mean, 2:M2}) * ldo + channel]
     float* stats;
 };
@@ -101,11 +107,12 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int step_img = gridDim.x / tiles_per_img, step_rem = gridDim.x - step_img * tiles_per_img;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int w0 = tw * HALO_TW - p.pad_w, h0 = th * HALO_TH * p.sh + p.h_off;
+            const int n_kw_loads = p.kwd ? 1 : p.KWl;
             for (int cb = 0; cb < p.cblocks; ++cb)
-                for (int kw = 0; kw < p.KWl; ++kw) {
+                for (int kw = 0; kw < n_kw_loads; ++kw) {
                     mbar_wait(&empty[s], ph ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(&full[s], p.stage_bytes);
+                        mbar_expect_tx(&full[s], p.tx_bytes);
                         tma_load_4d(sA + s * p.stage_bytes, &tmA, &full[s], cb * 32, w0 + kw, h0, n_img);
                     }
                     if (++s == S) { s = 0; ph ^= 1; }
@@ -133,6 +140,28 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
             uint32_t fresh = 0;   // 0 for the first MMA of the tile (overwrite the accumulator), 1 afterwards
+            if (p.kwd) {
+                const uint32_t a_hi_d = desc_hi((uint32_t)p.kwd * 128, kLayoutSW128);
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        uint32_t b_lo_l = b_lo0 + (uint32_t)cb * B_ENC;
+                        for (int kw = 0; kw < p.KWl; ++kw, b_lo_l += (uint32_t)p.cblocks * B_ENC)
+                            for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_tf32_split(tacc, a_lo_s + (uint32_t)((kh * p.kwd + kw) * 8 + k * 2), a_hi_d,
+                                                    b_lo_l + (uint32_t)kh * bt_kh_enc + (uint32_t)(k * 2), b_hi, idesc,
+                                                    (kw | kh | k) ? 1u : fresh);
+                        umma_commit(&empty[s]);
+                    }
+                    __syncwarp();
+                    fresh = 1;
+                    a_lo_s += stage_enc;
+                    if (++s == S) { s = 0; ph ^= 1; a_lo_s = a_lo0; }
+                }
+            } else
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 uint32_t b_lo_l = b_lo0 + (uint32_t)cb * B_ENC;
                 for (int kw = 0; kw < p.KWl; ++kw, b_lo_l += (uint32_t)p.cblocks * B_ENC) {
@@ -326,7 +355,8 @@ static void halo_attach_stats(HaloParams& p, StatsReq* st) {
 static bool halo_s1_accepts(int Cx, int OCx, int KH, int KW, int OH, int OW) {
     if (Cx % 32 != 0 || (OCx != 64 && OCx != 128) || KH > HALO_MAX_KH) return false;
     const int rows = HALO_TH - 1 + KH;
-    if (halo_stages(KH * KW * (Cx / 32), OCx, rows * 1024) == 0 || rows > 256) return false;
+    const int stage = (rows * (HALO_TW + KW - 1) * A_ROW_BYTES + 1023) & ~1023;     // (the kwd form: the larger stage)
+    if (halo_stages(KH * KW * (Cx / 32), OCx, stage) == 0 || rows > 256) return false;
     const int tiles_w = (OW + HALO_TW - 1) / HALO_TW, tiles_h = (OH + HALO_TH - 1) / HALO_TH;
     return (int64_t)OH * OW * 10 >= (int64_t)tiles_w * tiles_h * HALO_TW * HALO_TH * 8;
 }
@@ -340,7 +370,10 @@ static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const floa
     if (Cx % 32 != 0 || (OCx != 64 && OCx != 128) || KH > HALO_MAX_KH) return XSB_ERR_UNSUPPORTED;
     const int n_btiles = KH * KW * cblocks;
     const int rows = HALO_TH - 1 + KH;
-    const int stage_bytes = rows * 1024;
+    static const int kwd_on = [] { const char* e = getenv("XSB_TC_HALO_KWD"); return (e && e[0] == '0') ? 0 : 1; }();
+    const int kwd = (kwd_on && KW > 1) ? HALO_TW + KW - 1 : 0;
+    const int tx_bytes = rows * (kwd ? kwd : HALO_TW) * A_ROW_BYTES;
+    const int stage_bytes = (tx_bytes + 1023) & ~1023;
     const int stages = halo_stages(n_btiles, OCx, stage_bytes);
     if (stages == 0 || rows > 256) return XSB_ERR_UNSUPPORTED;
     // small images waste most of an 8x16 tile: leave them to the im2col kernel
@@ -350,7 +383,7 @@ static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const floa
     CUtensorMap ta, tb;
     cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)Cx * 4, (cuuint64_t)W * Cx * 4, (cuuint64_t)H * W * Cx * 4};
-    cuuint32_t box[4] = {32, HALO_TW, (cuuint32_t)rows, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)(kwd ? kwd : HALO_TW), (cuuint32_t)rows, 1};
     if (!make_map_tiled(&ta, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !make_map_2d(&tb, flt, (uint64_t)OCx, (uint64_t)KH * KW * Cx, (uint32_t)OCx))
         return XSB_ERR_UNSUPPORTED;
@@ -360,6 +393,7 @@ static int halo_conv_s1(const float* in, int N, int H, int W, int Cx, const floa
     p.cblocks = cblocks; p.KWl = KW; p.KH = KH; p.sh = 1; p.pad_w = pad_w; p.bt_kh_stride = KW * cblocks;
     p.h_off = -pad_h;
     p.stage_bytes = stage_bytes; p.n_stages = stages; p.n_btiles = n_btiles; p.accumulate = accumulate;
+    p.kwd = kwd; p.tx_bytes = tx_bytes;
     halo_attach_stats(p, st);
     return OCx == 64 ? launch_halo<64>(ta, tb, p, s) : launch_halo<128>(ta, tb, p, s);
 }

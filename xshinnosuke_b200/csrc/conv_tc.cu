@@ -1054,7 +1054,7 @@ static int stem_fwd(const float* x, const float* w, const float* bias, float* y,
     p.tiles_w = (g.OW + HALO_TW - 1) / HALO_TW; p.tiles_h = (g.OH + HALO_TH - 1) / HALO_TH;
     p.n_tiles = g.N * p.tiles_w * p.tiles_h;
     p.cblocks = 1; p.KWl = 1; p.KH = g.KH; p.sh = g.sh; p.pad_w = 0; p.bt_kh_stride = 1; p.h_off = 0;
-    p.stage_bytes = rows * 1024; p.n_stages = stages; p.n_btiles = g.KH; p.accumulate = 0;
+    p.stage_bytes = rows * 1024; p.tx_bytes = rows * 1024; p.n_stages = stages; p.n_btiles = g.KH; p.accumulate = 0;
     halo_attach_stats(p, st);
     return g.OC == 64 ? launch_halo<64>(ta, tb, p, s) : launch_halo<128>(ta, tb, p, s);
 }
