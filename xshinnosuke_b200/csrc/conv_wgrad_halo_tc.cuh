@@ -36,6 +36,10 @@ struct WgradHaloParams {
     int stem;             // epilogue: rows are (kh, kw*4 + c) -> scattered red.add into dw_raw[oc][kh][kw][c]
     int KW_real, C_real;
     float* dw_raw;
+    // kwd > 0: one halo load {32 ch, kwd = 8 + KW - 1 columns, rows} per channel block feeds all KW filter columns -- the
+    // operand view of column kw starts kw*128 B into the block, rows are kwd*128 B apart (LBO). As in conv_halo_tc.cuh
+    // the MMA unit takes the swizzle phase (here SWIZZLE_128B_BASE32B) from the absolute shared-memory address.
+    int kwd;
 };
 
 // SH = conv stride along h, G = accumulators (groups of four filter rows) per load: compile-time so that the issue
@@ -68,8 +72,10 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int cb0 = (pass / p.n_oc_tiles) * p.cbp;
     int cbn = p.cblocks - cb0;                 // channel blocks of this pass
     if (cbn > p.cbp) cbn = p.cbp;
-    const int n_loads = cbn * p.KWl;
-    const int n_acc = n_loads * G;
+    const int kw_per_load = p.kwd ? p.KWl : 1;                  // filter columns served by one halo load
+    const int n_loads = cbn * (p.kwd ? 1 : p.KWl);              // TMA halo loads per tile
+    const int n_acc = n_loads * kw_per_load * G;
+    const int wpx = p.kwd ? p.kwd : WH_TW;                      // pixels per halo row
     // contiguous tile range of this CTA
     const int t_begin = (int)((int64_t)blockIdx.x * p.n_tiles / gridDim.x);
     const int t_end = (int)((int64_t)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
@@ -93,7 +99,7 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
-    const int a_box_bytes = ((WH_TH - 1) * SH + p.KH) * WH_TW * A_ROW_BYTES;   // bytes the halo load writes
+    const int a_box_bytes = ((WH_TH - 1) * SH + p.KH) * wpx * A_ROW_BYTES;     // bytes the halo load writes
 
     if (warp == 0) {
         int sa = 0, sb = 0, ts = 0;
@@ -113,7 +119,7 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
             if (++sb == SB) { sb = 0; phb ^= 1; }
             for (int cb = cb0; cb < cb0 + cbn; ++cb)
-                for (int kw = 0; kw < p.KWl; ++kw) {
+                for (int kw = 0; kw < (p.kwd ? 1 : p.KWl); ++kw) {
                     mbar_wait(&emptyA[sa], pha ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(full, a_box_bytes);
@@ -130,7 +136,8 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc(BN, 1, 1);
         const uint32_t hi = desc_hi(512, kLayoutSW128Base32B);
-        const uint32_t a_lo0 = desc_lo(smem_u32(sA), 1024), b_lo0 = desc_lo(smem_u32(sB), B_BOX);
+        const uint32_t a_lo0 = desc_lo(smem_u32(sA), (uint32_t)wpx * 128), b_lo0 = desc_lo(smem_u32(sB), B_BOX);
+        const uint32_t row_enc = (uint32_t)wpx * 8;     // one halo row in descriptor units (16 B)
         const uint32_t a_enc = (uint32_t)p.a_slot_bytes >> 4;
         int sa = 0, sb = 0, ts = 0;
         uint32_t pht = 0, a_lo = a_lo0, b_lo = b_lo0;
@@ -141,13 +148,15 @@ conv_wgrad_halo_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (++ts == TS) { ts = 0; pht ^= 1; }
             for (int a = 0; a < n_loads; ++a) {
                 if (elect_one()) {
+                    for (int kw = 0; kw < kw_per_load; ++kw) {
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const uint32_t tacc = tmem_base + (uint32_t)((a * G + g) * BN);
+                        for (int g = 0; g < G; ++g) {
+                            const uint32_t tacc = tmem_base + (uint32_t)(((a * kw_per_load + kw) * G + g) * BN);
 #pragma unroll
-                        for (int r = 0; r < WH_TH; ++r)   // tile row r: K = 8 pixels = 1024 bytes of both operands
-                            umma_tf32_split(tacc, a_lo + (uint32_t)((g * 4 + r * SH) * 64), hi, b_lo + (uint32_t)(r * 64), hi,
-                                            idesc, r ? 1u : fresh);
+                            for (int r = 0; r < WH_TH; ++r)   // tile row r: K = 8 pixels = 1024 bytes of both operands
+                                umma_tf32_split(tacc, a_lo + (uint32_t)(g * 4 + r * SH) * row_enc + (uint32_t)(kw * 8), hi,
+                                                b_lo + (uint32_t)(r * 64), hi, idesc, r ? 1u : fresh);
+                        }
                     }
                     umma_commit(&emptyA[sa]);
                     if (a == n_loads - 1) umma_commit(&emptyB[sb]);
@@ -244,16 +253,20 @@ static int wgrad_halo(const float* dy, const float* x, float* dw, const ConvGeom
     if (ctas < 1) return XSB_ERR_UNSUPPORTED;
     if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
     const int a_rows = WH_TH + g.KH - 1;
-    const int a_slot_bytes = (WH_TH + 4) * WH_TW * A_ROW_BYTES;   // room for the rows the (unused) M blocks kh < 4 touch
+    static const int kwd_on = [] { const char* e = getenv("XSB_TC_WGRAD_KWD"); return (e && e[0] == '0') ? 0 : 1; }();
+    const int kwd = (kwd_on && g.KW > 1) ? WH_TW + g.KW - 1 : 0;
+    const int wpx = kwd ? kwd : WH_TW;
+    // room for the rows the (unused) M blocks kh < 4 touch
+    const int a_slot_bytes = ((WH_TH + 4) * wpx * A_ROW_BYTES + 1023) & ~1023;
     const int b_bytes = (BN / 32) * WH_TW * WH_TH * A_ROW_BYTES;
     const int sb_slots = 3;
     int sa_slots = (227 * 1024 - 1024 - 512 - sb_slots * b_bytes) / a_slot_bytes;
     if (sa_slots > 16) sa_slots = 16;
-    if (sa_slots < 4 || sa_slots < cbp * g.KW) return XSB_ERR_UNSUPPORTED;   // a tile's loads must all fit the ring (one full barrier per tile)
+    if (sa_slots < 4 || sa_slots < cbp * (kwd ? 1 : g.KW)) return XSB_ERR_UNSUPPORTED;   // a tile's loads must all fit the ring (one full barrier per tile)
     CUtensorMap tx, tdy, tw;
     cuuint64_t xd[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
     cuuint64_t xs_[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.W * g.C * 4, (cuuint64_t)g.H * g.W * g.C * 4};
-    cuuint32_t xb[4] = {32, WH_TW, (cuuint32_t)a_rows, 1};
+    cuuint32_t xb[4] = {32, (cuuint32_t)wpx, (cuuint32_t)a_rows, 1};
     cuuint64_t dd[4] = {(cuuint64_t)g.OC, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
     cuuint64_t ds[3] = {(cuuint64_t)g.OC * 4, (cuuint64_t)g.OW * g.OC * 4, (cuuint64_t)g.OH * g.OW * g.OC * 4};
     cuuint32_t db[4] = {32, WH_TW, WH_TH, 1};
@@ -262,7 +275,7 @@ static int wgrad_halo(const float* dy, const float* x, float* dw, const ConvGeom
         !make_map_2d(&tw, dw, (uint64_t)g.OC, (uint64_t)g.KH * g.KW * g.C, 32, CU_TENSOR_MAP_SWIZZLE_NONE))
         return XSB_ERR_UNSUPPORTED;
     WgradHaloParams p{g.N, g.OH, g.OW, tiles_w, tiles_h, n_tiles, g.KH, g.KW, g.pad, cblocks, cbp, n_oc_tiles,
-                      sa_slots, sb_slots, a_slot_bytes, g.C, 1, 1, g.KW, g.pad, g.pad, 0, g.KW, g.C, dw};
+                      sa_slots, sb_slots, a_slot_bytes, g.C, 1, 1, g.KW, g.pad, g.pad, 0, g.KW, g.C, dw, kwd};
     const int smem = 1024 + sa_slots * a_slot_bytes + sb_slots * b_bytes + 512;
     dim3 grid(ctas, passes);
     if (BN == 64) {
@@ -318,7 +331,7 @@ static int wgrad_halo_stem(const float* dy, const float* xp, float* dw, const Co
         return XSB_ERR_UNSUPPORTED;
     tw = tdy;   // unused by the stem epilogue
     WgradHaloParams p{g.N, g.OH, g.OW, tiles_w, tiles_h, n_tiles, g.KH, 1, 0, 1, 1, 1,
-                      sa_slots, sb_slots, a_slot_bytes, 4, g.sh, groups, 1, 0, 0, 1, g.KW, g.C, dw};
+                      sa_slots, sb_slots, a_slot_bytes, 4, g.sh, groups, 1, 0, 0, 1, g.KW, g.C, dw, 0};
     const int smem = 1024 + sa_slots * a_slot_bytes + sb_slots * b_bytes + 512;
     auto go = [&](auto kern) -> int {
         XSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
