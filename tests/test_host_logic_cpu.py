@@ -36,6 +36,33 @@ def test_postponed_shortcut_dgrad():
     S.check_postponed_shortcut_dgrad(TOL)
 
 
+def test_postponed_add_is_dropped_by_zero_grad_and_flushed_by_clone():
+    """DevArray.defer_add bookkeeping: a parked kernel belongs to the gradient it was parked on -- zero_grad discards it,
+    clone / to_numpy run it first, and a second parked kernel is refused (it runs immediately as the "+=" writer)."""
+    import numpy as np
+    from xshinnosuke_b200.core.device import DevArray
+    ran = []
+    a = DevArray.empty((2, 3), pending_zero=True)
+    a.cl = False
+    assert a.defer_add(lambda acc: ran.append(("first", acc)))
+    assert not a.defer_add(lambda acc: ran.append(("second", acc)))      # one parked kernel at most
+    assert a.take_acc() == 0 and not ran                                  # a writer in between: "=", nothing flushed
+    a.buf.zero_()
+    b = a.clone()                                                         # a reader: the parked kernel runs as "+="
+    assert ran == [("first", 1)] and not b.pending_zero
+    c = DevArray.empty((4,), pending_zero=True)
+    c.cl = False
+    assert c.defer_add(lambda acc: ran.append(("third", acc)))
+    assert np.array_equal(c.to_numpy(), np.zeros(4, dtype=np.float32)) or ran[-1] == ("third", 0)
+    assert ran[-1] == ("third", 0)                                        # alone: it is the first writer after all
+    import xshinnosuke_b200 as xs
+    t = xs.tensor(np.ones((2, 2), dtype=np.float32), requires_grad=True)
+    t.zero_grad()
+    assert t.grad.arr.defer_add(lambda acc: ran.append(("stale", acc)))
+    t.zero_grad()                                                         # discards the parked kernel
+    assert np.array_equal(t.grad.eval, np.zeros((2, 2), dtype=np.float32)) and ran[-1] != ("stale", 0)
+
+
 def test_bn(golden):
     S.check_bn(golden, 1e-5)
     S.check_bn_eval(1e-6)
