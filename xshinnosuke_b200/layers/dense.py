@@ -1,68 +1,47 @@
-"""Dense and Flatten layers (mirror of xs/layers/linear.py:5-76)."""
+"""Dense and Flatten layers (API of xs/layers/linear.py:5-76; ops: nn.functional.addmm / mm / flatten)."""
 from functools import reduce
+from operator import mul
 
-from ..core.tensor import Parameter
 from ..nn import functional as F
-from ..nn.initializers import get_initializer
-from .act import get_activator
+from ._weighted import WeightedLayer
 from .base import Layer
 
 
-class Dense(Layer):
+class Dense(WeightedLayer):
     def __init__(self, out_features, activation=None, use_bias=True, kernel_initializer="normal",
                  bias_initializer="zeros", **kwargs):
         self.out_features = out_features
-        self.use_bias = use_bias
-        self.kernel_initializer = get_initializer(kernel_initializer)
-        self.bias_initializer = get_initializer(bias_initializer)
-        self.activation = get_activator(activation) if activation is not None else None
-        super().__init__(**kwargs)
+        super().__init__(use_bias, activation, kernel_initializer, bias_initializer, **kwargs)
 
+    # the layer's visible output is the activation's when there is one (xs/layers/linear.py:15-17)
     @property
     def data(self):
-        return self._data if self.activation is None else self.activation.data
+        return self.activation.data if self.activation is not None else self._data
 
     @data.setter
     def data(self, v):
-        if self.activation is None:
-            self._data = v
-        else:
+        if self.activation is not None:
             self.activation.data = v
+        else:
+            self._data = v
 
     def compute_output_shape(self, input_shape=None):
         return (self.out_features,)
 
+    def _activation_input_shape(self):
+        return self.out_features
+
     def init_params(self, input_shape=None, *args):
         if input_shape is not None:
             self._input_shape = input_shape
-        # kernel is [in, out], NOT transposed (xs/layers/linear.py:32); bias [1, out]
-        self._parameters.append(Parameter(self.kernel_initializer(tuple(self._input_shape) + (self.out_features,),
-                                                                   requires_grad=True)))
-        if self.use_bias:
-            self._parameters.append(Parameter(self.bias_initializer((1, self.out_features), requires_grad=True)))
-
-    def init_layer_out_tensor(self, x=None):
-        super().init_layer_out_tensor(x)
-        if self.activation is not None:
-            self.activation.compute_output_shape(self.out_features)
-            self.activation.init_layer_out_tensor(self._data)
+        # kernel [in, out] -- NOT transposed (xs/layers/linear.py:32), bias [1, out]
+        self._make_params(tuple(self._input_shape) + (self.out_features,), (1, self.out_features), keep_bias_slot=False)
 
     def call(self, x, *args, **kwargs):
-        out = self._data if (self._data is not None and self._data.is_static) else None
-        if self.use_bias:
-            weight, bias = self._parameters
-            self._data = F.addmm(bias, x, weight, out)
-        else:
-            weight, = self._parameters
-            self._data = F.mm(x, weight, out)
-        if self.activation is not None:
-            return self.activation.forward(self._data)
-        return self._data
-
-    def backward(self, gradients=None):
-        if self.activation is not None:
-            self.activation.backward()
-        super().backward()
+        weight, bias = self._kernel_and_bias()
+        out = self._static_out()
+        self._data = F.mm(x, weight, out) if bias is None else F.addmm(bias, x, weight, out)
+        return self._activate()
 
 
 class Flatten(Layer):
@@ -74,8 +53,8 @@ class Flatten(Layer):
 
     def compute_output_shape(self, input_shape=None):
         assert len(input_shape) >= 3
-        flat = reduce(lambda a, b: a * b, input_shape[self.start_dim - 1:])
-        return tuple(input_shape[: self.start_dim - 1]) + (flat,)
+        lead = self.start_dim - 1                        # input_shape excludes the batch axis
+        return tuple(input_shape[:lead]) + (reduce(mul, input_shape[lead:]),)
 
     def call(self, x, *args, **kwargs):
         out = self._data if (self._data is not None and self._data.is_static) else None
