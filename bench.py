@@ -365,6 +365,8 @@ def run_ours(args, wl):
                            l2="no flush: per-step working set (activations + 2x45 MB params/grads) exceeds the 126 MB L2",
                            vs_baseline_ref="README.md:37-38 XS dynamic graph on CuPy, 265 img/s, unspecified GPU"),
                clocks=clocks, gpu_launches=launches,
+               gpu_launches_unit="C-ABI entry calls of libxsb200.so in the timed region (a lower bound on kernels: a BatchNorm "
+                                 "backward is 2 launches, a strided dgrad one per parity class + the filter copy)",
                e2e=dict(value=e2e_val, unit="images/s", h2d_bytes_per_step=int(x_host.nbytes + y_host.nbytes),
                         d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
                roofline=roof, kernels=per_kernel)
