@@ -26,8 +26,9 @@ from xshinnosuke_b200.utils import opcost  # noqa: E402
 # (name, C, H, OC, k, s, p) of tests/resnet ResNet-18 at 224x224 / 56x56 input
 LAYERS = {
     "r224": [("stem", 3, 224, 64, 7, 2, 3), ("layer1", 64, 56, 64, 3, 1, 1), ("layer2.0", 64, 56, 128, 3, 2, 1),
-             ("layer2", 128, 28, 128, 3, 1, 1), ("layer2.sc", 64, 56, 128, 1, 2, 0), ("layer3", 256, 14, 256, 3, 1, 1),
-             ("layer4", 512, 7, 512, 3, 1, 1)],
+             ("layer2", 128, 28, 128, 3, 1, 1), ("layer2.sc", 64, 56, 128, 1, 2, 0), ("layer3.0", 128, 28, 256, 3, 2, 1),
+             ("layer3", 256, 14, 256, 3, 1, 1), ("layer3.sc", 128, 28, 256, 1, 2, 0), ("layer4.0", 256, 14, 512, 3, 2, 1),
+             ("layer4", 512, 7, 512, 3, 1, 1), ("layer4.sc", 256, 14, 512, 1, 2, 0)],
     "r56": [("stem", 3, 56, 64, 7, 2, 3), ("layer1", 64, 14, 64, 3, 1, 1), ("layer2", 128, 7, 128, 3, 1, 1),
             ("layer3", 256, 4, 256, 3, 1, 1), ("layer4", 512, 2, 512, 3, 1, 1)],
 }
@@ -61,12 +62,17 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--layers", default="")
     ap.add_argument("--json", default="")
+    ap.add_argument("--pers", type=int, default=-1,
+                    help="xsb_tc_config(2, v): 0 = per-tile im2col kernels only, 1 = persistent kernel for strided dgrads "
+                         "(default), 2 = persistent kernel for every im2col forward / dgrad")
     ap.add_argument("--cpu-ref", action="store_true",
                     help="also time the reference's NumPy algorithm (oracle/, float64 im2col + np.dot + col2im) for conv "
                          "fwd / bwd and BN on a 2-image slice of each layer, on the host cores (context, SURVEY 8d)")
     a = ap.parse_args()
     rt.ensure()
     xs.set_math_mode(a.math)
+    if a.pers >= 0:
+        lib.xsb_tc_config(2, a.pers)
     peaks = json.load(open(os.path.join(os.path.dirname(HERE), "MEASURED_PEAKS.json"))) \
         if os.path.exists(os.path.join(os.path.dirname(HERE), "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     N = a.batch or (128 if a.shapes == "r224" else 32)

@@ -24,6 +24,7 @@
 // XSB_ERR_UNSUPPORTED from the xsb_tc_* probes and the caller runs the fp32 FFMA kernel instead.
 #include "conv_halo_tc.cuh"
 #include "conv_wgrad_halo_tc.cuh"
+#include "conv_pers_tc.cuh"
 #include "gemm_tc.cuh"
 
 namespace tc {
@@ -958,6 +959,96 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
     return launch_fprop<64, 4, 2>(ta, tb, to, p, m_tiles, parts, s);
 }
 
+// ---- persistent multi-job launches (conv_pers_tc.cuh)
+// g_pers_mode: 0 = never, 1 = strided dgrads (all parity classes in one launch), 2 = every im2col forward / dgrad too
+static int g_pers_mode = -1;     // -1: read XSB_TC_PERS on first use (default 1)
+static int pers_mode() {
+    if (g_pers_mode < 0) {
+        const char* e = getenv("XSB_TC_PERS");
+        g_pers_mode = e ? atoi(e) : 1;
+    }
+    return g_pers_mode;
+}
+
+struct PersJobDesc {      // host description of one job: stride-(sh,sw) conv of `in` with flt[OCx, KH*KW*Cx]
+    const float* flt;
+    int KH, KW, sh, sw, pad_h, pad_w, OH, OW, o_a, o_b;
+};
+
+// in [N,H,W,Cx] channels-last, every job writes OCx channels of `out`. Jobs must be ordered heaviest first.
+static int pers_dispatch(const float* in, int N, int H, int W, int Cx, int OCx, const PersJobDesc* jd, int n_jobs,
+                         const float* bias, float* out, int accumulate, int o_strided, int o_H, int o_W, int o_sh, int o_sw,
+                         float* stats, int* n_partials, cudaStream_t s) {
+    if (n_jobs < 1 || n_jobs > PERS_MAX_JOBS || Cx % 32 != 0 || OCx % 32 != 0) return XSB_ERR_UNSUPPORTED;
+    if (!load_driver_entry_points()) {
+        xsb_set_error("cuTensorMapEncode* entry points unavailable");
+        return XSB_ERR_CUDA;
+    }
+    const int S = xsb_sm_count_cached();
+    PersParams p{};
+    PersMaps maps;
+    p.out = out; p.bias = bias; p.stats = nullptr; p.ldo = OCx; p.C = Cx; p.accumulate = accumulate;
+    p.o_strided = o_strided; p.o_H = o_H; p.o_W = o_W; p.o_sh = o_sh; p.o_sw = o_sw; p.n_jobs = n_jobs;
+    int64_t m_tiles_total = 0;
+    for (int j = 0; j < n_jobs; ++j) m_tiles_total += ((int64_t)N * jd[j].OH * jd[j].OW + BM - 1) / BM;
+    // column parts: <= 256 columns each; fewer tiles than SMs -> more (narrower) parts so that every SM has a tile
+    const int w32 = OCx / 32;
+    int parts = (OCx + 255) / 256;
+    if (m_tiles_total * parts < S) {
+        int want = (int)(S / m_tiles_total);
+        if (want > w32) want = w32;
+        if (want > 16) want = 16;
+        if (want > parts) parts = want;
+    }
+    if (parts > 16) return XSB_ERR_UNSUPPORTED;
+    int widest = 0, n0 = 0;
+    for (int i = 0; i < parts; ++i) {
+        const int cols = (w32 / parts + (i < w32 % parts ? 1 : 0)) * 32;
+        p.part_n0[i] = (short)n0;
+        p.part_cols[i] = (short)cols;
+        n0 += cols;
+        if (cols > widest) widest = cols;
+    }
+    p.n_parts = parts;
+    const int bn = widest <= 64 ? 64 : widest <= 96 ? 96 : widest <= 128 ? 128 : widest <= 192 ? 192 : 256;
+    int tile = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const PersJobDesc& d = jd[j];
+        PersJob& J = p.job[j];
+        J.M = N * d.OH * d.OW; J.OH = d.OH; J.OW = d.OW; J.KH = d.KH; J.KW = d.KW; J.pad_h = d.pad_h; J.pad_w = d.pad_w;
+        J.sh = d.sh; J.sw = d.sw; J.tile_begin = tile; J.o_a = d.o_a; J.o_b = d.o_b;
+        tile += ((J.M + BM - 1) / BM) * parts;
+        const int lo_h = -d.pad_h, lo_w = -d.pad_w;
+        const int up_h = lo_h + (d.OH - 1) * d.sh - (H - 1), up_w = lo_w + (d.OW - 1) * d.sw - (W - 1);
+        if (d.KH > 255 || d.KW > 255 ||
+            !make_map_im2col(&maps.a[j], in, N, H, W, Cx, d.sh, d.sw, lo_h, lo_w, up_h, up_w, BM) ||
+            !make_map_2d(&maps.b[j], d.flt, (uint64_t)OCx, (uint64_t)d.KH * d.KW * Cx, (uint32_t)bn)) {
+            xsb_set_error("cuTensorMapEncode failed (persistent conv job %d: N=%d H=%d W=%d C=%d OC=%d k=%dx%d)", j, N, H, W, Cx,
+                          OCx, d.KH, d.KW);
+            return XSB_ERR_CUDA;
+        }
+    }
+    p.total_tiles = tile;
+    maps.o = maps.a[0];      // unused by strided-destination launches
+    if (!o_strided) {
+        if (n_jobs != 1) return XSB_ERR_UNSUPPORTED;
+        if (!make_map_2d(&maps.o, out, (uint64_t)p.job[0].M, (uint64_t)OCx, 32)) {
+            xsb_set_error("cuTensorMapEncode failed (persistent conv output M=%d OC=%d)", p.job[0].M, OCx);
+            return XSB_ERR_CUDA;
+        }
+        if (stats) {
+            p.stats = stats;
+            if (n_partials) *n_partials = (p.job[0].M + BM - 1) / BM;
+        }
+    }
+    const int grid = tile < S ? tile : S;
+    if (bn == 256) return launch_pers<256, 1, 4>(maps, p, grid, s);
+    if (bn == 192) return launch_pers<192, 1, 4>(maps, p, grid, s);
+    if (bn == 128) return launch_pers<128, 2, 3>(maps, p, grid, s);
+    if (bn == 96) return launch_pers<96, 2, 3>(maps, p, grid, s);
+    return launch_pers<64, 2, 4>(maps, p, grid, s);
+}
+
 template <int BN, int BKP, int STAGES>
 static int launch_wgrad(const CUtensorMap& x, const CUtensorMap& dy, const WgradParams& p, dim3 grid, cudaStream_t s) {
     constexpr int smem = STAGES * ((4 + BN / 32) * BKP * A_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
@@ -1152,9 +1243,16 @@ static int tc_conv_fwd(const float* x, const float* w, const float* bias, float*
         const int rc = halo_conv_s1(x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.pad, g.pad, g.OH, g.OW, bias, y, 0, s, st);
         if (rc != XSB_ERR_UNSUPPORTED) return rc;
     }
+    const int64_t m_tiles = ((int64_t)g.N * g.OH * g.OW + BM - 1) / BM;
+    if (pers_mode() >= 2) {
+        const PersJobDesc jd{w, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, 0, 0};
+        const bool want_stats = st && st->buf && st->floats >= m_tiles * 3 * g.OC;
+        const int rc = pers_dispatch(x, g.N, g.H, g.W, g.C, g.OC, &jd, 1, bias, y, 0, 0, 0, 0, 1, 1,
+                                     want_stats ? st->buf : nullptr, want_stats ? st->n_partials : nullptr, s);
+        if (rc != XSB_ERR_UNSUPPORTED) return rc;
+    }
     FpropJob j{x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, bias, y, 0,
                0, 0, 0, 1, 1, 0, 0, nullptr, nullptr};
-    const int64_t m_tiles = ((int64_t)g.N * g.OH * g.OW + BM - 1) / BM;
     if (st && st->buf && st->floats >= m_tiles * 3 * g.OC) {
         j.stats = st->buf;
         j.n_partials = st->n_partials;
@@ -1220,6 +1318,40 @@ static int tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvG
         dim3 grid((g.C + 31) / 32, (g.OC + 31) / 32, taps), block(32, 8);
         gather_subfilters_k<<<grid, block, 0, s>>>(w, ws, g.OC, taps, g.C, tp);
         XSB_LAUNCH_CHECK();
+    }
+    // all parity classes (or the single stride-1 class the halo kernel does not take) in ONE persistent launch
+    if (gathered && !halo_first && (strided ? pers_mode() >= 1 : pers_mode() >= 2)) {
+        PersJobDesc jd[PERS_MAX_JOBS];
+        int nj = 0;
+        bool fits = true;
+        for (int a = 0; a < g.sh && fits; ++a)
+            for (int b = 0; b < g.sw; ++b) {
+                if (ch[a].n == 0 || cw[b].n == 0 || ch[a].T == 0 || cw[b].T == 0) continue;
+                if (nj == PERS_MAX_JOBS) { fits = false; break; }
+                jd[nj++] = PersJobDesc{ws + cls_base[a][b], ch[a].T, cw[b].T, 1, 1, ch[a].padp, cw[b].padp, ch[a].n, cw[b].n, a, b};
+            }
+        if (fits && nj > 0) {
+            for (int i = 1; i < nj; ++i)           // heaviest job first (insertion sort by tap count)
+                for (int k = i; k > 0 && jd[k].KH * jd[k].KW > jd[k - 1].KH * jd[k - 1].KW; --k) {
+                    const PersJobDesc t = jd[k]; jd[k] = jd[k - 1]; jd[k - 1] = t;
+                }
+            const int rc = pers_dispatch(dy, g.N, g.OH, g.OW, g.OC, g.C, jd, nj, nullptr, dx, accumulate, strided, g.H, g.W,
+                                         g.sh, g.sw, nullptr, nullptr, s);
+            if (rc != XSB_ERR_UNSUPPORTED) {
+                if (rc != XSB_OK) return rc;
+                if (!accumulate)                   // classes no filter tap reaches: their gradient is zero
+                    for (int a = 0; a < g.sh; ++a)
+                        for (int b = 0; b < g.sw; ++b) {
+                            const int Ha = ch[a].n, Wb = cw[b].n;
+                            if (Ha == 0 || Wb == 0 || (ch[a].T != 0 && cw[b].T != 0)) continue;
+                            const int64_t total = (int64_t)g.N * Ha * Wb * (g.C / 4);
+                            zero_class_k<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(reinterpret_cast<float4*>(dx), Ha, Wb,
+                                                                                         g.C / 4, g.H, g.W, g.sh, g.sw, a, b, total);
+                            XSB_LAUNCH_CHECK();
+                        }
+                return XSB_OK;
+            }
+        }
     }
     for (int a = 0; a < g.sh; ++a)
         for (int b = 0; b < g.sw; ++b) {
@@ -1322,6 +1454,10 @@ int xsb_tc_config(int key, int value) {
     }
     if (key == 1) {
         tc::g_dgrad_mn = value ? 1 : 0;
+        return XSB_OK;
+    }
+    if (key == 2) {
+        tc::g_pers_mode = value;
         return XSB_OK;
     }
     xsb_set_error("xsb_tc_config: unknown key %d", key);
