@@ -151,7 +151,8 @@ int xsb_conv2d_wgrad(const float* dy, const float* x, float* dw, int N, int H, i
  * that ran the fp32 FFMA kernel while in XSB_MATH_TF32 mode (shape outside the tensor-core envelope). */
 int xsb_tc_stats(uint64_t* out2);
 /* kernel-selection switches for tests / A-B measurements: key 0 = CTA-pair (tcgen05 cta_group::2) forward kernels (0/1),
- * key 1 = dgrad reads the forward filter as stored (MN-major operand) instead of a flipped / transposed copy (0/1) */
+ * key 1 = dgrad reads the forward filter as stored (MN-major operand) instead of a flipped / transposed copy (0/1),
+ * key 2 = persistent multi-job convolution kernel: 0 never, 1 strided dgrads (default), 2 every im2col forward / dgrad */
 int xsb_tc_config(int key, int value);
 
 /* ---- losses. replaces xs/nn/functional.py:984-1010 + xs/nn/td_functional.py:73-78,115-128 +
@@ -166,15 +167,18 @@ int xsb_mse_bwd(const float* a, const float* b, const float* dloss, float* da /*
                 int64_t n, int reduction, int acc_a, int acc_b, void* stream);
 
 /* ---- fused multi-tensor optimizer over the flat parameter buffer. replaces xs/optim/sgd.py:5-9 and
- *      xs/optim/adam.py:13-30. grad_scale = 1/world for all-reduced (summed) gradients. ---- */
-int xsb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, void* stream);
+ *      xs/optim/adam.py:13-30. grad_scale = 1/world for all-reduced (summed) gradients. weight_decay: every rule sees
+ *      g' = grad_scale*g + weight_decay*p (L2 term, applied in the same pass). The reference accepts the argument
+ *      (xs/optim/optimizer.py:9) and never applies it; 0 reproduces the reference's arithmetic exactly. ---- */
+int xsb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, float weight_decay, void* stream);
 int xsb_adam_step(float* p, const float* g, float* v /* 1st moment */, float* m /* 2nd moment */, int64_t n, float lr,
-                  float beta1, float beta2, float eps, float grad_scale, const int* step_dev, void* stream);
+                  float beta1, float beta2, float eps, float grad_scale, float weight_decay, const int* step_dev,
+                  void* stream);
 int xsb_counter_inc(int* counter_dev, void* stream);
 /* Momentum (xs/optim/sgd.py:12-29), RMSprop (rmsprop.py:4-21), AdaGrad (adagrad.py:4-18), AdaDelta
  * (adadelta.py:4-26) -- kind 0..3; s1/s2 = per-parameter state buffers (s2: AdaDelta's delta_x only). */
 int xsb_rule_step(int kind, float* p, const float* g, float* s1, float* s2, int64_t n, float lr, float rho, float eps,
-                  float grad_scale, void* stream);
+                  float grad_scale, float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

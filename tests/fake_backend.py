@@ -310,11 +310,13 @@ class FakeLib:
             _store(f32(db, n), -g, acc_b)
 
     # ---- optimizers
-    def _sgd_step(self, p, g, n, lr, gscale, s):
-        f32(p, n)[...] = f32(p, n).astype(np.float64) - lr * gscale * f32(g, n).astype(np.float64)
+    def _sgd_step(self, p, g, n, lr, gscale, wd, s):
+        pv = f32(p, n).astype(np.float64)
+        f32(p, n)[...] = pv - lr * (gscale * f32(g, n).astype(np.float64) + wd * pv)
 
-    def _rule_step(self, kind, p, g, s1, s2, n, lr, rho, eps, gscale, s):
-        P, G = [f32(p, n).astype(np.float64)], [f32(g, n).astype(np.float64) * gscale]
+    def _rule_step(self, kind, p, g, s1, s2, n, lr, rho, eps, gscale, wd, s):
+        P = [f32(p, n).astype(np.float64)]
+        G = [f32(g, n).astype(np.float64) * gscale + wd * P[0]]
         st = {"v": [f32(s1, n).astype(np.float64)], "s": [f32(s1, n).astype(np.float64)]}
         if kind == 3:
             st["x"] = [f32(s2, n).astype(np.float64)]
@@ -342,9 +344,9 @@ class FakeLib:
     def _counter_inc(self, c, s):
         i32(c, 1)[0] += 1
 
-    def _adam_step(self, p, g, v, m, n, lr, b1, b2, eps, gscale, step, s):
+    def _adam_step(self, p, g, v, m, n, lr, b1, b2, eps, gscale, wd, step, s):
         t = int(i32(step, 1)[0])
-        gv = f32(g, n).astype(np.float64) * gscale
+        gv = f32(g, n).astype(np.float64) * gscale + wd * f32(p, n).astype(np.float64)
         vv = b1 * f32(v, n).astype(np.float64) + (1 - b1) * gv
         mv = b2 * f32(m, n).astype(np.float64) + (1 - b2) * gv * gv
         f32(p, n)[...] = f32(p, n).astype(np.float64) - lr * (vv / (1 - b1 ** t)) / (np.sqrt(mv / (1 - b2 ** t)) + eps)

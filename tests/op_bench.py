@@ -178,10 +178,10 @@ def main():
     fp, fg, fv, fm = dev(P), dev(P), dev(P, zero=True), dev(P, zero=True)
     stp = torch.ones(1, dtype=torch.int32, device=rt.device)
     if "sgd" in ops:
-        args = (fp.data_ptr(), fg.data_ptr(), P, 0.1, 1.0, st)
+        args = (fp.data_ptr(), fg.data_ptr(), P, 0.1, 1.0, 0.0, st)
         report("sgd", "flat", "xsb_sgd_step", args, timed(lambda: lib.xsb_sgd_step(*args), a.iters), "(90 MB: L2-resident)")
     if "adam" in ops:
-        args = (fp.data_ptr(), fg.data_ptr(), fv.data_ptr(), fm.data_ptr(), P, 1e-3, 0.9, 0.999, 1e-8, 1.0, stp.data_ptr(), st)
+        args = (fp.data_ptr(), fg.data_ptr(), fv.data_ptr(), fm.data_ptr(), P, 1e-3, 0.9, 0.999, 1e-8, 1.0, 0.0, stp.data_ptr(), st)
         report("adam", "flat", "xsb_adam_step", args, timed(lambda: lib.xsb_adam_step(*args), a.iters))
     if a.json:
         json.dump(dict(shapes=a.shapes, batch=N, math=a.math, iters=a.iters, rows=rows), open(a.json, "w"), indent=1)

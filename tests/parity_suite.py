@@ -218,6 +218,33 @@ def check_optimizers(golden, tol):
                 close(p.eval, want[f"p{i}"], max(tol, 2e-6), f"{name}/step{step}/p{i}")
 
 
+def check_weight_decay(golden, tol, wd=0.05):
+    """SURVEY 8f-3 "real weight_decay": the reference accepts the argument and never applies it (Q8), so there is no
+    golden vector; the oracle is the reference's own update rule fed g' = g + wd*p (classic L2 term), float64."""
+    init = golden.case("optim/init")
+    n = len(init)
+    cases = (("sgd", lambda ps: xs.optim.SGD(ps, lr=0.1, weight_decay=wd), lambda P, G, st: X.sgd_step(P, G, 0.1)),
+             ("adam", lambda ps: xs.optim.Adam(ps, lr=0.01, weight_decay=wd), lambda P, G, st: X.adam_step(P, G, st, lr=0.01)),
+             ("momentum", lambda ps: xs.optim.Momentum(ps, lr=0.05, weight_decay=wd),
+              lambda P, G, st: X.momentum_step(P, G, st, 0.05, 0.9)),
+             ("rmsprop", lambda ps: xs.optim.RMSprop(ps, lr=0.01, weight_decay=wd),
+              lambda P, G, st: X.rmsprop_step(P, G, st, 0.01, 0.9, 1e-7)))
+    for name, ctor, rule in cases:
+        ps = [nn.Parameter(init[f"p{i}"]) for i in range(n)]
+        ref = [init[f"p{i}"].astype(np.float64).copy() for i in range(n)]
+        opt, st = ctor(ps), {}
+        for step in range(3):
+            opt.zero_grad()
+            g = golden.case(f"optim/grads{step}")
+            for i, p in enumerate(ps):
+                p.grad.eval = g[f"g{i}"]
+            opt.step()
+            rule(ref, [g[f"g{i}"].astype(np.float64) + wd * ref[i] for i in range(n)], st)
+            for i, p in enumerate(ps):
+                close(p.eval, ref[i], max(tol, 2e-6), f"weight_decay/{name}/step{step}/p{i}")
+        # wd = 0 must stay the reference's arithmetic (golden vectors): covered by check_optimizers
+
+
 # ------------------------------------------------------------------ reference test scripts
 def check_gradient_check_scripts(golden, tol):
     # tests/gradient_check/check_cnn.py

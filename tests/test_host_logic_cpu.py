@@ -74,6 +74,7 @@ def test_dense_losses(golden):
 
 def test_optimizers(golden):
     S.check_optimizers(golden, TOL)
+    S.check_weight_decay(golden, TOL)
 
 
 def test_gradient_check_scripts(golden):

@@ -76,6 +76,7 @@ def test_dense_losses(golden):
 def test_optimizers(golden):
     import parity_suite as S
     S.check_optimizers(golden, TOL)
+    S.check_weight_decay(golden, TOL)
 
 
 def test_gradient_check_scripts(golden):

@@ -7,8 +7,9 @@ view of it, and lays the gradients out in a parallel flat buffer. `zero_grad()` 
 (gradients are flagged logically zero, see DevArray.pending_zero) and `step()` is a single
 128-bit-vectorised kernel (xsb_sgd_step / xsb_adam_step). The parameter collection may be a live set
 that is still empty at construction (tests/resnet/resnet18_dg.py:88 builds the optimizer before the
-first forward); it is re-flattened whenever it grows. `weight_decay` is accepted and ignored, like
-the reference (Q8). The data-parallel engine (parallel.py) all-reduces buckets of the flat gradient
+first forward); it is re-flattened whenever it grows. `weight_decay`: the reference accepts it and
+never applies it (Q8); here a non-zero value adds the L2 term wd*p to the gradient inside the fused kernel
+(g' = grad_scale*g + wd*p), the default 0 is the reference's arithmetic. The data-parallel engine (parallel.py) all-reduces buckets of the flat gradient
 buffer and passes grad_scale = 1/world.
 """
 from ..core.device import DevArray, rt, torch
@@ -106,7 +107,7 @@ class SGD(Optimizer):
             self.before_step(self)
         if flat.total:
             lib.xsb_sgd_step(flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), flat.total, float(self.lr),
-                             float(self.grad_scale), rt.stream())
+                             float(self.grad_scale), float(self.weight_decay), rt.stream())
             rt.launches += 1
         super().step()
 
@@ -135,7 +136,7 @@ class Adam(Optimizer):
         if flat.total:
             lib.xsb_adam_step(flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), flat.extra[0].data_ptr(),
                               flat.extra[1].data_ptr(), flat.total, float(self.lr), float(self.beta1),
-                              float(self.beta2), float(self.epsilon), float(self.grad_scale),
+                              float(self.beta2), float(self.epsilon), float(self.grad_scale), float(self.weight_decay),
                               self._step_dev.data_ptr(), st)
         rt.launches += 2
 
@@ -158,7 +159,7 @@ class _RuleOptimizer(Optimizer):
             s2 = flat.extra[1].data_ptr() if self.n_state > 1 else None
             lib.xsb_rule_step(self.kind, flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), flat.extra[0].data_ptr(), s2,
                               flat.total, float(self.lr), float(self.rho), float(self.epsilon), float(self.grad_scale),
-                              rt.stream())
+                              float(self.weight_decay), rt.stream())
             rt.launches += 1
         self.iterations += 1
 
