@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- ResNet-18 (tests/resnet) training throughput on N B200s, one JSON line on stdout.
+"""bench.py -- training throughput of the xs hot path on N B200s, one JSON line on stdout.
 
-    python bench.py --gpus N --steps K --warmup W [--workload r56|r224] [--math fp32|tf32]
+    python bench.py --gpus N --steps K --warmup W [--workload r224|r56|cnn|mlp] [--math tf32|fp32|fp32x3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's NumPy algorithm (oracle port) on the host cores
 
-A "step" = zero_grad, forward, cross-entropy, backward, (bucketed all-reduce), fused optimizer step on one
-batch of synthetic images through the public xs API of xshinnosuke_b200 (the reference's
-tests/resnet/resnet18_dg.py:92-100 loop). `value` keeps the batch resident in HBM; `e2e` uploads every
-step's batch from pinned host memory and reads the loss back. See DESIGN.md "Measurement".
+A "step" = zero_grad, forward, cross-entropy, backward, (bucketed all-reduce), fused optimizer step on one batch of
+synthetic data through the public xs API of xshinnosuke_b200 (the loop of the reference's
+tests/resnet/resnet18_dg.py:92-100, resp. the body of Model.fit, xs/nn/models.py:100-106). `value` keeps the batch
+resident in HBM; `e2e` uploads every step's batch from pinned host memory and reads the loss back.
+
+Workloads (BASELINE.json configs): r224 = configs[4] per GPU (default, the configuration the headline metric is quoted
+on), r56 = configs[3], cnn = configs[0], mlp = configs[1]; configs[2] (op sweep) is tests/op_bench.py --sweep.
+See DESIGN.md "Measurement" for what every key means and how the kernel table is timed.
 """
 import argparse
 import json
@@ -26,13 +30,23 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # BASELINE.json configs[3] (3x32x32 does not run on the reference: min input 33, SURVEY.md 8c -> its own 56x56)
-    "r56": dict(batch=32, hw=56, optimizer="sgd", lr=0.1, classes=100,
+    "r56": dict(kind="resnet", batch=32, hw=56, optimizer="sgd", lr=0.1, classes=100, metric="resnet18_train_images_per_sec",
                 name="ResNet-18 (tests/resnet), batch 32/GPU, synthetic 3x56x56, SGD lr 0.1, dynamic graph"),
     # BASELINE.json configs[4]
-    "r224": dict(batch=128, hw=224, optimizer="adam", lr=1e-3, classes=100,
+    "r224": dict(kind="resnet", batch=128, hw=224, optimizer="adam", lr=1e-3, classes=100, metric="resnet18_train_images_per_sec",
                  name="ResNet-18 (tests/resnet), batch 128/GPU, synthetic 3x224x224, Adam lr 1e-3, dynamic graph"),
+    # BASELINE.json configs[0] in the form that runs on the reference
+    "cnn": dict(kind="cnn", batch=256, optimizer="sgd", lr=0.01, classes=10, metric="readme_cnn_train_images_per_sec",
+                name="README functional CNN Input(1,28,28)-Conv2D(8,2x2)-relu-MaxPooling2D(2)-Flatten-Dense(10), batch 256/GPU, "
+                     "SGD lr 0.01, static graph (Model)"),
+    # BASELINE.json configs[1]
+    "mlp": dict(kind="mlp", batch=128, optimizer="sgd", lr=0.05, classes=10, metric="mlp_train_images_per_sec",
+                name="Sequential MLP Dense(784->500, relu)-Dense(10), batch 128/GPU, SGD lr 0.05, static graph (Sequential)"),
 }
 README_GPU_IMG_S = 265.0   # XS dynamic graph on CuPy, unspecified GPU (README.md:37-38)
+TENSOR_ENTRIES = ("xsb_conv2d_fwd", "xsb_conv2d_fwd_stats", "xsb_conv2d_fwd_acc", "xsb_conv2d_dgrad", "xsb_conv2d_wgrad", "xsb_gemm")
+CONV_ENTRIES = TENSOR_ENTRIES[:5]
+PARITY_TOL_NET = 5e-3      # whole network in tf32 (20 tf32 convolutions deep); per-op bar is 2e-3 (tests/test_parity_gpu.py)
 
 
 def peaks():
@@ -78,7 +92,7 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.12)
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -86,19 +100,20 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    power_w_max=max(power) if power else None, reasons=sorted(reasons), samples=len(sm))
 
 
 def signature(name, a):
-    """Kernel + shape key for the per-launch roofline (conv geometry / GEMM dims / element count)."""
+    """Kernel + shape key (conv geometry / GEMM dims / element count)."""
     try:
-        if name in ("xsb_conv2d_fwd", "xsb_conv2d_fwd_stats"):
+        if name in ("xsb_conv2d_fwd", "xsb_conv2d_fwd_stats", "xsb_conv2d_fwd_acc"):
             N, H, W, C, OC, KH, KW, sh, sw, pad = a[4:14]
         elif name in ("xsb_conv2d_dgrad", "xsb_conv2d_wgrad"):
             N, H, W, C, OC, KH, KW, sh, sw, pad = a[3:13]
@@ -119,7 +134,7 @@ def signature(name, a):
         return name
 
 
-# ---------------------------------------------------------------------------------------------- reference arm
+# ---------------------------------------------------------------------------------------------- CPU arms (oracle)
 def _use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
     try:
@@ -130,104 +145,289 @@ def _use_all_host_threads():
         return os.cpu_count()
 
 
+def synthetic_host_batch(wl, n, seed):
+    """Host batch of the workload's shape: images rand [0,1) fp32, labels randint."""
+    rs = np.random.RandomState(seed)
+    if wl["kind"] == "resnet":
+        x = rs.rand(n, 3, wl["hw"], wl["hw"])
+    elif wl["kind"] == "cnn":
+        x = rs.rand(n, 1, 28, 28)
+    else:
+        x = rs.rand(n, 784)
+    return x.astype(np.float32), rs.randint(0, wl["classes"], (n,)).astype(np.int64)
+
+
+def oracle_net(wl, weight_seed):
+    """The float64 NumPy restatement of the reference path for this workload (oracle/ -- test infrastructure; here it is
+    the thing TIMED on the host cores and the checker of `parity_checked`, never part of the product path)."""
+    np.random.seed(weight_seed)
+    if wl["kind"] == "resnet":
+        from oracle.resnet18 import ResNet18 as OracleNet
+        net, state = OracleNet(num_classes=wl["classes"]), {}
+        if wl["optimizer"] == "sgd":
+            return net, (lambda x, y: net.train_step(x, y, wl["lr"]))
+        return net, (lambda x, y: net.train_step(x, y, wl["lr"], "adam", state))
+    from oracle.small_nets import ReadmeCNN, ReadmeMLP
+    net = ReadmeCNN() if wl["kind"] == "cnn" else ReadmeMLP()
+    return net, (lambda x, y: net.train_step(x, y, wl["lr"]))
+
+
+def cpu_sample_size(wl):
+    # bounded sample: a step on the full 224x224 batch is ~1.4 TFLOP of float64 -> a slice of the batch instead
+    return 2 if (wl["kind"] == "resnet" and wl["hw"] > 64) else wl["batch"]
+
+
+def time_oracle(wl, budget_s, max_steps, min_steps=2):
+    cores = _use_all_host_threads()
+    n = cpu_sample_size(wl)
+    x, y = synthetic_host_batch(wl, n, seed=0)
+    x = x.astype(np.float64)
+    _, step = oracle_net(wl, weight_seed=0)
+    step(x, y)
+    t0, k = time.perf_counter(), 0
+    while k < min_steps or (time.perf_counter() - t0 < budget_s and k < max_steps):
+        step(x, y)
+        k += 1
+    dt = (time.perf_counter() - t0) / k
+    shape = "x".join(str(s) for s in x.shape[1:])
+    return dict(value=n / dt, unit="images/s", cores=cores, kind="port",
+                sample=f"{k} steps of {n} samples ({shape}) through oracle/ (float64 NumPy restatement of the reference "
+                       f"path: im2col + np.dot + col2im), {dt * 1e3:.1f} ms/step"), dt, k, n
+
+
 def run_reference(args, wl):
-    """The reference's own algorithm (float64 im2col + np.dot + col2im, oracle/ port of xs/nn/functional.py,
-    xs/nn/grad_fn.py, xs/optim) on the host cores, every BLAS thread it can use. Rank 0 only."""
+    """The reference's own algorithm (oracle/ port of xs/nn/functional.py, xs/nn/grad_fn.py, xs/optim; the reference itself
+    is pure Python and cannot travel to the GPU box) on the host cores, every BLAS thread it can use. Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle.resnet18 import ResNet18 as OracleNet, synthetic_batch
-    cores = _use_all_host_threads()
-    # bounded sample: a step on the full 224x224 batch is ~1.4 TFLOP of float64 -> time a 4-image slice instead
-    n = wl["batch"] if wl["hw"] <= 64 else 4
-    x, y = synthetic_batch(n, wl["hw"], wl["classes"], seed=0)
-    net = OracleNet(num_classes=wl["classes"])
-    state = {}
-    step = (lambda: net.train_step(x, y, wl["lr"])) if wl["optimizer"] == "sgd" else \
-        (lambda: net.train_step(x, y, wl["lr"], "adam", state))
-    for _ in range(max(1, min(args.warmup, 2))):
-        step()
-    steps = max(1, min(args.steps, 20))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    val = n / dt
-    sample = f"{steps} steps of {n} images ({wl['hw']}x{wl['hw']}), float64 NumPy (im2col + np.dot + col2im)"
-    out = dict(metric="resnet18_train_images_per_sec", value=val, unit="images/s", n_gpus=args.gpus, steps=steps,
-               warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+    cpu, dt, k, n = time_oracle(wl, budget_s=60.0, max_steps=max(1, min(args.steps, 200)), min_steps=min(2, max(1, args.steps)))
+    out = dict(metric=wl["metric"], value=cpu["value"], unit="images/s", n_gpus=args.gpus, steps=k,
+               warmup=1, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f64", data="synthetic", impl="reference",
-               config=dict(workload=wl["name"], sample_batch=n),
-               cpu_baseline=dict(value=val, unit="images/s", cores=cores, kind="port", sample=sample),
-               e2e=dict(value=val, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+               config=dict(workload=wl["name"], sample_batch=n), cpu_baseline=cpu,
+               e2e=dict(value=cpu["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(out)
 
 
-def cpu_baseline_leg(wl, budget_s=20.0):
-    from oracle.resnet18 import ResNet18 as OracleNet, synthetic_batch
-    cores = _use_all_host_threads()
-    n = wl["batch"] if wl["hw"] <= 64 else 2
-    x, y = synthetic_batch(n, wl["hw"], wl["classes"], seed=0)
-    net = OracleNet(num_classes=wl["classes"])
-    state = {}
-    step = (lambda: net.train_step(x, y, wl["lr"])) if wl["optimizer"] == "sgd" else \
-        (lambda: net.train_step(x, y, wl["lr"], "adam", state))
-    step()
-    t0, k = time.perf_counter(), 0
-    while k < 2 or (time.perf_counter() - t0 < budget_s and k < 12):
-        step()
-        k += 1
-    dt = (time.perf_counter() - t0) / k
-    return dict(value=n / dt, unit="images/s", cores=cores, kind="port",
-                sample=f"{k} steps of {n} images ({wl['hw']}x{wl['hw']}) through oracle/resnet18.py "
-                       f"(float64 NumPy restatement of the reference path), {dt * 1e3:.0f} ms/step")
-
-
 # ---------------------------------------------------------------------------------------------- our arm
+def build_workload(wl, xs, nn, x_host, y_host):
+    """-> (eager_step, x_dev, y_dev, net_parameters, optimizer, model) through the public xs API."""
+    x_dev, y_dev = xs.tensor(x_host), xs.tensor(y_host)
+    if wl["kind"] == "resnet":
+        from xshinnosuke_b200.recipes import ResNet18
+        net = ResNet18(num_classes=wl["classes"])
+        opt = xs.optim.SGD(net.parameters(), lr=wl["lr"]) if wl["optimizer"] == "sgd" else \
+            xs.optim.Adam(net.parameters(), lr=wl["lr"])
+        crit = nn.CrossEntropyLoss()
+
+        def step():
+            opt.zero_grad()
+            loss = crit(net(x_dev), y_dev)
+            loss.backward()
+            opt.step()
+            return loss
+        return step, x_dev, y_dev, net, opt
+    from xshinnosuke_b200.recipes import readme_cnn, readme_mlp
+    model = readme_cnn(lr=wl["lr"]) if wl["kind"] == "cnn" else readme_mlp(lr=wl["lr"])
+    model.init_graph_out_tensor(x_dev, y_dev)
+
+    def step():          # the body of Model.fit's batch loop (xs/nn/models.py:100-106) on the static graph
+        model.train()
+        model.optimizer.zero_grad()
+        pred = model.forward(x_dev)
+        loss = model.loss.forward(pred, y_dev)
+        model.backward(loss)
+        model.optimizer.step()
+        return loss
+    return step, x_dev, y_dev, model, model.optimizer
+
+
+def parity_check(wl, args, xs, nn):
+    """Step 0 of the GPU path (the bench's math mode) against the float64 oracle on the SAME bounded sample the CPU arm
+    times, from identical seeded weights: loss, logits, the LAST layer's weight gradient (one product away from the loss)
+    and the FIRST layer's (through the whole backward pass). The first-layer figure is informational: a deep, randomly
+    initialised ResNet amplifies any rounding (ReLU-mask and arg-max flips) -- the float64 oracle itself moves by
+    `oracle_tf32_model_*` when its GEMM operands are cut to tf32 (oracle.xs_numpy.TF32_OPERANDS), and the pure-fp32 FFMA
+    path shows 1e-3..1e-2 there as well (tools/parity_probe.py)."""
+    import xshinnosuke_b200.core.state as G
+    from oracle import xs_numpy as X
+    n = cpu_sample_size(wl)
+    x, y = synthetic_host_batch(wl, n, seed=0)
+    x64 = x.astype(np.float64)
+
+    def oracle_step0(tf32_operands):
+        X.TF32_OPERANDS = tf32_operands
+        try:
+            onet, _ = oracle_net(wl, weight_seed=0)
+            if wl["kind"] == "resnet":
+                logits = onet.forward(x64)
+                loss, probs = X.cross_entropy_fwd(logits, y)
+                grads = onet.backward(X.cross_entropy_bwd(probs, y))
+                return dict(loss=float(loss[0]), logits=logits, dw_first=grads[0], dw_last=grads[-2])
+            w0 = [p.copy() for p in onet.params]
+            lossv = onet.train_step(x64, y, wl["lr"])            # SGD: dW = (W0 - W1) / lr
+            return dict(loss=lossv, logits=None, dw_first=(w0[0] - onet.params[0]) / wl["lr"],
+                        dw_last=(w0[-2] - onet.params[-2]) / wl["lr"])
+        finally:
+            X.TF32_OPERANDS = False
+    ref = oracle_step0(False)
+    G.INPUTS = G.OUTPUTS = G.GRAPH = None
+    np.random.seed(0)
+    tx, ty = xs.tensor(x), xs.tensor(y)
+    got_logits = None
+    if wl["kind"] == "resnet":
+        from xshinnosuke_b200.recipes import ResNet18
+        net = ResNet18(num_classes=wl["classes"])
+        opt = xs.optim.SGD(net.parameters(), lr=wl["lr"])
+        opt.zero_grad()
+        out = net(tx)
+        got_logits = out.eval
+        loss = nn.CrossEntropyLoss()(out, ty)
+        got_loss = loss.item()
+        loss.backward()
+        params = sorted(net.parameters(), key=lambda p: p.ticket)
+    else:
+        from xshinnosuke_b200.recipes import readme_cnn, readme_mlp
+        model = readme_cnn(lr=wl["lr"]) if wl["kind"] == "cnn" else readme_mlp(lr=wl["lr"])
+        model.init_graph_out_tensor(tx, ty)
+        model.train()
+        model.optimizer.zero_grad()
+        pred = model.forward(tx)
+        loss = model.loss.forward(pred, ty)
+        got_loss = loss.item()
+        model.backward(loss)
+        params = sorted(model.parameters(), key=lambda p: p.ticket)
+    got_first, got_last = params[0].grad.eval, params[-2].grad.eval
+    G.INPUTS = G.OUTPUTS = G.GRAPH = None
+    errs = dict(loss_rel_err=abs(got_loss - ref["loss"]) / abs(ref["loss"]),
+                last_layer_dw_rel_err=float(X.rel_err(got_last.reshape(ref["dw_last"].shape), ref["dw_last"])))
+    if ref["logits"] is not None:
+        errs["logits_rel_err"] = float(X.rel_err(got_logits, ref["logits"]))
+    tol = 1e-5 if args.math in ("fp32", "fp32x3") else PARITY_TOL_NET
+    # fp32 modes through a whole network: fp32 storage rounding of every activation on the way (the per-op bar is 1e-5)
+    net_tol = max(tol, 1e-4) if wl["kind"] == "resnet" else max(tol, 2e-5)
+    passed = bool(all(v <= net_tol for v in errs.values()))
+    info = dict(first_layer_dw_rel_err=float(X.rel_err(got_first.reshape(ref["dw_first"].shape), ref["dw_first"])))
+    if args.math == "tf32" and wl["kind"] == "resnet":
+        model_ref = oracle_step0(True)
+        info["oracle_tf32_model_first_layer_dw_dev"] = float(X.rel_err(model_ref["dw_first"], ref["dw_first"]))
+        info["oracle_tf32_model_logits_dev"] = float(X.rel_err(model_ref["logits"], ref["logits"]))
+        info["first_layer_dw_vs_tf32_model"] = float(X.rel_err(got_first.reshape(ref["dw_first"].shape), model_ref["dw_first"]))
+    errs.update(info)
+    errs.update(sample=f"{n} samples, step 0, identical seeded weights, float64 oracle", math_mode=args.math, tol=net_tol,
+                tol_applies_to="loss, logits, last_layer_dw (first_layer_dw is informational: chaotic amplification)",
+                metric="max|a-b|/max|b|", passed=passed)
+    return errs
+
+
+def kernel_timeline(eager_step, graphed, lib, torch, n_replays=3):
+    """Per C-ABI call kernel time measured INSIDE the CUDA-graph replay.
+
+    (1) one eager step under the profiler with every C-ABI call wrapped in a record_function range: CUPTI attributes each
+    kernel to the call that launched it; (2) `n_replays` graph replays under the profiler: the replay runs the same kernels in
+    the same order, so kernel i of a replay is kernel i of the eager list and takes ITS replay duration. Falls back to the
+    eager kernel durations if the two lists do not line up. -> (records [(entry, args, seconds)], how)."""
+    from torch.profiler import ProfilerActivity, profile, record_function
+    from torch.autograd import DeviceType
+    names = [n for n in lib.protos if n.startswith("xsb_") and lib.protos[n][1] and
+             n not in ("xsb_init", "xsb_stream_sync", "xsb_memcpy_h2d", "xsb_memcpy_d2h", "xsb_bn_workspace_floats",
+                       "xsb_tc_stats", "xsb_tc_config", "xsb_tc_conv_supported")]
+    originals, calls = {}, []
+    for n in names:
+        fn = getattr(lib, n)
+        originals[n] = fn
+
+        def wrapped(*a, _fn=fn, _n=n):
+            idx = len(calls)
+            calls.append((_n, a))
+            with record_function(f"xsbcall::{idx}"):
+                return _fn(*a)
+        setattr(lib, n, wrapped)
+    try:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            eager_step()
+            torch.cuda.synchronize()
+    finally:
+        for n, fn in originals.items():
+            setattr(lib, n, fn)
+    # attribution: kernel --(correlation id)--> its cudaLaunchKernel runtime event --(launch time inside the range)--> C-ABI call
+    import bisect
+    evs = list(prof.events())
+    ranges = sorted((ev.time_range.start, ev.time_range.end, int(ev.name.split("::")[1])) for ev in evs
+                    if ev.name.startswith("xsbcall::"))
+    starts = [r[0] for r in ranges]
+    launch_t = {ev.id: ev.time_range.start for ev in evs
+                if ev.device_type == DeviceType.CPU and ev.name.startswith(("cudaLaunch", "cuLaunch"))}
+    eager_kernels = []          # (call index, kernel name, eager duration us) in launch order
+    dev = [ev for ev in evs if ev.device_type == DeviceType.CUDA and
+           not ev.name.lower().startswith(("memcpy", "memset", "xsbcall::"))]      # (ranges have a GPU-side twin)
+    dev.sort(key=lambda ev: ev.time_range.start)
+    for ev in dev:
+        t = launch_t.get(ev.id)
+        if t is None:
+            continue
+        j = bisect.bisect_right(starts, t) - 1
+        if j >= 0 and t <= ranges[j][1]:
+            eager_kernels.append((ranges[j][2], ev.name, ev.time_range.elapsed_us()))
+    how = "eager kernel durations (CUPTI), attributed to C-ABI calls"
+    durs = [d for _, _, d in eager_kernels]
+    if graphed is not None and eager_kernels:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof2:
+            for _ in range(n_replays):
+                graphed()
+            torch.cuda.synchronize()
+        ks = [ev for ev in prof2.events() if ev.device_type == DeviceType.CUDA and
+              not ev.name.lower().startswith(("memcpy", "memset"))]
+        ks.sort(key=lambda ev: ev.time_range.start)
+        L = len(eager_kernels)
+        # the graph holds the step's kernels only; library fills (at::FillFunctor) launched outside C-ABI calls are
+        # in the replay as well: align by name, skipping replay kernels the eager attribution does not know
+        if len(ks) >= n_replays * L:
+            per = len(ks) // n_replays
+            if per * n_replays == len(ks):
+                acc, ok = [0.0] * L, True
+                for r in range(n_replays):
+                    seq, i = ks[r * per:(r + 1) * per], 0
+                    for ev in seq:
+                        if i < L and ev.name == eager_kernels[i][1]:
+                            acc[i] += ev.time_range.elapsed_us()
+                            i += 1
+                    ok = ok and i == L
+                if ok:
+                    durs = [a / n_replays for a in acc]
+                    how = f"CUDA-graph replay kernel durations (CUPTI, mean of {n_replays} replays), attributed through the eager launch order"
+    how += f" [{len(eager_kernels)} kernels of {len(calls)} C-ABI calls; {len(dev)} device kernels, {len(launch_t)} launch records seen]"
+    by_call = {}
+    for (idx, _, _), d in zip(eager_kernels, durs):
+        by_call[idx] = by_call.get(idx, 0.0) + d
+    return [(calls[i][0], calls[i][1], by_call.get(i, 0.0) * 1e-6) for i in range(len(calls))], how
+
+
 def run_ours(args, wl):
     import torch
     import xshinnosuke_b200 as xs
     from xshinnosuke_b200 import nn
     from xshinnosuke_b200._lib import lib
     from xshinnosuke_b200.core.device import rt
-    from xshinnosuke_b200.recipes import ResNet18
     from xshinnosuke_b200.utils import opcost
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     rt.ensure()
     xs.set_math_mode(args.math)
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        parity = parity_check(wl, args, xs, nn)
     dp = None
-    B, hw = wl["batch"], wl["hw"]
-    rs = np.random.RandomState(1000 + rank)
-    x_host = rs.rand(B, 3, hw, hw).astype(np.float32)
-    y_host = rs.randint(0, wl["classes"], (B,)).astype(np.int64)
+    B = wl["batch"]
+    x_host, y_host = synthetic_host_batch(wl, B, seed=1000 + rank)
     np.random.seed(0)   # identical initial weights on every rank
-    net = ResNet18(num_classes=wl["classes"])
-    opt = xs.optim.SGD(net.parameters(), lr=wl["lr"]) if wl["optimizer"] == "sgd" else \
-        xs.optim.Adam(net.parameters(), lr=wl["lr"])
-    crit = nn.CrossEntropyLoss()
+    eager_step, x_dev, y_dev, net, opt = build_workload(wl, xs, nn, x_host, y_host)
     if world > 1:
         from xshinnosuke_b200.parallel import DataParallel
         dp = DataParallel(net, opt, bucket_mb=args.bucket_mb)
-    x_dev, y_dev = xs.tensor(x_host), xs.tensor(y_host)
     x_pin = torch.from_numpy(x_host).pin_memory()
     y_pin = torch.from_numpy(y_host).pin_memory()
-
-    def step_resident():
-        opt.zero_grad()
-        loss = crit(net(x_dev), y_dev)
-        loss.backward()
-        opt.step()
-        return loss
-
-    def step_e2e():
-        # the call a user makes: host batch in, loss value out (resnet18_dg.py:93-100)
-        x, y = xs.tensor(x_pin.numpy()), xs.tensor(y_pin.numpy())
-        opt.zero_grad()
-        loss = crit(net(x), y)
-        loss.backward()
-        opt.step()
-        return loss.item()
 
     def barrier():
         if dp is not None:
@@ -250,19 +450,23 @@ def run_ours(args, wl):
         return ms
 
     use_graph = args.graph in ("on", "auto")   # NCCL bucket all-reduces are captured together with the kernels
-    eager_step = step_resident
-    graphed = None
+    step_resident, graphed = eager_step, None
+    xh, yh = x_pin.numpy(), y_pin.numpy()
     if use_graph:
         # the whole step replayed as one CUDA graph (same kernels, no Python between launches)
         graphed = xs.GraphedStep(eager_step, warmup=max(args.warmup, 3), inputs=(x_dev, y_dev))
         step_resident = graphed
-        xh, yh = x_pin.numpy(), y_pin.numpy()
         graphed.prefetch(xh, yh)
 
-        def step_e2e():  # noqa: F811 -- one H2D upload of a pinned host batch and one D2H loss read per step
+        def step_e2e():  # one H2D upload of a pinned host batch and one D2H loss read per step
             loss = graphed(xh, yh)       # staged batch -> captured inputs (device transpose), replay
             graphed.prefetch(xh, yh)     # the NEXT step's upload runs on a side stream under this replay
             return loss.item()
+    else:
+        def step_e2e():                  # the call a user makes: host batch in, loss value out
+            x_dev.eval = xh
+            y_dev.eval = yh
+            return eager_step().item()
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -277,99 +481,121 @@ def run_ours(args, wl):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
-    # ---- per-kernel CUDA-event profile (3 extra steps, same stream) for the roofline of the dominant kernel
-    prof = {}
-    if rank != 0 and dp is not None:
-        for _ in range(3):          # the profiled steps contain collectives: every rank must take part
-            eager_step()
-        torch.cuda.synchronize()
-    if rank == 0:
+    # ---- kernel table: time of every C-ABI call's kernels inside the graph replay (CUPTI), rank 0 of a 1-GPU run
+    records, how = [], None
+    if not args.no_kernel_table:
         lib.load()
-        names = [n for n in lib.protos if n.startswith("xsb_") and lib.protos[n][1] and
-                 n not in ("xsb_init", "xsb_stream_sync", "xsb_memcpy_h2d", "xsb_memcpy_d2h", "xsb_bn_workspace_floats")]
-        originals, records = {}, []
-        for n in names:
-            fn = getattr(lib, n)
-            originals[n] = fn
-
-            def wrapped(*a, _fn=fn, _n=n):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                r = _fn(*a)
-                e.record()
-                records.append((_n, a, s, e))
-                return r
-            setattr(lib, n, wrapped)
-        for _ in range(3):
-            eager_step()          # per-call events need the eager path (a graph replay is one opaque launch)
-        torch.cuda.synchronize()
-        for n, fn in originals.items():
-            setattr(lib, n, fn)
-        by_shape = {}
-        for n, a, s, e in records:
-            kind, amount = opcost.cost(n, a)
-            ms_ = s.elapsed_time(e)
-            d = prof.setdefault(n, dict(ms=0.0, calls=0, amount=0.0, kind=kind))
-            d["ms"] += ms_
-            d["calls"] += 1
-            d["amount"] += amount
-            d2 = by_shape.setdefault(signature(n, a), dict(ms=0.0, calls=0, amount=0.0, kind=kind, name=n))
-            d2["ms"] += ms_
-            d2["calls"] += 1
-            d2["amount"] += amount
+        try:
+            if world == 1:
+                records, how = kernel_timeline(eager_step, graphed, lib, torch)
+            elif rank == 0:          # N > 1: one eager step (it contains collectives: every rank takes part), no replay alignment
+                records, how = kernel_timeline(eager_step, None, lib, torch)
+            else:
+                eager_step()
+                torch.cuda.synchronize()
+        except Exception as e:       # profiler unavailable: the table is omitted, the headline numbers stand
+            how = f"unavailable ({type(e).__name__}: {e})"
     if rank != 0:
         return
 
     pk = peaks()
-    total_ms = sum(d["ms"] for d in prof.values()) or 1.0
-    # dominant kernel = the (entry point, shape) pair with the most device time: `achieved` is then a true
-    # per-launch figure (one shape), not an average over differently sized launches
-    tn, td = max(by_shape.items(), key=lambda kv: kv[1]["ms"])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(tn)
-    if td["kind"] == "flop":
-        achieved = td["amount"] / (td["ms"] * 1e-3) / 1e12
-        # kind::tf32 runs at half the bf16 rate; the FFMA (fp32) mode is still reported against the tensor peak
+    prof, by_shape = {}, {}
+    for n, a, sec in records:
+        kind, amount = opcost.cost(n, a)
+        for key, table in ((n, prof), (signature(n, a), by_shape)):
+            d = table.setdefault(key, dict(s=0.0, calls=0, amount=0.0, kind=kind, name=n))
+            d["s"] += sec
+            d["calls"] += 1
+            d["amount"] += amount
+    total_s = sum(d["s"] for d in prof.values())
+    ncu = {}
+    npath = os.path.join(ROOT, "profiles", "ncu_metrics.json")
+    if os.path.exists(npath):
+        ncu = json.load(open(npath))
+
+    def rate(d):
+        return d["amount"] / d["s"] / (1e12 if d["kind"] == "flop" else 1e9) if d["s"] > 0 else 0.0
+
+    def tensor_roofline(entries, label):
+        ds = [prof[e] for e in entries if e in prof]
+        if not ds or sum(d["s"] for d in ds) <= 0:
+            return None
+        sec, flop = sum(d["s"] for d in ds), sum(d["amount"] for d in ds)
+        achieved = flop / sec / 1e12
+        # the step is seconds-long back-to-back work for the part: the sustained bf16 figure is the denominator;
+        # kind::tf32 runs at half the bf16 rate -> frac_of_tf32_peak is the fraction of what these kernels can reach
         peak = pk["tc_sustained"]
-        roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
-                    frac_of_tf32_nominal=achieved / (peak / 2.0) if args.math == "tf32" else None,
-                    tf32_measured_peak=pk.get("tf32_sustained"),
-                    frac_of_tf32_measured=(achieved / pk["tf32_sustained"]) if (args.math == "tf32" and pk.get("tf32_sustained")) else None)
-    else:
-        achieved = td["amount"] / (td["ms"] * 1e-3) / 1e9
-        roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic)
-    roof.update(kernel=tn, calls_per_step=td["calls"] / 3.0, avg_launch_us=td["ms"] * 1e3 / td["calls"],
-                share_of_kernel_time=td["ms"] / total_ms, peak_source=pk["source"],
-                algorithmic_per_launch=td["amount"] / td["calls"],
-                note="peak = measured dense bf16 (sustained, kernel timed inside a long step); kind::tf32 runs at half "
-                     "the bf16 rate, see frac_of_tf32_nominal" if td["kind"] == "flop" else "")
-    per_kernel = {n: dict(share=round(d["ms"] / total_ms, 4), us_per_step=round(d["ms"] * 1e3 / 3.0, 1),
-                          calls_per_step=round(d["calls"] / 3.0, 1),
-                          achieved=round(d["amount"] / (d["ms"] * 1e-3) / (1e12 if d["kind"] == "flop" else 1e9), 2),
+        tf32 = args.math in ("tf32", "fp32x3")
+        r = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                 traffic=ncu.get(label, {}).get("dram_bytes_per_step"), kernel=label,
+                 us_per_step=sec * 1e6, share_of_kernel_time=sec / total_s if total_s else None,
+                 algorithmic_flop_per_step=flop, peak_source=pk["source"] + " (bf16 sustained)",
+                 frac_of_tf32_peak=achieved / (peak / 2.0) if tf32 else None,
+                 frac_of_bf16_burst=achieved / pk["tc_burst"],
+                 tf32_cublas_measured=pk.get("tf32_sustained"),
+                 frac_of_tf32_cublas_measured=achieved / pk["tf32_sustained"] if (tf32 and pk.get("tf32_sustained")) else None,
+                 pipe_tensor_active_pct=ncu.get(label, {}).get("pipe_tensor_active_pct"),
+                 by_entry={e: dict(tflops=round(rate(prof[e]), 1), us_per_step=round(prof[e]["s"] * 1e6, 1),
+                                   calls=prof[e]["calls"]) for e in entries if e in prof},
+                 note="achieved = algorithmic FLOPs of every convolution of the step / their summed kernel time in the graph "
+                      "replay; in fp32x3 mode each product is three tf32 MMAs (algorithmic FLOPs counted once)")
+        return r
+
+    def hbm_roofline():
+        hb = {n: d for n, d in prof.items() if d["kind"] == "byte" and d["s"] > 0}
+        if not hb:
+            return None
+        n, d = max(hb.items(), key=lambda kv: kv[1]["s"])
+        achieved = rate(d)
+        return dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
+                    traffic=ncu.get(n, {}).get("dram_bytes_per_step"), kernel=n + " (all shapes of the step)",
+                    us_per_step=d["s"] * 1e6, calls_per_step=d["calls"], share_of_kernel_time=d["s"] / total_s,
+                    algorithmic_bytes_per_step=d["amount"], peak_source=pk["source"] + " (HBM copy)")
+
+    roof_t = tensor_roofline([e for e in CONV_ENTRIES], "conv family (xsb_conv2d_fwd + dgrad + wgrad)")
+    if roof_t is None:
+        roof_t = tensor_roofline(["xsb_gemm"], "Dense products (xsb_gemm)")
+    roof_h = hbm_roofline()
+    t_share = (roof_t or {}).get("share_of_kernel_time") or 0.0
+    h_share = sum(d["s"] for d in prof.values() if d["kind"] == "byte") / total_s if total_s else 0.0
+    roofline, other = (roof_t, roof_h) if t_share >= 0.3 or roof_h is None else (roof_h, roof_t)
+    per_kernel = {n: dict(share=round(d["s"] / total_s, 4), us_per_step=round(d["s"] * 1e6, 1), calls_per_step=d["calls"],
+                          achieved=round(rate(d), 2), unit="TFLOP/s" if d["kind"] == "flop" else "GB/s")
+                  for n, d in sorted(prof.items(), key=lambda kv: -kv[1]["s"])} if total_s else {}
+    top_shapes = {k: dict(us_per_step=round(d["s"] * 1e6, 1), calls=d["calls"], achieved=round(rate(d), 1),
                           unit="TFLOP/s" if d["kind"] == "flop" else "GB/s")
-                  for n, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+                  for k, d in sorted(by_shape.items(), key=lambda kv: -kv[1]["s"])[:24]} if total_s else {}
 
     nparams = sum(p.numel() for p in net.parameters())
     value = B * world * args.steps / (ms * 1e-3)
     e2e_val = B * world * args.steps / (ms_e2e * 1e-3)
-    cpu = cpu_baseline_leg(wl) if (world == 1 and not args.no_cpu_baseline) else None
-    out = dict(metric="resnet18_train_images_per_sec", value=value, unit="images/s", n_gpus=world, steps=args.steps,
+    cpu = time_oracle(wl, budget_s=20.0, max_steps=200)[0] if (world == 1 and not args.no_cpu_baseline) else None
+    shape = "x".join(str(s) for s in x_host.shape[1:])
+    out = dict(metric=wl["metric"], value=value, unit="images/s", n_gpus=world, steps=args.steps,
                warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                vs_baseline=value / README_GPU_IMG_S if args.workload == "r56" else None,
-               dtype=args.math, data="synthetic",
-               config=dict(workload=wl["name"], global_batch=B * world, per_gpu_batch=B, image=f"3x{hw}x{hw}",
+               dtype={"tf32": "tf32", "fp32": "f32", "fp32x3": "f32 (3xTF32 split on tcgen05)"}[args.math], data="synthetic",
+               config=dict(workload=wl["name"], global_batch=B * world, per_gpu_batch=B, sample_shape=shape,
                            optimizer=wl["optimizer"], parallelism=f"dp{world}", params=nparams,
                            math_mode=args.math, cuda_graph=bool(use_graph),
-                           l2="no flush: per-step working set (activations + 2x45 MB params/grads) exceeds the 126 MB L2",
+                           l2="no flush: per-step working set (activations + parameters/gradients/moments) exceeds the 126 MB L2"
+                           if wl["kind"] == "resnet" else
+                           "no flush: the whole step is L2-resident by nature (launch-latency bound workload); the kernels "
+                           "of one step never re-read a buffer they did not just produce",
                            vs_baseline_ref="README.md:37-38 XS dynamic graph on CuPy, 265 img/s, unspecified GPU"),
                clocks=clocks, gpu_launches=launches,
                gpu_launches_unit="C-ABI entry calls of libxsb200.so in the timed region (a lower bound on kernels: a BatchNorm "
-                                 "backward is 2 launches, a strided dgrad one per parity class + the filter copy)",
+                                 "backward is 2 launches, a convolution may add a filter re-layout)",
                e2e=dict(value=e2e_val, unit="images/s", h2d_bytes_per_step=int(x_host.nbytes + y_host.nbytes),
                         d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
-               roofline=roof, kernels=per_kernel)
+               roofline=roofline, kernels=per_kernel)
+    if other is not None:
+        out["roofline_" + other["bound"]] = other
+    out["kernel_timing"] = dict(how=how, kernels_sum_ms=total_s * 1e3, ms_per_step=ms / args.steps,
+                                sum_over_step=(total_s * 1e3) / (ms / args.steps) if ms else None,
+                                hbm_bound_share=h_share, top_shapes=top_shapes)
+    if parity is not None:
+        out["parity_checked"] = parity
     if cpu is not None:
         out["cpu_baseline"] = cpu
     emit(out)
@@ -396,13 +622,15 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="r224", choices=sorted(WORKLOADS))
-    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32", "fp32x3"])
     ap.add_argument("--bucket-mb", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step (incl. the bucketed all-reduce) as one CUDA graph; auto = on")
     args = ap.parse_args()

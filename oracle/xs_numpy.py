@@ -24,6 +24,21 @@ def _pair(v):
     return (int(v), int(v)) if isinstance(v, (int, float)) else (int(v[0]), int(v[1]))
 
 
+# Checker-side model of the tf32 tensor-core mode (no reference counterpart): with TF32_OPERANDS = True every GEMM operand
+# (col / W / dY / x) is first rounded to fp32 and cut to tf32's 10 mantissa bits, as tcgen05 kind::tf32 reads fp32 data
+# (tools/tf32_probe.py: truncation); products and sums stay float64. "The reference's algorithm on tf32-truncated
+# operands" is what the GPU's tf32 mode must reproduce -- it separates kernel error from the amplification of the tf32
+# rounding itself by a deep, randomly initialised network (tools/parity_probe.py).
+TF32_OPERANDS = False
+
+
+def _gemm_in(a):
+    if not TF32_OPERANDS:
+        return a
+    f = np.ascontiguousarray(a, dtype=np.float32)
+    return (f.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+
+
 def conv_out_size(h, k, s, p):
     """xs/nn/functional.py:415-416 -- (H - k + 2p) // s + 1."""
     return (h - k + 2 * p) // s + 1
@@ -102,7 +117,7 @@ def conv2d_fwd(x, w, b=None, stride=(1, 1), padding=0):
     oh = conv_out_size(h, kh, stride[0], padding)
     ow = conv_out_size(wd, kw, stride[1], padding)
     col = unfold(_zero_pad(x, padding), oh, ow, kh, kw, stride)
-    flat = np.dot(col, w.reshape(oc, -1).T)
+    flat = np.dot(_gemm_in(col), _gemm_in(w.reshape(oc, -1)).T)
     if b is not None:
         flat = flat + b
     y = np.empty((n, oc, oh, ow), dtype=x.dtype)
@@ -119,11 +134,12 @@ def conv2d_bwd(dy, x_shape, w, col, stride=(1, 1), padding=0, need_dx=True):
     stride = _pair(stride)
     oc, c, kh, kw = w.shape
     g = dy.transpose(1, 0, 2, 3).reshape(oc, -1)
-    dw = np.dot(g, col).reshape(oc, c, kh, kw)
     db = np.sum(dy, axis=(0, 2, 3))
+    g = _gemm_in(g)
+    dw = np.dot(g, _gemm_in(col)).reshape(oc, c, kh, kw)
     # the dcol GEMM runs even when the input needs no gradient (grad_fn.py:199 sits
     # outside the `if`), only the col2im is skipped -- kept so CPU timings stay faithful
-    dcol = g.T.dot(w.reshape(oc, -1))
+    dcol = g.T.dot(_gemm_in(w.reshape(oc, -1)))
     dx = fold(x_shape, padding, kh, kw, stride, dcol) if need_dx else None
     return dx, dw, db
 
@@ -250,7 +266,7 @@ def batch_norm_bwd(dy, xhat, sqrtvar, gamma, axis=1):
 # --------------------------------------------------------------------------------------
 def addmm_fwd(b, x, w):
     """y = x . W + b with W [in,out] (NOT transposed), b [1,out]."""
-    return np.dot(x, w) + b
+    return np.dot(_gemm_in(x), _gemm_in(w)) + b
 
 
 def addmm_bwd(dy, x, w, b_shape):
@@ -258,7 +274,8 @@ def addmm_bwd(dy, x, w, b_shape):
     when N == 1 (grad_fn.py:89-95, Q12)."""
     mism = [k for k, v in enumerate(dy.shape) if v != b_shape[k]]
     db = np.sum(dy, axis=mism[0]) if mism else dy
-    return np.dot(dy, w.T), np.dot(x.T, dy), db
+    g = _gemm_in(dy)
+    return np.dot(g, _gemm_in(w).T), np.dot(_gemm_in(x).T, g), db
 
 
 def mm_bwd(dy, x, w):

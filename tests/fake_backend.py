@@ -251,6 +251,19 @@ class FakeLib:
                              b, (sh, sw), pad)
         f32(y, yv.size)[...] = yv.transpose(0, 2, 3, 1).reshape(-1)
 
+    def _conv2d_fwd_acc(self, x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, acc, mode, ws, wsn, s):
+        OH, OW = (H - KH + 2 * pad) // sh + 1, (W - KW + 2 * pad) // sw + 1
+        old = f32(y, N * OH * OW * OC).astype(np.float64).copy() if acc else 0.0
+        self._conv2d_fwd(x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, s)
+        if acc:
+            f32(y, N * OH * OW * OC)[...] = f32(y, N * OH * OW * OC).astype(np.float64) + old
+
+    def _split_tf32(self, x, hi, lo, n, s):
+        v = f32(x, n)
+        h = (v.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        f32(hi, n)[...] = h
+        f32(lo, n)[...] = v - h
+
     def _conv2d_fwd_stats(self, x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, stats, stats_n,
                           n_partials, s):
         # contract: y as xsb_conv2d_fwd; stats[p][{n, mean, M2}][OC] partials (two here, split over the rows)
@@ -364,7 +377,8 @@ def install(monkeypatch=None):
     import xshinnosuke_b200.nn.grad_fn as G
     import xshinnosuke_b200.optim.optimizer as O
     import xshinnosuke_b200.layers.graph_ops as GO
-    targets += [F, G, O, GO]
+    import xshinnosuke_b200.nn.x3 as X3
+    targets += [F, G, O, GO, X3]
     try:
         import xshinnosuke_b200.parallel as P
         targets.append(P)

@@ -62,6 +62,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--layers", default="")
     ap.add_argument("--json", default="")
+    ap.add_argument("--sweep", default="", choices=["", "small", "full"],
+                    help="BASELINE.json configs[2]: conv fwd/dgrad/wgrad and max-pool over N=32-256 x C=3-512 x 32-224 px x "
+                         "k=1/3/7 ('small' = one batch size per shape class, 'full' = the whole grid that fits 8 GB per tensor)")
     ap.add_argument("--pers", type=int, default=-1,
                     help="xsb_tc_config(2, v): 0 = per-tile im2col kernels only, 1 = persistent kernel for strided dgrads "
                          "(default), 2 = persistent kernel for every im2col forward / dgrad")
@@ -117,8 +120,23 @@ def main():
         print(f"cpu_ref      {lname:10s} NumPy f64, {n} images: conv fwd {row['conv_fwd_gflops']:7.1f} GFLOP/s, "
               f"conv bwd {row['conv_bwd_gflops']:7.1f} GFLOP/s, BN fwd {row['bn_fwd_gbs']:6.2f} GB/s", flush=True)
 
-    sel = [l for l in LAYERS[a.shapes] if not a.layers or l[0] in a.layers.split(",")]
-    for (lname, C, H, OC, k, s, p) in sel:
+    sel = [l + (N,) for l in LAYERS[a.shapes] if not a.layers or l[0] in a.layers.split(",")]
+    if a.sweep:
+        # configs[2]: N x C x H x k grid (stride 1 for k = 1 / 3, stride 2 for k = 7 as in the stem; pad = k // 2; OC = max(64, C))
+        sel = []
+        for n_ in ((32, 64, 128, 256) if a.sweep == "full" else (64,)):
+            for C_ in (3, 64, 128, 256, 512):
+                for H_ in (32, 56, 112, 224):
+                    for k_ in (1, 3, 7):
+                        OC_ = max(64, C_)
+                        s_ = 2 if k_ == 7 else 1
+                        OH_ = (H_ - k_ + 2 * (k_ // 2)) // s_ + 1
+                        big = 4.0 * n_ * max(H_ * H_ * C_, OH_ * OH_ * OC_)
+                        if big > (8e9 if a.sweep == "full" else 2e9) or (C_ == 3 and k_ == 1):
+                            continue
+                        sel.append((f"N{n_}C{C_}H{H_}k{k_}", C_, H_, OC_, k_, s_, k_ // 2, n_))
+        ops = [o for o in ops if o in ("conv_fwd", "conv_dgrad", "conv_wgrad", "maxpool_fwd", "maxpool_bwd")]
+    for (lname, C, H, OC, k, s, p, N) in sel:
         OH = (H - k + 2 * p) // s + 1
         x, w, b = dev(N, H, H, C), dev(OC, k, k, C) * 0.1, dev(OC)
         y, dy = dev(N, OH, OH, OC), dev(N, OH, OH, OC)
@@ -129,7 +147,7 @@ def main():
         if "conv_fwd" in ops:
             args = (x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr()) + g + (mode, ws, wsn, st)
             report("conv_fwd", lname, "xsb_conv2d_fwd", args, timed(lambda: lib.xsb_conv2d_fwd(*args), a.iters))
-        if "conv_dgrad" in ops and C >= 32:
+        if "conv_dgrad" in ops and C >= 32:   # (the first layer's input needs no gradient)
             args = (dy.data_ptr(), w.data_ptr(), dx.data_ptr()) + g + (0, mode, ws, wsn, st)
             report("conv_dgrad", lname, "xsb_conv2d_dgrad", args, timed(lambda: lib.xsb_conv2d_dgrad(*args), a.iters))
         if "conv_wgrad" in ops:
@@ -161,7 +179,20 @@ def main():
         if "add" in ops:
             args = (y.data_ptr(), dy.data_ptr(), y.data_ptr(), n, st)
             report("add", lname, "xsb_add", args, timed(lambda: lib.xsb_add(*args), a.iters), note)
-        if lname == "stem" and ("maxpool_fwd" in ops or "maxpool_bwd" in ops):
+        if a.sweep and k == 3 and C >= 64 and ("maxpool_fwd" in ops or "maxpool_bwd" in ops):
+            for pk_, pp_ in ((2, 0), (3, 1)):          # max-pool k in {2, 3}, stride 2, pad in {0, 1} on the INPUT tensor
+                PH = (H + 2 * pp_ - pk_) // 2 + 1
+                py, am = dev(N, PH, PH, C), torch.zeros(N * PH * PH * C, dtype=torch.uint8, device=rt.device)
+                xr = torch.relu(x)
+                args = (xr.data_ptr(), py.data_ptr(), am.data_ptr(), N, H, H, C, pk_, 2, 2, pp_, st)
+                if "maxpool_fwd" in ops:
+                    report("maxpool_fwd", f"{lname}p{pk_}", "xsb_maxpool2d_fwd", args, timed(lambda: lib.xsb_maxpool2d_fwd(*args), a.iters))
+                lib.xsb_maxpool2d_fwd(*args)
+                args2 = (py.data_ptr(), am.data_ptr(), dx.data_ptr(), N, H, H, C, pk_, 2, 2, pp_, 0, st)
+                if "maxpool_bwd" in ops:
+                    report("maxpool_bwd", f"{lname}p{pk_}", "xsb_maxpool2d_bwd", args2, timed(lambda: lib.xsb_maxpool2d_bwd(*args2), a.iters))
+                del py, am, xr
+        if not a.sweep and lname == "stem" and ("maxpool_fwd" in ops or "maxpool_bwd" in ops):
             PH = (OH + 2 - 3) // 2 + 1
             py, am = dev(N, PH, PH, OC), torch.zeros(N * PH * PH * OC, dtype=torch.uint8, device=rt.device)
             yr = torch.relu(y)

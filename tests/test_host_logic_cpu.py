@@ -92,3 +92,41 @@ def test_resnet18_small(golden):
 
 def test_fit_static_graph(golden):
     S.check_fit_configs(golden, 1e-6)
+
+
+def test_fp32x3_mode_host_logic(golden):
+    """fp32x3 math mode (nn/x3.py): every GEMM-shaped op inside the tensor-core envelope is issued as the three accumulating
+    products of the hi/lo operand split (split, lo.hi, hi.lo, hi.hi+bias), the others as one fp32 call; results stay the
+    reference's (the fake kernels are exact, so the split must reassemble x.w to fp32 rounding)."""
+    import numpy as np
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    xs.set_math_mode("fp32x3")
+    try:
+        rs = np.random.RandomState(5)
+        x = rs.randn(2, 64, 6, 6).astype(np.float32)
+        w = (rs.randn(64, 64, 3, 3) * 0.1).astype(np.float32)
+        b = rs.randn(1, 64).astype(np.float32)
+        tx, tw, tb = xs.tensor(x, requires_grad=True), nn.Parameter(w), nn.Parameter(b)
+        fake = fake_backend.install()
+        del fake.calls[:]
+        y = F.conv2d(tx, tw, tb, (1, 1), 1)
+        yr, col = X.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (1, 1), 1)
+        assert X.rel_err(y.eval, yr) <= 1e-6
+        assert fake.calls.count("xsb_conv2d_fwd_acc") == 3 and fake.calls.count("xsb_split_tf32") == 2
+        g = rs.randn(*yr.shape).astype(np.float32)
+        y.backward(gradients=g)
+        dx, dw, db = X.conv2d_bwd(g.astype(np.float64), x.shape, w.astype(np.float64), col, (1, 1), 1)
+        assert X.rel_err(tx.grad.eval, dx) <= 1e-6 and X.rel_err(tw.grad.eval, dw) <= 1e-6
+        assert fake.calls.count("xsb_conv2d_wgrad") == 3 and fake.calls.count("xsb_conv2d_dgrad") == 3
+        # outside the envelope (20 channels): ONE fp32 call, no split
+        del fake.calls[:]
+        x2 = rs.randn(2, 20, 5, 5).astype(np.float32)
+        w2 = (rs.randn(12, 20, 3, 3) * 0.1).astype(np.float32)
+        y2 = F.conv2d(xs.tensor(x2), nn.Parameter(w2), None, (1, 1), 1)
+        y2.eval
+        assert fake.calls.count("xsb_conv2d_fwd") == 1 and "xsb_split_tf32" not in fake.calls
+    finally:
+        xs.set_math_mode("fp32")

@@ -168,3 +168,21 @@ def test_resnet18_n32_recorded(golden):
     # the recipe of BASELINE.md section 4, as the reference actually evaluates it in this container
     np.testing.assert_allclose(c["losses"], [6.642040132035239, 0.836408809753542, 0.020209142234972645], rtol=1e-12)
     assert c["nparams"].tolist() == [11232612, 82]
+
+
+def test_small_net_oracles_reproduce_the_reference_fit_trajectories(golden):
+    """oracle/small_nets.py (BASELINE configs[0], [1]; the CPU arm of bench.py --workload cnn|mlp) against the losses the
+    unmodified reference's Model.fit / Sequential.fit produced (tests/golden/make_golden.py gen_fit_configs)."""
+    from oracle.small_nets import ReadmeCNN, ReadmeMLP
+    np.random.seed(0)
+    xd, yd = np.random.rand(96, 1, 28, 28), np.random.randint(0, 10, (96,))
+    np.random.seed(1)
+    net = ReadmeCNN()
+    losses = [net.train_step(xd[i:i + 32], yd[i:i + 32], 0.01) for _ in range(2) for i in range(0, 96, 32)]
+    np.testing.assert_allclose(losses, golden.case("fit/cnn")["losses"], rtol=1e-12)
+    np.random.seed(0)
+    xd, yd = np.random.rand(80, 784), np.random.randint(0, 10, (80,))
+    np.random.seed(1)
+    net = ReadmeMLP()
+    losses = [net.train_step(xd[i:i + 32], yd[i:i + 32], 0.05) for _ in range(2) for i in range(0, 80, 32)]
+    np.testing.assert_allclose(losses, golden.case("fit/mlp")["losses"], rtol=1e-12)

@@ -13,60 +13,60 @@ from . import state as GLOBAL
 from .tensor import Parameter
 
 
-def backward(outputs, inputs, retain_graph=False):
-    graph = topological_sort(inputs, outputs)
-    hook = GLOBAL.AFTER_NODE_BACKWARD
-    for node in reversed(graph):
-        if node.grad_fn is not None:
-            node.grad_fn(node)
-            if hook is not None:
-                hook(node)
-        for layer in node.next_layers:
-            layer.data = None
-        if retain_graph or node.is_leaf or node.retain_grad():
-            node.reset_(requires_grad=node.requires_grad, name=node.name, slices=node.slices(),
-                        static_graph_tensor=node.is_static, retain_grad=node.retain_grad(), grad=node.grad)
-        else:
-            node.free_memory()
-            node.reset_(requires_grad=node.requires_grad, name=node.name, slices=node.slices(),
-                        static_graph_tensor=node.is_static)
-    if retain_graph:
-        GLOBAL.GRAPH = graph
+def _recycle(node, keep):
+    """Return a visited node to its pre-forward state. `keep` (leaf, retain_grad or retain_graph): payload and gradient
+    survive; otherwise both go back to the caching device allocator right here, inside the backward walk."""
+    state = dict(requires_grad=node.requires_grad, name=node.name, slices=node.slices(), static_graph_tensor=node.is_static)
+    if keep:
+        state.update(retain_grad=node.retain_grad(), grad=node.grad)
     else:
-        del graph[:]
-        GLOBAL.INPUTS = None
-        GLOBAL.OUTPUTS = None
-        GLOBAL.GRAPH = None
+        node.free_memory()
+    node.reset_(**state)
+
+
+def backward(outputs, inputs, retain_graph=False):
+    order = topological_sort(inputs, outputs)
+    if GLOBAL.BEFORE_BACKWARD is not None:
+        GLOBAL.BEFORE_BACKWARD()
+    after_node = GLOBAL.AFTER_NODE_BACKWARD
+    for node in reversed(order):                       # loss first, inputs last
+        closure = node.grad_fn
+        if closure is not None:
+            closure(node)                              # accumulates into the gradients of node.in_bounds
+            if after_node is not None:
+                after_node(node)
+        for layer in node.next_layers:                 # layers that consumed this tensor drop their handle on it
+            layer.data = None
+        _recycle(node, keep=retain_graph or node.is_leaf or node.retain_grad())
+    if retain_graph:
+        GLOBAL.GRAPH = order
+    else:
+        reset_graph(order)
 
 
 def topological_sort(ins, outs):
-    """Post-order DFS (iterative: ResNet graphs are deeper than the default recursion limit allows
-    once Python frames of closures are added)."""
-    topo, visited = [], set()
-    stack = [(outs, iter(()), False)]
-    # emulate the reference's recursion exactly: a node is appended after all its children
+    """Post-order depth-first walk from the loss through `in_bounds` (a node is listed after everything it was computed
+    from; Parameters and None are not descended into; the walk stops at `ins`). Iterative with an explicit stack of
+    (node, iterator over its operands): ResNet graphs are deeper than Python's recursion limit allows."""
+    order, seen = [], set()
     stack = [(outs, None)]
     while stack:
-        v, it = stack.pop()
-        if it is None:
-            if ins is not None and v is ins:
-                topo.append(v)
+        node, operands = stack.pop()
+        if operands is None:                           # first visit
+            if ins is not None and node is ins:
+                order.append(node)
                 continue
-            if id(v) in visited:
+            if id(node) in seen:
                 continue
-            visited.add(id(v))
-            it = iter(v.in_bounds)
-        advanced = False
-        for child in it:
-            if child is None or isinstance(child, Parameter):
-                continue
-            stack.append((v, it))
+            seen.add(id(node))
+            operands = iter(node.in_bounds)
+        child = next((c for c in operands if c is not None and not isinstance(c, Parameter)), None)
+        if child is None:
+            order.append(node)                         # all operands done
+        else:
+            stack.append((node, operands))             # come back for the remaining operands
             stack.append((child, None))
-            advanced = True
-            break
-        if not advanced:
-            topo.append(v)
-    return topo
+    return order
 
 
 def reset_graph(graph):

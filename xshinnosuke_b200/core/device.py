@@ -89,14 +89,19 @@ class Runtime:
 rt = Runtime()
 
 
+MATH_FP32X3 = 2   # host-level composition of XSB_MATH_TF32 calls (nn/x3.py); never passed to the C ABI
+
+
 def set_math_mode(mode):
-    """'fp32' (CUDA-core FFMA, <=1e-5 vs the reference) or 'tf32' (tcgen05 tensor cores, <=2e-3)."""
-    m = {"fp32": MATH_FP32, "tf32": MATH_TF32, MATH_FP32: MATH_FP32, MATH_TF32: MATH_TF32}[mode]
+    """'fp32' (CUDA-core FFMA, <=1e-5 vs the reference), 'tf32' (tcgen05 tensor cores, <=2e-3) or 'fp32x3' (tcgen05 with
+    the 3xTF32 operand split, <=1e-5: nn/x3.py)."""
+    m = {"fp32": MATH_FP32, "tf32": MATH_TF32, "fp32x3": MATH_FP32X3, MATH_FP32: MATH_FP32, MATH_TF32: MATH_TF32,
+         MATH_FP32X3: MATH_FP32X3}[mode]
     rt.math_mode = m
 
 
 def get_math_mode():
-    return "fp32" if rt.math_mode == MATH_FP32 else "tf32"
+    return {MATH_FP32: "fp32", MATH_TF32: "tf32", MATH_FP32X3: "fp32x3"}[rt.math_mode]
 
 
 def _prod(shape):

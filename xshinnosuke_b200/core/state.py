@@ -11,5 +11,7 @@ IS_TRAINING = True      # written by train()/eval(); like the reference, ops rea
 COMPUTE_GRAD = True
 USE_CUDA = True         # always: this backend has no host compute path
 
-# data-parallel hook: called by core.autograd.backward after every node's closure ran
+# data-parallel hooks: called by core.autograd.backward / Model.backward before the first closure of a backward pass
+# and after every node's closure ran
+BEFORE_BACKWARD = None
 AFTER_NODE_BACKWARD = None

@@ -1116,7 +1116,7 @@ static int stem_prepare(const float* x, const ConvGeom& g, const StemPlan& pl, f
 }
 
 static int stem_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                    int64_t ws_floats, cudaStream_t s, StatsReq* st) {
+                    int64_t ws_floats, cudaStream_t s, StatsReq* st, int accumulate) {
     const StemPlan pl = stem_plan(g);
     if (!ws || ws_floats < pl.xp_floats + pl.wq_floats) return XSB_ERR_UNSUPPORTED;
     if ((g.OC != 64 && g.OC != 128) || g.KH > HALO_MAX_KH) return XSB_ERR_UNSUPPORTED;
@@ -1145,7 +1145,7 @@ static int stem_fwd(const float* x, const float* w, const float* bias, float* y,
     p.tiles_w = (g.OW + HALO_TW - 1) / HALO_TW; p.tiles_h = (g.OH + HALO_TH - 1) / HALO_TH;
     p.n_tiles = g.N * p.tiles_w * p.tiles_h;
     p.cblocks = 1; p.KWl = 1; p.KH = g.KH; p.sh = g.sh; p.pad_w = 0; p.bt_kh_stride = 1; p.h_off = 0;
-    p.stage_bytes = rows * 1024; p.tx_bytes = rows * 1024; p.n_stages = stages; p.n_btiles = g.KH; p.accumulate = 0;
+    p.stage_bytes = rows * 1024; p.tx_bytes = rows * 1024; p.n_stages = stages; p.n_btiles = g.KH; p.accumulate = accumulate;
     halo_attach_stats(p, st);
     return g.OC == 64 ? launch_halo<64>(ta, tb, p, s) : launch_halo<128>(ta, tb, p, s);
 }
@@ -1236,22 +1236,23 @@ static int counted(int rc) {
 }
 
 static int tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                       int64_t ws_floats, cudaStream_t s, StatsReq* st) {
-    if (stem_ok(g) && aligned16(x) && aligned16(w) && aligned16(y)) return stem_fwd(x, w, bias, y, g, ws, ws_floats, s, st);
+                       int64_t ws_floats, cudaStream_t s, StatsReq* st, int accumulate) {
+    if (stem_ok(g) && aligned16(x) && aligned16(w) && aligned16(y))
+        return stem_fwd(x, w, bias, y, g, ws, ws_floats, s, st, accumulate);
     if (!fprop_ok(g.C, g.OC, x, w, y) || g.KW > 255 || g.KH > 255) return XSB_ERR_UNSUPPORTED;
     if (g.sh == 1 && g.sw == 1 && halo_enabled()) {
-        const int rc = halo_conv_s1(x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.pad, g.pad, g.OH, g.OW, bias, y, 0, s, st);
+        const int rc = halo_conv_s1(x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.pad, g.pad, g.OH, g.OW, bias, y, accumulate, s, st);
         if (rc != XSB_ERR_UNSUPPORTED) return rc;
     }
     const int64_t m_tiles = ((int64_t)g.N * g.OH * g.OW + BM - 1) / BM;
     if (pers_mode() >= 2) {
         const PersJobDesc jd{w, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, 0, 0};
         const bool want_stats = st && st->buf && st->floats >= m_tiles * 3 * g.OC;
-        const int rc = pers_dispatch(x, g.N, g.H, g.W, g.C, g.OC, &jd, 1, bias, y, 0, 0, 0, 0, 1, 1,
+        const int rc = pers_dispatch(x, g.N, g.H, g.W, g.C, g.OC, &jd, 1, bias, y, accumulate, 0, 0, 0, 1, 1,
                                      want_stats ? st->buf : nullptr, want_stats ? st->n_partials : nullptr, s);
         if (rc != XSB_ERR_UNSUPPORTED) return rc;
     }
-    FpropJob j{x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, bias, y, 0,
+    FpropJob j{x, g.N, g.H, g.W, g.C, w, g.OC, g.KH, g.KW, g.sh, g.sw, g.pad, g.pad, g.OH, g.OW, bias, y, accumulate,
                0, 0, 0, 1, 1, 0, 0, nullptr, nullptr};
     if (st && st->buf && st->floats >= m_tiles * 3 * g.OC) {
         j.stats = st->buf;
@@ -1260,10 +1261,12 @@ static int tc_conv_fwd(const float* x, const float* w, const float* bias, float*
     return fprop_dispatch(j, s);
 }
 
+// accumulate = 1: y += conv(x, w) (+ bias) -- the later passes of the 3xTF32 split (XSB_MATH_FP32X3); statistics describe
+// the pass's own contribution, so callers ask for them only with accumulate = 0
 int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                    int64_t ws_floats, cudaStream_t s, float* stats, int64_t stats_floats, int* n_partials) {
+                    int64_t ws_floats, cudaStream_t s, float* stats, int64_t stats_floats, int* n_partials, int accumulate) {
     StatsReq st{stats, stats_floats, n_partials};
-    return counted(tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, stats ? &st : nullptr));
+    return counted(tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, (stats && !accumulate) ? &st : nullptr, accumulate));
 }
 
 static int tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,

@@ -187,6 +187,32 @@ __global__ void axpy_scalar(float* dst, const float* src, float alpha, int64_t n
     if (i < n) dst[i] += alpha * src[i];
 }
 
+// 3xTF32 split: hi = x with the 13 low mantissa bits cleared (exactly representable in tf32, so tcgen05 kind::tf32 reads it
+// unchanged whatever its fp32 -> tf32 reduction is), lo = x - hi (exact in fp32). Roofline: HBM, 3e*n.
+__global__ void __launch_bounds__(256) split_tf32_vec(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
+                                                      int64_t n4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        const float4 v = ldg_stream(x + i);
+        float4 h;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        stg_stream(hi + i, h);
+        stg_stream(lo + i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+    }
+}
+__global__ void split_tf32_scalar(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float h = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = x[i] - h;
+    }
+}
+
 __global__ void fill_k(float* dst, float v, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -366,6 +392,20 @@ int xsb_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream)
         axpy_vec<<<vec_blocks(n / 4), kThreads, 0, s>>>((float4*)dst, (const float4*)src, alpha, n / 4);
     else
         axpy_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(dst, src, alpha, n);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+int xsb_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+    if (n <= 0) return XSB_OK;
+    cudaStream_t s = xsb_stream(stream);
+    if (n % 4 == 0 && aligned16(x) && aligned16(hi) && aligned16(lo)) {
+        const int64_t n4 = n / 4;
+        const unsigned blocks = (unsigned)(ceil_div64(n4, 256) < 148 * 16 ? ceil_div64(n4, 256) : 148 * 16);
+        split_tf32_vec<<<blocks, 256, 0, s>>>((const float4*)x, (float4*)hi, (float4*)lo, n4);
+    } else {
+        split_tf32_scalar<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(x, hi, lo, n);
+    }
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

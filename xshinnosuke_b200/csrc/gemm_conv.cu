@@ -18,7 +18,7 @@ using namespace igemm;
 int xsb_tc_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
                 int transB, int accumulate, float* ws, int64_t ws_floats, cudaStream_t s);
 int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
-                    int64_t ws_floats, cudaStream_t s, float* stats, int64_t stats_floats, int* n_partials);
+                    int64_t ws_floats, cudaStream_t s, float* stats, int64_t stats_floats, int* n_partials, int accumulate);
 int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
                       int64_t ws_floats, cudaStream_t s);
 int xsb_tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
@@ -91,7 +91,7 @@ int xsb_conv2d_fwd_stats(const float* x, const float* w, const float* bias, floa
     XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_fwd: bad geometry");
     cudaStream_t s = xsb_stream(stream);
     if (n_partials) *n_partials = 0;
-    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, stats, stats_floats, n_partials));
+    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, stats, stats_floats, n_partials, 0));
     if (n_partials) *n_partials = 0;
     const int P = N * g.OH * g.OW, J = KH * KW * C;
     PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
@@ -106,11 +106,26 @@ int xsb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
     ConvGeom g;
     XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_fwd: bad geometry");
     cudaStream_t s = xsb_stream(stream);
-    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, nullptr, 0, nullptr));
+    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, nullptr, 0, nullptr, 0));
     const int P = N * g.OH * g.OW, J = KH * KW * C;
     PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
     MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};
     return launch(la, lb, y, OC, bias, P, OC, J, 0, true, ws, ws_floats, s);
+}
+
+// y (+)= conv(x, w) (+ bias): the forward convolution with the gradient kernels' accumulate flag. One product of the
+// 3xTF32 split of the fp32x3 math mode (x = x_hi + x_lo, w = w_hi + w_lo; y = x_lo*w_hi + x_hi*w_lo + x_hi*w_hi) is one call.
+int xsb_conv2d_fwd_acc(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int C, int OC,
+                       int KH, int KW, int sh, int sw, int pad, int accumulate, int math_mode, float* ws, int64_t ws_floats,
+                       void* stream) {
+    ConvGeom g;
+    XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad), "conv2d_fwd_acc: bad geometry");
+    cudaStream_t s = xsb_stream(stream);
+    XSB_TRY_TC(xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, nullptr, 0, nullptr, accumulate));
+    const int P = N * g.OH * g.OW, J = KH * KW * C;
+    PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
+    MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};
+    return launch(la, lb, y, OC, bias, P, OC, J, accumulate, true, ws, ws_floats, s);
 }
 
 // dx[N,H,W,C] (+)= sum_{kh,kw,oc} dy[n,(h+p-kh)/sh,(w+p-kw)/sw,oc] * w[oc,kh,kw,c]

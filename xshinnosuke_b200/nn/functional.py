@@ -16,6 +16,7 @@ from ..core.device import DevArray, rt
 from ..core.tensor import Parameter, Tensor
 from ..utils.common import initialize_ops_grad, pair
 from .._lib import lib
+from . import x3
 from .grad_fn import (AddBackward, AddmmBackward, Avgpool2DBackward, BatchNormBackward, Conv2DBackward,
                       CrossEntropyLossBackward, FlattenBackward, Maxpool2DBackward, MeanBackward, MMBackward,
                       MSELossBackward, ReLUBackward, SumBackward, ViewBackward)
@@ -109,8 +110,12 @@ def add(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
 def _gemm_fwd(x, w, bias, y):
     m, k = x.shape
     n = w.shape[-1]
-    lib.xsb_gemm(x.ptr, w.ptr, y.wptr, bias.ptr if bias is not None else None, m, n, k, 0, 0, 0, rt.math_mode,
-                 rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream())
+    bptr = bias.ptr if bias is not None else None
+    if rt.math_mode == x3.MATH_FP32X3 and x3.gemm_ok(k, n):
+        x3.gemm(x.ptr, m * k, w.ptr, k * n, y.wptr, bptr, m, n, k, 0, 0, 0)
+        return
+    lib.xsb_gemm(x.ptr, w.ptr, y.wptr, bptr, m, n, k, 0, 0, 0, x3.c_mode(False), rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS,
+                 rt.stream())
     rt.launches += 1
 
 
@@ -270,8 +275,16 @@ def conv2d(inputs: Tensor, weight: Tensor, bias: Tensor = None, stride=(1, 1), p
     def run(mask=None, stats=False, _x=x, _w=w):
         # deferred by one op: a BatchNorm that consumes y asks for `stats` and the conv epilogue gathers the
         # per-channel (count, mean, M2) partials on the way out -> no statistics pass over y (returns #partials)
+        if rt.math_mode == x3.MATH_FP32X3 and x3.conv_ok(c, oc):
+            # 3xTF32: three accumulating tcgen05 passes; the x split is kept for the weight gradient
+            xparts = x3.split(_x.ptr, _x.size)
+            if GLOBAL.COMPUTE_GRAD and weight.requires_grad:
+                out.cache["x3_x"] = xparts
+            x3.conv_fwd(xparts, x3.split(_w.ptr, _w.size), barr.ptr if barr is not None else None, ybuf.data_ptr(),
+                        (n, h, wd, c, oc, kh, kw, sh, sw, padding))
+            return 0                    # (statistics of a partial sum are useless: the BatchNorm runs its own pass)
         args = (_x.ptr, _w.ptr, barr.ptr if barr is not None else None, ybuf.data_ptr(), n, h, wd, c, oc, kh, kw, sh, sw,
-                padding, rt.math_mode, rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS)
+                padding, x3.c_mode(False), rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS)
         rt.launches += 1
         if not stats:
             lib.xsb_conv2d_fwd(*args, rt.stream())

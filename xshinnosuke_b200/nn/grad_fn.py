@@ -45,6 +45,7 @@ def accumulate_into(t, src):
     else:
         src.flush()
         g.buf[: g.size].copy_(src.buf[: g.size])   # first write: a plain device-to-device copy
+    _done(t)
 
 
 def accumulate_rowmajor_into(t, src_rm):
@@ -81,6 +82,7 @@ def AddBackward(outputs: Tensor, relu_mask=None):
                     continue
                 lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), g.peek_ptr(), g.size, g.take_acc(), rt.stream())
                 rt.launches += 1
+                _done(t)
             return
         lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), dy.peek_ptr(), dy.size, 0, rt.stream())
         rt.launches += 1
@@ -144,7 +146,11 @@ SumBackward = MeanBackward
 
 # ------------------------------------------------------------------ Dense
 def _gemm(a, b, c_arr, bias, M, N, K, ta, tb, acc):
-    lib.xsb_gemm(a, b, c_arr, bias, M, N, K, ta, tb, acc, rt.math_mode, rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS,
+    from . import x3
+    if rt.math_mode == x3.MATH_FP32X3 and x3.gemm_ok(M if ta else K, K if tb else N, N):
+        x3.gemm(a, M * K, b, K * N, c_arr, bias, M, N, K, ta, tb, acc)
+        return
+    lib.xsb_gemm(a, b, c_arr, bias, M, N, K, ta, tb, acc, x3.c_mode(False), rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS,
                  rt.stream())
     rt.launches += 1
 
@@ -196,11 +202,21 @@ def Conv2DBackward(outputs: Tensor):
     oc, _, kh, kw = weight.shape
     (sh, sw), pad = outputs.cache["stride"], outputs.cache["padding"]
     ws, wsn, st = rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream()
+    from . import x3
+    geom = (n, h, w, c, oc, kh, kw, sh, sw, pad)
+    split_mode = rt.math_mode == x3.MATH_FP32X3
+    mode = x3.c_mode(False)
+    xparts = outputs.cache.pop("x3_x", None)
+    dyparts = None
     if weight.requires_grad:
         g = _grad_arr(weight)
-        lib.xsb_conv2d_wgrad(dy.ptr, x.ptr, g.peek_ptr(), n, h, w, c, oc, kh, kw, sh, sw, pad, g.take_acc(),
-                             rt.math_mode, ws, wsn, st)
-        rt.launches += 1
+        if split_mode and x3.conv_ok(c, oc):
+            dyparts = x3.split(dy.ptr, dy.size)
+            x3.conv_wgrad(dyparts, xparts if xparts is not None else x3.split(x.ptr, x.size), g.peek_ptr(), geom, g.take_acc())
+        else:
+            lib.xsb_conv2d_wgrad(dy.ptr, x.ptr, g.peek_ptr(), *geom, g.take_acc(), mode, ws, wsn, st)
+            rt.launches += 1
+        del xparts
         _done(weight)
     if bias is not None and bias.requires_grad:
         if outputs.cache.pop("bias_grad_done", False):
@@ -214,11 +230,16 @@ def Conv2DBackward(outputs: Tensor):
         g = _grad_arr(inputs)
         assert g.cl, "conv input gradient must be channels-last"
         dy_ptr, w_ptr = dy.ptr, weight.arr.ptr
+        if split_mode and x3.dgrad_ok(c, oc, kh, kw, sh, sw):
+            dyparts = dyparts if dyparts is not None else x3.split(dy_ptr, dy.size)
+            wparts = x3.split(w_ptr, weight.arr.size)
 
-        def dgrad(acc, _keep=(dy.buf, weight.arr.buf)):      # the buffers stay alive while the kernel is postponed
-            lib.xsb_conv2d_dgrad(dy_ptr, w_ptr, g.peek_ptr(), n, h, w, c, oc, kh, kw, sh, sw, pad, acc, rt.math_mode, ws,
-                                 wsn, st)
-            rt.launches += 1
+            def dgrad(acc, _keep=(dy.buf, weight.arr.buf)):
+                x3.conv_dgrad(dyparts, wparts, g.peek_ptr(), geom, acc)
+        else:
+            def dgrad(acc, _keep=(dy.buf, weight.arr.buf)):      # the buffers stay alive while the kernel is postponed
+                lib.xsb_conv2d_dgrad(dy_ptr, w_ptr, g.peek_ptr(), *geom, acc, mode, ws, wsn, st)
+                rt.launches += 1
 
         # a filter smaller than its stride (the 1x1/2 shortcut) reaches only some parity classes of dX: postponed until
         # dX is read, so that the other branch of the block writes "=" and this one only adds (see DevArray.defer_add)

@@ -163,6 +163,8 @@ class _Model(_Base):
         if loss.grad is None or loss.grad.arr.pending_zero:
             loss.zero_grad()
             loss.grad.fill_(1.0)
+        if GLOBAL.BEFORE_BACKWARD is not None:
+            GLOBAL.BEFORE_BACKWARD()
         loss.grad_fn(loss)
         hook = GLOBAL.AFTER_NODE_BACKWARD
         for layer in reversed(self._graph):

@@ -86,6 +86,8 @@ class Optimizer:
         flat = self._ensure_flat()
         for p in flat.params:
             p._grad._arr.pending_zero = True
+            p._grad._arr._pz[2] = None      # a postponed add belongs to the gradient that is being discarded
+            p.pending_uses = 0              # forwards whose backward never ran (e.g. validation) are forgotten here
 
     def _materialize_grads(self):
         for p in self.flat.params:

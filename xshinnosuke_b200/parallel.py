@@ -5,6 +5,11 @@ north_star asks for. Semantics: every rank is "the reference run on its own shar
 BatchNorm statistics, loss = mean over the local batch); parameter gradients are SUMMED across ranks
 and the fused optimizer kernel applies grad_scale = 1/world (so the update uses the average).
 
+Gradient accumulation (several backward() calls before one step()): a bucket is all-reduced IN PLACE once per step, so a
+backward that starts after buckets of this step were already reduced would add local gradients on top of a cross-rank
+sum. That is refused with an error; wrap every backward but the last in `with dp.no_sync():` -- inside it nothing is
+reduced, and the last backward (or step()) reduces the accumulated local gradients once.
+
 Mechanics: parameter gradients already live in one flat fp32 buffer laid out in parameter-creation
 order (optim/optimizer.py). It is cut into buckets from the END (fc -> layer4 -> ... -> conv1: the order
 in which backward produces them). `core.autograd.backward` calls `after_node` after every closure;
@@ -69,10 +74,12 @@ class DataParallel:
         self._buckets = []
         self._next = 0
         self._comm = None
+        self._sync = True          # False inside no_sync(): backward passes only accumulate locally
         self.n_allreduce = 0
         optimizer.grad_scale = 1.0 / self.world
         optimizer.before_step = self._before_step
         GLOBAL.AFTER_NODE_BACKWARD = self._after_node
+        GLOBAL.BEFORE_BACKWARD = self._before_backward
 
     # ---- plumbing
     def _cuda(self):
@@ -119,9 +126,30 @@ class DataParallel:
                 return False
         return True
 
+    # ---- gradient accumulation
+    def no_sync(self):
+        """Context manager: backward passes inside it do not all-reduce (use for all but the last micro-batch)."""
+        dp = self
+
+        class _NoSync:
+            def __enter__(self):
+                self.prev, dp._sync = dp._sync, False
+
+            def __exit__(self, *exc):
+                dp._sync = self.prev
+                return False
+        return _NoSync()
+
     # ---- hooks
+    def _before_backward(self):
+        if self.world > 1 and self._next > 0:
+            raise RuntimeError(
+                "DataParallel: backward() started after gradient buckets of this step were already all-reduced "
+                f"({self._next} of {len(self._buckets)}); with several backward passes per step() wrap all but the last in "
+                "`with dp.no_sync():`")
+
     def _after_node(self, node):
-        if not self.overlap or self.world == 1 or self._flat is None or self.opt.flat is not self._flat:
+        if not self.overlap or not self._sync or self.world == 1 or self._flat is None or self.opt.flat is not self._flat:
             return
         while self._next < len(self._buckets) and self._bucket_ready(self._next):
             self._launch(self._next)
@@ -136,10 +164,15 @@ class DataParallel:
             if self._cuda():
                 torch().cuda.current_stream().wait_stream(self._comm_stream())
         self._next = 0
+        # a forward that never saw its backward (validation without no_grad) must not hold buckets back for ever
+        for p in self._flat.params:
+            p.pending_uses = 0
 
     def close(self):
         if GLOBAL.AFTER_NODE_BACKWARD == self._after_node:
             GLOBAL.AFTER_NODE_BACKWARD = None
+        if GLOBAL.BEFORE_BACKWARD == self._before_backward:
+            GLOBAL.BEFORE_BACKWARD = None
         self.opt.before_step = None
         self.opt.grad_scale = 1.0
 

@@ -17,8 +17,10 @@ def _pool_out(H, W, k, sh, sw, pad):
 
 
 def cost(name, a):
-    if name in ("xsb_conv2d_fwd", "xsb_conv2d_fwd_stats"):
+    if name in ("xsb_conv2d_fwd", "xsb_conv2d_fwd_stats", "xsb_conv2d_fwd_acc"):
         return "flop", _conv_flops(a, 4)
+    if name == "xsb_split_tf32":
+        return "byte", 12.0 * a[3]
     if name in ("xsb_conv2d_dgrad", "xsb_conv2d_wgrad"):
         return "flop", _conv_flops(a, 3)
     if name == "xsb_gemm":
