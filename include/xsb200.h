@@ -34,9 +34,10 @@ extern "C" {
 #define XSB_MATH_FP32 0 /* CUDA-core FFMA, fp32 accumulate: <= 1e-5 vs the float64 reference      */
 #define XSB_MATH_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM: <= 2e-3 vs the reference  */
 /* fp32-accurate products ON the tensor cores ("fp32x3", <= 1e-5 vs the reference) are a host-level composition of
- * XSB_MATH_TF32 calls: xsb_split_tf32 writes x = hi + lo with hi exact in tf32, and a product x.w becomes
+ * XSB_MATH_TF32 calls: xsb_split_tf32 writes x ~ hi + lo with both parts exact in tf32, and a product x.w becomes
  * lo.hi + hi.lo + hi.hi -- three accumulating calls (xsb_conv2d_fwd_acc, xsb_conv2d_dgrad / _wgrad / xsb_gemm with
- * accumulate = 1). hi.hi is exact in fp32, the dropped lo.lo term is ~2^-22 relative (xshinnosuke_b200/nn/x3.py). */
+ * accumulate = 1). The products are exact in fp32; dropped: lo.lo and the rounding of lo, ~2^-22 relative, unbiased
+ * (xshinnosuke_b200/nn/x3.py). */
 
 /* ---- runtime (no reference counterpart; plumbing) ---- */
 int xsb_version(void);
@@ -64,7 +65,8 @@ int xsb_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream)
 /* residual add fused with the in-place ReLU that follows it: y = max(0, a+b), mask bit e = [(a+b)[e] < 0] */
 int xsb_add_relu(const float* a, const float* b, float* y, uint8_t* mask, int64_t n, void* stream);
 int xsb_fill(float* dst, float value, int64_t n, void* stream);
-/* hi = x with the 13 low mantissa bits cleared (exact in tf32), lo = x - hi (exact in fp32): operands of the 3xTF32 split */
+/* hi = x rounded to tf32, lo = (x - hi) rounded to tf32 (both exact in tf32, so the tensor core's operand truncation is a
+ * no-op on them): operands of the 3xTF32 split */
 int xsb_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 
 /* ---- mean/sum over one axis and its backward. replaces xs/nn/functional.py mean/sum + grad_fn.py:122-137 ---- */

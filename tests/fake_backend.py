@@ -259,10 +259,13 @@ class FakeLib:
             f32(y, N * OH * OW * OC)[...] = f32(y, N * OH * OW * OC).astype(np.float64) + old
 
     def _split_tf32(self, x, hi, lo, n, s):
+        def rnd(a):      # round to tf32 (10 mantissa bits), nearest
+            u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+            return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
         v = f32(x, n)
-        h = (v.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        h = rnd(v)
         f32(hi, n)[...] = h
-        f32(lo, n)[...] = v - h
+        f32(lo, n)[...] = rnd(v - h)
 
     def _conv2d_fwd_stats(self, x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, stats, stats_n,
                           n_partials, s):

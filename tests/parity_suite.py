@@ -396,3 +396,74 @@ def check_fit_configs(golden, tol):
     mlp = readme_mlp(lr=0.05)
     prof = mlp.fit(xd, yd, batch_size=32, epochs=2, verbose=0, shuffle=False)   # 80 = 32+32+16: partial batch
     np.testing.assert_allclose(prof.data["train_loss"], golden.case("fit/mlp")["losses"], rtol=max(20 * tol, 1e-4))
+
+
+# ------------------------------------------------------------------ Model API around the hot path
+def check_model_api(tol, tmpdir):
+    """evaluate / predict / save / load of xs/nn/models.py:146-202 on a small functional Model with a BatchNorm:
+    eval() really switches BatchNorm to its running statistics (predictions do not depend on how the data is batched),
+    `evaluate` = accuracy / mean cross entropy of `predict` (oracle softmax), a checkpoint restores parameters, running
+    statistics AND optimizer state (a resumed Adam run continues bit-compatibly), mismatching files are refused."""
+    import os
+    import pickle
+    import xshinnosuke_b200.core.state as G
+    from xshinnosuke_b200.layers import Activation, BatchNormalization, Conv2D, Dense, Flatten, Input, MaxPooling2D
+
+    def build(seed):
+        np.random.seed(seed)
+        inp = Input((3, 8, 8))
+        h = Conv2D(8, 3, padding=1)(inp)
+        h = BatchNormalization()(h)
+        h = Activation("relu")(h)
+        h = MaxPooling2D(2)(h)
+        h = Flatten()(h)
+        out = Dense(5)(h)
+        m = nn.Model(inputs=inp, outputs=out)
+        m.compile(optimizer="adam", loss="cross_entropy", lr=0.01)
+        return m
+    rs = np.random.RandomState(0)
+    x, y = rs.rand(40, 3, 8, 8).astype(np.float32), rs.randint(0, 5, (40,))
+    try:
+        model = build(1)
+        model.fit(x, y, batch_size=16, epochs=2, verbose=0, shuffle=False)
+        full = model.predict(x).eval
+        assert full.shape == (40, 5)
+        close(model.predict(x, batch_size=7).eval, full, max(tol, 1e-6), "predict: batched == unbatched (BN on running statistics)")
+        acc, loss = model.evaluate(x, y)
+        ref_loss, probs = X.cross_entropy_fwd(full.astype(np.float64), y)
+        assert abs(loss - ref_loss[0]) <= max(tol, 1e-6) * abs(ref_loss[0])
+        assert abs(acc - float(np.mean(np.argmax(full, axis=1) == y))) < 1e-9
+        acc_b, loss_b = model.evaluate(x, y, batch_size=8)           # 5 equal batches: mean of batch means == overall mean
+        assert abs(loss_b - loss) <= max(tol, 1e-6) * abs(loss) and abs(acc_b - acc) < 1e-9
+        path = os.path.join(str(tmpdir), "ckpt")
+        model.save(path)
+        other = build(7)
+        assert X.rel_err(other.predict(x).eval, full) > 1e-3           # different weights before loading
+        other.load(path)
+        np.testing.assert_array_equal(other.predict(x).eval, full)
+        for m in (model, other):                                         # resume: Adam moments and step counter came along
+            m.fit(x[:32], y[:32], batch_size=16, epochs=1, verbose=0, shuffle=False)
+        for a, b in zip(model.parameters(), other.parameters()):
+            close(b.eval, a.eval, max(tol, 1e-6), "resumed run == uninterrupted run")
+        assert other.optimizer.iterations == model.optimizer.iterations
+        # refused files
+        np.random.seed(3)
+        inp = Input((3, 8, 8))
+        wrong = nn.Model(inputs=inp, outputs=Dense(5)(Flatten()(Conv2D(4, 3, padding=1)(inp))))
+        wrong.compile(optimizer="adam", loss="cross_entropy", lr=0.01)
+        for bad, what in ((lambda: wrong.load(path), "parameter"),):
+            try:
+                bad()
+                raise AssertionError("architecture mismatch accepted")
+            except ValueError as e:
+                assert what in str(e)
+        ref_fmt = os.path.join(str(tmpdir), "ref_format.pkl")
+        with open(ref_fmt, "wb") as f:
+            pickle.dump([["graph"], "optimizer", "loss"], f)
+        try:
+            other.load(ref_fmt)
+            raise AssertionError("reference-format pickle accepted")
+        except ValueError as e:
+            assert "reference-format" in str(e)
+    finally:
+        G.TRAINING = G.IS_TRAINING = True

@@ -130,3 +130,7 @@ def test_fp32x3_mode_host_logic(golden):
         assert fake.calls.count("xsb_conv2d_fwd") == 1 and "xsb_split_tf32" not in fake.calls
     finally:
         xs.set_math_mode("fp32")
+
+
+def test_model_evaluate_predict_save_load(tmp_path):
+    S.check_model_api(1e-6, tmp_path)

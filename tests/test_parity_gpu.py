@@ -648,3 +648,142 @@ def test_dataloader_prefetch_matches_plain():
     for (fx, fy), (sx, sy) in zip(full, r1):
         per = fx.shape[0] // 2
         assert np.array_equal(sx.eval, fx.eval[per:2 * per]) and np.array_equal(sy.eval, fy.eval[per:2 * per])
+
+
+# ------------------------------------------------------------------ fp32x3: fp32-accurate products on the tensor cores
+@pytest.mark.parametrize("n,c,h,oc,k,s,p,n_tc", [
+    (4, 64, 14, 64, 3, 1, 1, 9), (8, 64, 28, 128, 3, 2, 1, 9), (8, 64, 28, 128, 1, 2, 0, 9), (4, 128, 14, 256, 3, 1, 1, 9),
+    (2, 256, 7, 512, 3, 1, 1, 9), (16, 64, 56, 64, 3, 1, 1, 9), (4, 3, 56, 64, 7, 2, 3, 6), (3, 32, 9, 64, 3, 1, 1, 6),
+    (2, 3, 20, 8, 3, 1, 1, 0), (100, 128, 14, 256, 3, 1, 1, 9)])
+def test_conv_fp32x3_tensor_cores(n, c, h, oc, k, s, p, n_tc):
+    """fp32x3 math mode (nn/x3.py): fwd / dgrad / wgrad as three accumulating tcgen05 kind::tf32 launches over the hi/lo
+    operand split, held to the FP32 bar (1e-5 vs the float64 oracle, north_star) -- `n_tc` tensor-core entry calls must
+    have served the three ops (3 each inside the envelope; the stem's dgrad and off-grid channel counts run one FFMA call)."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    xs.set_math_mode("fp32x3")
+    try:
+        rs = np.random.RandomState(n * 1000 + c + h)
+        x = rs.randn(n, c, h, h).astype(np.float32)
+        w = (rs.randn(oc, c, k, k) * 0.1).astype(np.float32)
+        b = rs.randn(1, oc).astype(np.float32)
+        s0 = _tc_stats()
+        tx, tw, tb = xs.tensor(x, requires_grad=True), nn.Parameter(w), nn.Parameter(b)
+        y = F.conv2d(tx, tw, tb, (s, s), p)
+        yr, col = X.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), p)
+        assert X.rel_err(y.eval, yr) <= TOL
+        g = rs.randn(*yr.shape).astype(np.float32)
+        y.backward(gradients=g)
+        dx, dw, db = X.conv2d_bwd(g.astype(np.float64), x.shape, w.astype(np.float64), col, (s, s), p)
+        assert X.rel_err(tx.grad.eval, dx) <= TOL
+        assert X.rel_err(tw.grad.eval, dw) <= TOL
+        s1 = _tc_stats()
+        assert s1[0] - s0[0] == n_tc and s1[1] == s0[1]       # no silent FFMA fallback inside a split product
+    finally:
+        xs.set_math_mode("fp32")
+
+
+def test_dense_and_resnet_fp32x3():
+    """Dense products and a whole ResNet-18 step in fp32x3 mode: logits / loss at the FP32 bar of the fp32 (FFMA) mode."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    import parity_suite as S
+    xs.set_math_mode("fp32x3")
+    try:
+        rs = np.random.RandomState(3)
+        x, w, b = rs.randn(128, 784).astype(np.float32), (rs.randn(784, 500) * 0.1).astype(np.float32), rs.randn(1, 500).astype(np.float32)
+        tx, tw, tb = xs.tensor(x, requires_grad=True), nn.Parameter(w), nn.Parameter(b)
+        s0 = _tc_stats()
+        y = F.addmm(tb, tx, tw)
+        assert X.rel_err(y.eval, x.astype(np.float64) @ w.astype(np.float64) + b) <= TOL
+        g = rs.randn(128, 500).astype(np.float32)
+        y.backward(gradients=g)
+        assert X.rel_err(tx.grad.eval, g.astype(np.float64) @ w.astype(np.float64).T) <= TOL
+        assert X.rel_err(tw.grad.eval, x.astype(np.float64).T @ g.astype(np.float64)) <= TOL
+        assert _tc_stats()[0] - s0[0] == 9
+        net, losses, logits0 = S.resnet_steps(4, 56)
+        from conftest import Golden
+        c = Golden().case("resnet18/n4_56")
+        assert X.rel_err(logits0, c["logits0"]) <= 5e-5
+        assert abs(losses[0] - c["losses"][0]) / c["losses"][0] <= 2e-5
+    finally:
+        xs.set_math_mode("fp32")
+
+
+# ------------------------------------------------------------------ parity AT the benchmarked shapes (BASELINE configs[4])
+@pytest.mark.parametrize("name,c,h,oc,k,s,p", [
+    ("stem", 3, 224, 64, 7, 2, 3), ("layer1", 64, 56, 64, 3, 1, 1), ("layer2.0", 64, 56, 128, 3, 2, 1),
+    ("layer2", 128, 28, 128, 3, 1, 1), ("layer2.sc", 64, 56, 128, 1, 2, 0), ("layer3.0", 128, 28, 256, 3, 2, 1),
+    ("layer3", 256, 14, 256, 3, 1, 1), ("layer4.0", 256, 14, 512, 3, 2, 1), ("layer4", 512, 7, 512, 3, 1, 1)])
+def test_conv_tf32_at_benchmark_shapes(name, c, h, oc, k, s, p):
+    """Every ResNet-18 convolution shape of the benchmarked configuration (N = 128 per GPU, 3 x 224 x 224) in tf32 mode:
+    forward and dgrad are batch-separable, so images 0, 77 and 127 of the full-batch GPU result are held to 2e-3 of the
+    float64 oracle run on those three images; the weight gradient sums over the batch -- it is held to 2e-3 of the fp32
+    (FFMA) mode of the same library on the full batch, which is itself pinned to the oracle at 1e-5 on smaller batches."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.nn import functional as F
+    n, pick = 128, [0, 77, 127]
+    rs = np.random.RandomState(c + h + oc)
+    x = rs.randn(n, c, h, h).astype(np.float32)
+    w = (rs.randn(oc, c, k, k) * 0.1).astype(np.float32)
+    b = rs.randn(1, oc).astype(np.float32)
+    oh = (h - k + 2 * p) // s + 1
+    g = rs.randn(n, oc, oh, oh).astype(np.float32)
+
+    def run(mode):
+        xs.set_math_mode(mode)
+        tx, tw, tb = xs.tensor(x, requires_grad=c >= 32), nn.Parameter(w), nn.Parameter(b)
+        y = F.conv2d(tx, tw, tb, (s, s), p)
+        yv = y.eval[pick]
+        y.backward(gradients=g)
+        return yv, (tx.grad.eval[pick] if c >= 32 else None), tw.grad.eval
+    try:
+        s0 = _tc_stats()
+        y_tc, dx_tc, dw_tc = run("tf32")
+        s1 = _tc_stats()
+        assert s1[0] - s0[0] == (3 if c >= 32 else 2)
+        yr, col = X.conv2d_fwd(x[pick].astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), p)
+        assert X.rel_err(y_tc, yr) <= TOL_TC
+        if c >= 32:
+            dxr, _, _ = X.conv2d_bwd(g[pick].astype(np.float64), x[pick].shape, w.astype(np.float64), col, (s, s), p)
+            assert X.rel_err(dx_tc, dxr) <= TOL_TC
+        del col
+        _, _, dw_fp32 = run("fp32")
+        assert X.rel_err(dw_tc, dw_fp32) <= TOL_TC
+    finally:
+        xs.set_math_mode("fp32")
+
+
+# ------------------------------------------------------------------ data parallel over NCCL (needs >= 2 GPUs)
+@pytest.mark.parametrize("optimizer,graph", [("sgd", False), ("adam", False), ("sgd", True), ("adam", True)])
+def test_data_parallel_nccl_matches_per_shard_oracle(optimizer, graph):
+    """tests/dp_worker.py under torchrun on 2 GPUs: NCCL bucket all-reduces overlapped with backward (eager and captured
+    into the step's CUDA graph), parameters after 4 steps within 2e-5 of the per-shard oracle average."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(here, "dp_worker.py"), optimizer] + (["graph"] if graph else [])
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert res.stdout.count("DP_RESULT") == 2
+
+
+def test_model_evaluate_predict_save_load(tmp_path):
+    import parity_suite as S
+    S.check_model_api(TOL, tmp_path)

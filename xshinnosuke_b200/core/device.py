@@ -304,7 +304,9 @@ class DevArray:
                 lib.xsb_nhwc_to_nchw(src.data_ptr(), tmp.data_ptr(), nn_, c, h, w, 0, rt.stream())
                 rt.launches += 1
                 src = tmp
-        return src.cpu().numpy().reshape(self.shape)
+        host = src.cpu().numpy().reshape(self.shape)
+        # `.eval` hands out a COPY: when the buffer already lives on the host (CPU host-logic tests) .cpu() is the live buffer itself
+        return host.copy() if src.device.type == "cpu" else host
 
     def assign_numpy(self, a):
         """Overwrite the contents from a host array of the same logical shape (keeps the buffer:

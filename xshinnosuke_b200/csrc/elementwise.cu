@@ -187,29 +187,33 @@ __global__ void axpy_scalar(float* dst, const float* src, float alpha, int64_t n
     if (i < n) dst[i] += alpha * src[i];
 }
 
-// 3xTF32 split: hi = x with the 13 low mantissa bits cleared (exactly representable in tf32, so tcgen05 kind::tf32 reads it
-// unchanged whatever its fp32 -> tf32 reduction is), lo = x - hi (exact in fp32). Roofline: HBM, 3e*n.
+// 3xTF32 split: hi = x rounded to tf32 (cvt.rna: 10 mantissa bits, nearest), lo = (x - hi) rounded to tf32. Both parts
+// are exactly representable in tf32, so tcgen05 kind::tf32 -- which TRUNCATES fp32 operands (tools/tf32_probe.py) --
+// reads them unchanged: the only error left is the rounding of lo (<= 2^-22 |x|, unbiased). Cutting instead of rounding
+// lets the tensor core truncate lo itself: a one-sided 2^-21 |x.w| per product that adds up linearly over K (measured
+// 1.2e-5 on a K = 4608 dgrad against 1e-6 with rounding). Roofline: HBM, 3e*n.
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
 __global__ void __launch_bounds__(256) split_tf32_vec(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
                                                       int64_t n4) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n4; i += stride) {
         const float4 v = ldg_stream(x + i);
-        float4 h;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
         stg_stream(hi + i, h);
-        stg_stream(lo + i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+        stg_stream(lo + i, make_float4(round_tf32(v.x - h.x), round_tf32(v.y - h.y), round_tf32(v.z - h.z), round_tf32(v.w - h.w)));
     }
 }
 __global__ void split_tf32_scalar(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        const float h = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+        const float h = round_tf32(x[i]);
         hi[i] = h;
-        lo[i] = x[i] - h;
+        lo[i] = round_tf32(x[i] - h);
     }
 }
 

@@ -46,10 +46,13 @@ class _Base:
         self._parameters = ParameterSet()
 
     def train(self):
-        GLOBAL.IS_TRAINING = True
+        """The reference writes IS_TRAINING, which no op ever reads (models.py:18-22, SURVEY Q5: its BatchNorm stays on batch
+        statistics in `evaluate`). SURVEY 8f-4 "fixing the train()/eval() flag": here both flags move, so eval() puts
+        BatchNorm on its running statistics and stops in-place ReLUs from recording masks."""
+        GLOBAL.IS_TRAINING = GLOBAL.TRAINING = True
 
     def eval(self):
-        GLOBAL.IS_TRAINING = False
+        GLOBAL.IS_TRAINING = GLOBAL.TRAINING = False
 
     def parameters(self, parameters=None):
         if parameters is None:
@@ -73,81 +76,58 @@ class _Model(_Base):
     def init_graph_out_tensor(self, x, y):
         raise NotImplementedError
 
+    # ------------------------------------------------------------------ training
+    def _train_batch(self, bx, by):
+        """One update on the static graph: the body of the reference's batch loop (xs/nn/models.py:100-106)."""
+        self.train()
+        self.optimizer.zero_grad()
+        pred = self.forward(bx)
+        loss = self.loss.forward(pred, by)
+        self.backward(loss)
+        self.optimizer.step()
+        return pred, loss
+
     def fit(self, x, y, batch_size=None, epochs=1, verbose=1, shuffle=True, validation_data=None,
             validation_split=0.0, initial_epoch=0, cuda_graph=False):
         """xs/nn/models.py:61-129. `cuda_graph=True` (no reference counterpart): the static graph's
         train step -- zero_grad, forward into the preallocated `out=` buffers, loss, backward, optimizer step -- is
         captured into ONE CUDA graph after the first two full batches (which run eagerly: every batch is exactly one
         update either way) and replayed for every further full-size batch; a partial last batch runs eagerly."""
-        x, y = np.asarray(x), np.asarray(y)
-        names = ["train_loss", "train_acc"]
-        if validation_data is None and 0.0 < validation_split < 1.0:
-            split = int(x.shape[0] * validation_split)
-            validation_data = (x[-split:], y[-split:])
-            train_x, train_y = x[:-split], y[:-split]
-            names += ["validation_loss", "validation_acc"]
-        else:
-            train_x, train_y = x, y
-        loader = DataLoader(DataSet(train_x, train_y), batch_size, shuffle)
-        v_acc = v_loss = 0.0
         from ..core.device import rt
-        use_graph = bool(cuda_graph) and validation_data is None and batch_size is not None and \
-            rt.device is not None and rt.device.type == "cuda"
-        gx = gy = graphed = None
-        n_full = 0
-
-        def train_step_static():
-            self.train()
-            self.optimizer.zero_grad()
-            pred_ = self.forward(gx)
-            loss_ = self.loss.forward(pred_, gy)
-            self.backward(loss_)
-            self.optimizer.step()
-            return pred_, loss_
-        with SummaryProfile(*names, verbose=verbose) as profile:
+        x, y = np.asarray(x), np.asarray(y)
+        columns = ["train_loss", "train_acc"]
+        if validation_data is None and 0.0 < validation_split < 1.0:
+            n_val = int(x.shape[0] * validation_split)
+            validation_data, x, y = (x[-n_val:], y[-n_val:]), x[:-n_val], y[:-n_val]
+            columns += ["validation_loss", "validation_acc"]
+        loader = DataLoader(DataSet(x, y), batch_size, shuffle)
+        replay = _StaticStepReplay(self) if (cuda_graph and validation_data is None and batch_size is not None and
+                                             rt.device is not None and rt.device.type == "cuda") else None
+        val = (0.0, 0.0)
+        with SummaryProfile(*columns, verbose=verbose) as profile:
             for epoch in range(initial_epoch, epochs):
-                t0 = time.time()
+                started = time.time()
                 if verbose != 0:
                     print("\033[1;31m Epoch[%d/%d]\033[0m" % (epoch + 1, epochs))
-                bar = ProgressBar(max_iter=len(train_x), verbose=verbose)
-                for idx, (batch_x, batch_y) in enumerate(loader):
-                    full = use_graph and batch_x.shape[0] == batch_size
-                    if full:
-                        # fixed input tensors: every full batch is copied into them on the device
-                        if gx is None:
-                            gx, gy = Tensor(batch_x.arr.clone()), Tensor(batch_y.arr.clone())
-                        else:
-                            for dst, src in ((gx, batch_x), (gy, batch_y)):
-                                src.arr.ptr  # noqa: B018 -- materialise
-                                dst.arr.wptr  # noqa: B018
-                                dst.arr.buf[: max(dst.arr.size, 1)].copy_(src.arr.buf[: max(src.arr.size, 1)])
-                        if graphed is None or idx == 0:
-                            self.init_graph_out_tensor(gx, gy)
-                        if graphed is None and n_full >= 2:
-                            from ..utils.graph import GraphedStep
-                            graphed = GraphedStep(train_step_static, warmup=0)   # capture only, executes nothing
-                        pred, loss = graphed() if graphed is not None else train_step_static()
-                        n_full += 1
-                        batch_y = gy
+                bar = ProgressBar(max_iter=len(x), verbose=verbose)
+                last = len(loader) - 1
+                for idx, (bx, by) in enumerate(loader):
+                    if replay is not None and bx.shape[0] == batch_size:
+                        pred, loss, by = replay.step(bx, by, first_of_epoch=idx == 0)
                     else:
-                        if idx == 0 or idx == len(loader) - 1 or use_graph:
-                            self.init_graph_out_tensor(batch_x, batch_y)
-                        self.train()
-                        self.optimizer.zero_grad()
-                        pred = self.forward(batch_x)
-                        loss = self.loss.forward(pred, batch_y)
-                        self.backward(loss)
-                        self.optimizer.step()
-                    train_acc = self.loss.calc_acc(pred, batch_y)
-                    loss_value = loss.item()
-                    profile.step("train_acc", train_acc)
+                        # output buffers are (re)sized on the first batch and shrunk to a prefix view on a partial last one
+                        if idx in (0, last) or replay is not None:
+                            self.init_graph_out_tensor(bx, by)
+                        pred, loss = self._train_batch(bx, by)
+                    acc, loss_value = self.loss.calc_acc(pred, by), loss.item()
+                    profile.step("train_acc", acc)
                     profile.step("train_loss", loss_value)
                     if validation_data is not None:
-                        v_acc, v_loss = self.evaluate(validation_data[0], validation_data[1], batch_size=batch_size)
-                        profile.step("validation_loss", v_loss)
-                        profile.step("validation_acc", v_acc)
-                    bar.update(batch_x.shape[0])
-                    bar.console(verbose, time.time() - t0, loss_value, train_acc, v_loss, v_acc)
+                        val = self.evaluate(validation_data[0], validation_data[1], batch_size=batch_size)
+                        profile.step("validation_loss", val[1])
+                        profile.step("validation_acc", val[0])
+                    bar.update(bx.shape[0])
+                    bar.console(verbose, time.time() - started, loss_value, acc, val[1], val[0])
                 if verbose != 0:
                     print()
         return profile
@@ -173,58 +153,88 @@ class _Model(_Base):
                 hook(layer)
         GLOBAL.INPUTS = None
 
+    # ------------------------------------------------------------------ inference (xs/nn/models.py:146-186)
     def evaluate(self, x, y, batch_size=None):
+        """-> (accuracy, loss) with BatchNorm on its running statistics; batched: the mean over the batches."""
         self.eval()
         x, y = np.asarray(x), np.asarray(y)
-        if batch_size is not None:
-            assert type(batch_size) is int
-            loader = DataLoader(DataSet(x, y), batch_size)
-            accs, losses = [], []
-            for idx, (bx, by) in enumerate(loader):
-                if idx == 0 or idx == len(loader) - 1:
-                    self.init_graph_out_tensor(bx, by)
-                pred = self.forward(bx)
-                acc, loss = self.loss.metric(pred, by)
-                accs.append(acc)
-                losses.append(loss)
-            return float(np.mean(accs)), float(np.mean(losses))
-        tx, ty = Tensor(x), Tensor(y)
-        self.init_graph_out_tensor(tx, ty)
-        pred = self.forward(tx)
-        return self.loss.metric(pred, ty)
+        if batch_size is None:
+            tx, ty = Tensor(x), Tensor(y)
+            self.init_graph_out_tensor(tx, ty)
+            return self.loss.metric(self.forward(tx), ty)
+        assert type(batch_size) is int
+        loader = DataLoader(DataSet(x, y), batch_size)
+        last, scores = len(loader) - 1, []
+        for idx, (bx, by) in enumerate(loader):
+            if idx in (0, last):
+                self.init_graph_out_tensor(bx, by)
+            scores.append(self.loss.metric(self.forward(bx), by))
+        return float(np.mean([a for a, _ in scores])), float(np.mean([l for _, l in scores]))
 
     def predict(self, x, batch_size=None):
         self.eval()
         x = np.asarray(x)
-        outs = []
-        bs = batch_size if batch_size is not None else len(x)
-        for i in range(0, len(x), bs):
-            tx = Tensor(x[i:i + bs])
+        step = batch_size if batch_size is not None else max(len(x), 1)
+        chunks = []
+        for lo in range(0, len(x), step):
+            tx = Tensor(x[lo:lo + step])
             self.init_graph_out_tensor(tx, None)
-            outs.append(self.forward(tx).eval)
-        return Tensor(np.concatenate(outs, axis=0))
+            chunks.append(self.forward(tx).eval)
+        return Tensor(np.concatenate(chunks, axis=0))
+
+    # ------------------------------------------------------------------ persistence
+    CHECKPOINT_FORMAT = "xshinnosuke_b200.checkpoint"
+    CHECKPOINT_VERSION = 2
 
     def save(self, save_path):
-        """Pickle of host copies of every parameter (device buffers do not pickle)."""
+        """Pickle of a versioned dict of HOST arrays: parameters (creation order), BatchNorm running statistics and the
+        optimizer's state (per-parameter moment buffers out of the flat device buffers, step counters, hyper-parameters).
+        Intentionally NOT the reference's format -- that pickles the live `[graph, optimizer, loss]` objects
+        (xs/nn/models.py:188-192), which here hold device buffers; `load` says so when handed one."""
         if not save_path.endswith(".pkl"):
             save_path += ".pkl"
-        state = {"params": [p.eval for p in self._parameters],
+        params = list(self._parameters)
+        state = {"format": self.CHECKPOINT_FORMAT, "version": self.CHECKPOINT_VERSION,
+                 "params": [p.eval for p in params],
                  "running": [(l.moving_mean.eval, l.moving_variance.eval) for l in self._graph
-                             if getattr(l, "moving_mean", None) is not None]}
+                             if getattr(l, "moving_mean", None) is not None],
+                 "optimizer": self.optimizer.state_dict() if self.optimizer is not None else None}
         with open(save_path, "wb") as f:
             pickle.dump(state, f)
 
     def load(self, model_path):
+        """Restore what `save` wrote into THIS (already compiled) model; the architecture must match."""
         if not model_path.endswith(".pkl"):
             model_path += ".pkl"
         with open(model_path, "rb") as f:
             state = pickle.load(f)
-        for p, v in zip(self._parameters, state["params"]):
-            p.eval = v
+        if isinstance(state, (list, tuple)):
+            raise ValueError(f"{model_path} looks like a reference-format checkpoint (a pickled [graph, optimizer, loss] list, "
+                             "xs/nn/models.py:188-192); this backend stores a versioned dict of host arrays -- re-save it with "
+                             "Model.save of xshinnosuke_b200")
+        if not isinstance(state, dict) or state.get("format") != self.CHECKPOINT_FORMAT:
+            if isinstance(state, dict) and "params" in state and "format" not in state:
+                state = dict(state, format=self.CHECKPOINT_FORMAT, version=1, optimizer=None)    # round-1 files
+            else:
+                raise ValueError(f"{model_path} is not a {self.CHECKPOINT_FORMAT} file")
+        if state["version"] > self.CHECKPOINT_VERSION:
+            raise ValueError(f"checkpoint version {state['version']} is newer than this library ({self.CHECKPOINT_VERSION})")
+        params = list(self._parameters)
+        if len(params) != len(state["params"]):
+            raise ValueError(f"checkpoint holds {len(state['params'])} parameter tensors, the model has {len(params)}")
+        for i, (p, v) in enumerate(zip(params, state["params"])):
+            if tuple(p.shape) != tuple(np.shape(v)):
+                raise ValueError(f"parameter {i}: checkpoint shape {tuple(np.shape(v))} != model shape {tuple(p.shape)}")
         bns = [l for l in self._graph if getattr(l, "moving_mean", None) is not None]
+        if len(bns) != len(state["running"]):
+            raise ValueError(f"checkpoint holds {len(state['running'])} BatchNorm statistics, the model has {len(bns)}")
+        for p, v in zip(params, state["params"]):
+            p.eval = v
         for l, (mm, mv) in zip(bns, state["running"]):
             l.moving_mean.eval = mm
             l.moving_variance.eval = mv
+        if state.get("optimizer") is not None and self.optimizer is not None:
+            self.optimizer.load_state_dict(state["optimizer"])
 
     def __str__(self):
         if self._graph is None:
@@ -248,6 +258,35 @@ class _Model(_Base):
         lines += ["*" * 75, "Total params: %d" % total, "Trainable params: %d" % trainable,
                   "Non-trainable params: %d" % (total - trainable)]
         return "\n".join(lines)
+
+
+class _StaticStepReplay:
+    """Model.fit(cuda_graph=True): full-size batches are copied into two fixed input tensors on the device; the first
+    two run eagerly (they build the flat optimizer buffers and size every `out=` buffer), then the step is captured once
+    and replayed."""
+
+    def __init__(self, model):
+        self.model, self.x, self.y, self.graphed, self.done = model, None, None, None, 0
+
+    def _feed(self, bx, by):
+        if self.x is None:
+            self.x, self.y = Tensor(bx.arr.clone()), Tensor(by.arr.clone())
+            return
+        for dst, src in ((self.x, bx), (self.y, by)):
+            src.arr.ptr  # noqa: B018 -- materialise
+            dst.arr.wptr  # noqa: B018
+            dst.arr.buf[: max(dst.arr.size, 1)].copy_(src.arr.buf[: max(src.arr.size, 1)])
+
+    def step(self, bx, by, first_of_epoch):
+        self._feed(bx, by)
+        if self.graphed is None or first_of_epoch:
+            self.model.init_graph_out_tensor(self.x, self.y)
+        if self.graphed is None and self.done >= 2:
+            from ..utils.graph import GraphedStep
+            self.graphed = GraphedStep(lambda: self.model._train_batch(self.x, self.y), warmup=0)   # capture only
+        pred, loss = self.graphed() if self.graphed is not None else self.model._train_batch(self.x, self.y)
+        self.done += 1
+        return pred, loss, self.y
 
 
 class Sequential(_Model):

@@ -1,13 +1,14 @@
 """fp32-accurate GEMM-shaped ops ON the tensor cores: the 3xTF32 split ("fp32x3" math mode).
 
 The reference computes in float64 (xs/utils/common.py:37,56) and north_star holds fp32 results to 1e-5; tcgen05 has no fp32
-MMA and kind::tf32 alone gives ~5e-4. Every operand is split x = hi + lo with hi exact in tf32 (13 low mantissa bits
-cleared, xsb_split_tf32) and lo = x - hi exact in fp32; a product becomes
+MMA and kind::tf32 alone gives ~5e-4. Every operand is split x ~ hi + lo with hi = x rounded to tf32 and lo = (x - hi)
+rounded to tf32 (xsb_split_tf32); a product becomes
 
-    x . w  =  lo . hi  +  hi . lo  +  hi . hi        (lo . lo ~ 2^-22 relative, dropped)
+    x . w  =  lo . hi  +  hi . lo  +  hi . hi        (lo . lo and the rounding of lo: ~2^-22 relative, unbiased, dropped)
 
-three accumulating tcgen05 launches of the ordinary tf32 kernels (small terms first, bias with the last). hi . hi has exact
-fp32 products; what remains is the fp32 accumulation in TMEM (measured 4e-7 at K = 4608, tools/tf32_probe.py).
+three accumulating tcgen05 launches of the ordinary tf32 kernels (small terms first, bias with the last). Both parts are
+exact in tf32, so the tensor core's operand truncation changes nothing and every product is exact in fp32; what remains
+is the fp32 accumulation in TMEM (measured 4e-7 at K = 4608, tools/tf32_probe.py).
 Shapes outside the tensor-core envelope run the fp32 FFMA kernel once instead.
 """
 from .._lib import MATH_FP32, MATH_TF32, lib

@@ -12,6 +12,8 @@ never applies it (Q8); here a non-zero value adds the L2 term wd*p to the gradie
 (g' = grad_scale*g + wd*p), the default 0 is the reference's arithmetic. The data-parallel engine (parallel.py) all-reduces buckets of the flat gradient
 buffer and passes grad_scale = 1/world.
 """
+import numpy as np
+
 from ..core.device import DevArray, rt, torch
 from ..core.tensor import Tensor
 from .._lib import lib
@@ -81,6 +83,40 @@ class Optimizer:
                     no = new.offsets[new.params.index(p)]
                     new.extra[k][no:no + p.numel()].copy_(old.extra[k][o:o + p.numel()])
 
+    # ---- persistence (Model.save / Model.load)
+    _hyper = ("lr", "weight_decay")
+
+    def state_dict(self):
+        """Host copy of everything a resumed run needs: hyper-parameters, step counters and the per-parameter slices of
+        the flat state buffers (Adam's v / m, Momentum's v, ...), in parameter order."""
+        rt.ensure()
+        flat = self._ensure_flat()
+        slots = [[buf[o:o + p.numel()].cpu().numpy().reshape(p.shape) for p, o in zip(flat.params, flat.offsets)]
+                 for buf in flat.extra]
+        return {"class": type(self).__name__, "iterations": int(self.iterations), "slots": slots,
+                "hyper": {k: getattr(self, k) for k in self._hyper if hasattr(self, k)},
+                "step": int(self._step_dev.item()) if getattr(self, "_step_dev", None) is not None else None}
+
+    def load_state_dict(self, state):
+        if state["class"] != type(self).__name__:
+            raise ValueError(f"checkpoint optimizer is {state['class']}, the model was compiled with {type(self).__name__}")
+        flat = self._ensure_flat()
+        if len(state["slots"]) != len(flat.extra) or any(len(s) != len(flat.params) for s in state["slots"]):
+            raise ValueError("optimizer state does not match the model's parameters")
+        t = torch()
+        for buf, slot in zip(flat.extra, state["slots"]):
+            for p, o, v in zip(flat.params, flat.offsets, slot):
+                if tuple(v.shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state shape {tuple(v.shape)} != parameter shape {tuple(p.shape)}")
+                buf[o:o + p.numel()].copy_(t.from_numpy(np.ascontiguousarray(v, dtype=np.float32).reshape(-1)))
+        for k, v in state["hyper"].items():
+            setattr(self, k, v)
+        self.iterations = int(state["iterations"])
+        if state.get("step") is not None and hasattr(self, "_step_dev"):
+            if self._step_dev is None:
+                self._step_dev = t.zeros(1, dtype=t.int32, device=rt.device)
+            self._step_dev.fill_(int(state["step"]))
+
     def zero_grad(self):
         """xs/optim/optimizer.py:12-17 -- logical: each gradient view is flagged zero, no kernel runs."""
         flat = self._ensure_flat()
@@ -118,6 +154,7 @@ class Adam(Optimizer):
     """xs/optim/adam.py:4-30 (v = first moment, m = second moment, bias-corrected, eps outside the sqrt).
     The step counter lives on the device so a CUDA-graph replay advances the bias correction."""
     n_state = 2
+    _hyper = ("lr", "weight_decay", "beta1", "beta2", "epsilon")
 
     def __init__(self, parameters=None, lr=0.001, weight_decay=0.0, beta1=0.9, beta2=0.999, epsilon=1e-8):
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
@@ -151,6 +188,7 @@ class _RuleOptimizer(Optimizer):
     n_state = 1
     rho = 0.0
     epsilon = 0.0
+    _hyper = ("lr", "weight_decay", "rho", "epsilon")
 
     def step(self):
         flat = self._ensure_flat()
