@@ -137,12 +137,23 @@ int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, flo
 int xsb_gemm(const float* A, const float* B, float* C, const float* bias /* nullable */, int M, int N, int K,
              int transA, int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, void* stream);
 
+/* Dense(out, activation='relu') (xs/layers/linear.py:43-60: the activation layer chained behind addmm) as ONE kernel:
+ * C = op(A).op(B) + bias and act = max(0, C) both leave from the GEMM epilogue (C keeps the pre-activation the ReLU backward
+ * takes its x < 0 mask from, xs/nn/grad_fn.py:152-157). */
+int xsb_gemm_bias_relu(const float* A, const float* B, float* C, const float* bias /* nullable */, float* act, int M, int N,
+                       int K, int transA, int transB, int math_mode, float* ws, int64_t ws_floats, void* stream);
+
 /* ---- conv2d as implicit GEMM (no materialised im2col). replaces xs/nn/functional.py:405-442 +
  *      xs/utils/common.py:35-46 (forward), xs/nn/grad_fn.py:186-203 + xs/utils/common.py:49-65 (backward).
  *      x [N,H,W,C], w [OC,KH,KW,C], y/dy [N,OH,OW,OC], OH = (H-KH+2*pad)/sh+1. ---- */
 int xsb_conv2d_fwd(const float* x, const float* w, const float* bias /* nullable */, float* y, int N, int H, int W,
                    int C, int OC, int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws, int64_t ws_floats,
                    void* stream);
+/* Conv2D(..., activation='relu') (xs/layers/convolutional.py:61-83): y = conv(x, w) + bias and act = max(0, y); fused into the
+ * epilogue of the fp32 kernel, one extra elementwise pass behind the tcgen05 kernels. */
+int xsb_conv2d_fwd_relu(const float* x, const float* w, const float* bias /* nullable */, float* y, float* act, int N, int H,
+                        int W, int C, int OC, int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws,
+                        int64_t ws_floats, void* stream);
 /* y (+)= conv(x, w) (+ bias): xsb_conv2d_fwd with the accumulate flag of the gradient entry points */
 int xsb_conv2d_fwd_acc(const float* x, const float* w, const float* bias /* nullable */, float* y, int N, int H, int W,
                        int C, int OC, int KH, int KW, int sh, int sw, int pad, int accumulate, int math_mode, float* ws,

@@ -251,6 +251,15 @@ class FakeLib:
                              b, (sh, sw), pad)
         f32(y, yv.size)[...] = yv.transpose(0, 2, 3, 1).reshape(-1)
 
+    def _conv2d_fwd_relu(self, x, w, bias, y, act, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, s):
+        self._conv2d_fwd(x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, mode, ws, wsn, s)
+        OH, OW = (H - KH + 2 * pad) // sh + 1, (W - KW + 2 * pad) // sw + 1
+        f32(act, N * OH * OW * OC)[...] = np.maximum(f32(y, N * OH * OW * OC), 0.0)
+
+    def _gemm_bias_relu(self, A, B, C, bias, act, M, N, K, ta, tb, mode, ws, wsn, s):
+        self._gemm(A, B, C, bias, M, N, K, ta, tb, 0, mode, ws, wsn, s)
+        f32(act, M * N)[...] = np.maximum(f32(C, M * N), 0.0)
+
     def _conv2d_fwd_acc(self, x, w, bias, y, N, H, W, C, OC, KH, KW, sh, sw, pad, acc, mode, ws, wsn, s):
         OH, OW = (H - KH + 2 * pad) // sh + 1, (W - KW + 2 * pad) // sw + 1
         old = f32(y, N * OH * OW * OC).astype(np.float64).copy() if acc else 0.0

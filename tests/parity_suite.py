@@ -467,3 +467,48 @@ def check_model_api(tol, tmpdir):
             assert "reference-format" in str(e)
     finally:
         G.TRAINING = G.IS_TRAINING = True
+
+
+# ------------------------------------------------------------------ fused bias + activation epilogue (north_star)
+def check_fused_bias_relu(tol, spy):
+    """Dense(out, activation='relu') and Conv2D(..., activation='relu') (xs/layers/linear.py:43-60, convolutional.py:61-83):
+    forward = ONE fused call (xsb_gemm_bias_relu / xsb_conv2d_fwd_relu writes the pre-activation and max(0, .)), no
+    separate ReLU launch; values and gradients as the reference's two-step chain. `spy(names)` -> context manager that
+    records the C-ABI calls made inside it."""
+    rs = np.random.RandomState(11)
+    # Dense: 128 x 784 -> 500 (BASELINE configs[1]), then a ragged one; weights drawn like the reference does
+    for (m, k, n) in ((128, 784, 500), (5, 12, 10)):
+        x = rs.randn(m, k).astype(np.float32)
+        g = rs.randn(m, n).astype(np.float32)
+        np.random.seed(4)
+        layer = Dense(n, activation="relu")
+        tx = T(x, True)
+        with spy() as calls:
+            out = layer(tx)
+            got = out.eval
+        w, b = (p.eval.astype(np.float64) for p in layer.parameters())
+        pre = x.astype(np.float64) @ w + b
+        close(got, np.maximum(pre, 0.0), tol, f"dense+relu fwd {m}x{k}x{n}")
+        assert calls.count("xsb_gemm_bias_relu") == 1 and "xsb_relu_fwd" not in calls and "xsb_gemm" not in calls, calls
+        out.backward(gradients=g)
+        dpre = g.astype(np.float64) * (pre >= 0)
+        close(tx.grad.eval, dpre @ w.T, tol, "dense+relu dX")
+        close(layer.parameters()[0].grad.eval, x.astype(np.float64).T @ dpre, tol, "dense+relu dW")
+    # Conv2D 1 -> 8, 2x2 (BASELINE configs[0]) and 3 -> 16 3x3 with padding
+    for (c, h, oc, kk, p) in ((1, 28, 8, 2, 0), (3, 9, 16, 3, 1)):
+        x = rs.randn(4, c, h, h).astype(np.float32)
+        np.random.seed(5)
+        layer = Conv2D(oc, kk, padding=p, activation="relu")
+        tx = T(x, True)
+        with spy() as calls:
+            out = layer(tx)
+            got = out.eval
+        w, b = (q.eval.astype(np.float64) for q in layer.parameters())
+        pre, col = X.conv2d_fwd(x.astype(np.float64), w, b, (1, 1), p)
+        close(got, np.maximum(pre, 0.0), tol, f"conv+relu fwd c{c} k{kk}")
+        assert calls.count("xsb_conv2d_fwd_relu") == 1 and "xsb_relu_fwd" not in calls and "xsb_conv2d_fwd" not in calls, calls
+        g = rs.randn(*pre.shape).astype(np.float32)
+        out.backward(gradients=g)
+        dx, dw, db = X.conv2d_bwd(g.astype(np.float64) * (pre >= 0), x.shape, w, col, (1, 1), p)
+        close(tx.grad.eval, dx, tol, "conv+relu dX")
+        close(layer.parameters()[0].grad.eval, dw, tol, "conv+relu dW")

@@ -134,3 +134,16 @@ def test_fp32x3_mode_host_logic(golden):
 
 def test_model_evaluate_predict_save_load(tmp_path):
     S.check_model_api(1e-6, tmp_path)
+
+
+def test_fused_bias_relu_epilogue():
+    import contextlib
+    fake = fake_backend.install()
+
+    @contextlib.contextmanager
+    def spy():
+        start = len(fake.calls)
+        view = []
+        yield view
+        view.extend(fake.calls[start:])
+    S.check_fused_bias_relu(TOL, spy)

@@ -1215,10 +1215,10 @@ static bool fprop_ok(int Cx, int OCx, const void* a, const void* b, const void* 
 
 // Dense products (gemm_tc.cuh). XSB_TC_GEMM=0 (env, read once) keeps them on the FFMA kernel for A/B measurements.
 int xsb_tc_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA, int transB,
-                int accumulate, float*, int64_t, cudaStream_t s) {
+                int accumulate, float*, int64_t, cudaStream_t s, float* act) {
     static const int on = [] { const char* e = getenv("XSB_TC_GEMM"); return (e && e[0] == '0') ? 0 : 1; }();
     if (!on) return XSB_ERR_UNSUPPORTED;
-    const int rc = gemm_tf32(A, B, C, bias, M, N, K, transA, transB, accumulate, s);
+    const int rc = gemm_tf32(A, B, C, bias, M, N, K, transA, transB, accumulate, s, act);
     if (rc == XSB_OK) ++g_tc_launches;
     return rc;
 }

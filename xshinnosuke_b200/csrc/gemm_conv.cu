@@ -16,7 +16,7 @@ using namespace igemm;
 
 // implemented in conv_tc.cu (tcgen05). Return XSB_ERR_UNSUPPORTED when the shape is outside their envelope.
 int xsb_tc_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
-                int transB, int accumulate, float* ws, int64_t ws_floats, cudaStream_t s);
+                int transB, int accumulate, float* ws, int64_t ws_floats, cudaStream_t s, float* act);
 int xsb_tc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvGeom& g, float* ws,
                     int64_t ws_floats, cudaStream_t s, float* stats, int64_t stats_floats, int* n_partials, int accumulate);
 int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, int accumulate, float* ws,
@@ -55,29 +55,41 @@ bool fill_geom(ConvGeom& g, int N, int H, int W, int C, int OC, int KH, int KW, 
 
 extern "C" {
 
-// C[M,N] (+)= op(A) . op(B) (+ bias[N]); row-major. transA: A stored [K,M]; transB: B stored [N,K].
-int xsb_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
-             int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, void* stream) {
-    cudaStream_t s = xsb_stream(stream);
-    XSB_TRY_TC(xsb_tc_gemm(A, B, C, bias, M, N, K, transA, transB, accumulate, ws, ws_floats, s));
+static int gemm_impl(const float* A, const float* B, float* C, const float* bias, float* act, int M, int N, int K, int transA,
+                     int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, cudaStream_t s) {
+    XSB_TRY_TC(xsb_tc_gemm(A, B, C, bias, M, N, K, transA, transB, accumulate, ws, ws_floats, s, act));
     const bool split_ok = true;
     if (!transA && !transB) {
         MatK la{A, K, M, K, K % 4 == 0 && aligned16(A)};
         MatR lb{B, N, N, K, N % 4 == 0 && aligned16(B)};
-        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s, act);
     } else if (!transA && transB) {
         MatK la{A, K, M, K, K % 4 == 0 && aligned16(A)};
         MatK lb{B, K, N, K, K % 4 == 0 && aligned16(B)};
-        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s, act);
     } else if (transA && !transB) {
         MatR la{A, M, M, K, M % 4 == 0 && aligned16(A)};
         MatR lb{B, N, N, K, N % 4 == 0 && aligned16(B)};
-        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s, act);
     } else {
         MatR la{A, M, M, K, M % 4 == 0 && aligned16(A)};
         MatK lb{B, K, N, K, K % 4 == 0 && aligned16(B)};
-        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s);
+        return launch(la, lb, C, N, bias, M, N, K, accumulate, split_ok, ws, ws_floats, s, act);
     }
+}
+
+// C[M,N] (+)= op(A) . op(B) (+ bias[N]); row-major. transA: A stored [K,M]; transB: B stored [N,K].
+int xsb_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
+             int transB, int accumulate, int math_mode, float* ws, int64_t ws_floats, void* stream) {
+    return gemm_impl(A, B, C, bias, nullptr, M, N, K, transA, transB, accumulate, math_mode, ws, ws_floats, xsb_stream(stream));
+}
+
+// Dense(..., activation='relu') in one kernel: C = op(A).op(B) + bias (the pre-activation the ReLU backward reads its x < 0
+// mask from) and act = max(0, C), both written by the GEMM epilogue -- no ReLU pass over C.
+int xsb_gemm_bias_relu(const float* A, const float* B, float* C, const float* bias, float* act, int M, int N, int K,
+                       int transA, int transB, int math_mode, float* ws, int64_t ws_floats, void* stream) {
+    XSB_CHECK_ARG(act != nullptr, "gemm_bias_relu: act must not be null");
+    return gemm_impl(A, B, C, bias, act, M, N, K, transA, transB, 0, math_mode, ws, ws_floats, xsb_stream(stream));
 }
 
 // y[N,OH,OW,OC] = conv(x[N,H,W,C], w[OC,KH,KW,C]) (+ bias[OC]). With `stats`: the tensor-core kernels also leave
@@ -111,6 +123,30 @@ int xsb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
     PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
     MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};
     return launch(la, lb, y, OC, bias, P, OC, J, 0, true, ws, ws_floats, s);
+}
+
+// Conv2D(..., activation='relu'): y = conv(x, w) + bias AND act = max(0, y). The FFMA kernel writes both from its epilogue;
+// the tcgen05 kernels write y and the rectified copy is made by one elementwise pass over it (xsb_relu_fwd).
+int xsb_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream);
+int xsb_conv2d_fwd_relu(const float* x, const float* w, const float* bias, float* y, float* act, int N, int H, int W, int C,
+                        int OC, int KH, int KW, int sh, int sw, int pad, int math_mode, float* ws, int64_t ws_floats,
+                        void* stream) {
+    ConvGeom g;
+    XSB_CHECK_ARG(fill_geom(g, N, H, W, C, OC, KH, KW, sh, sw, pad) && act, "conv2d_fwd_relu: bad geometry");
+    cudaStream_t s = xsb_stream(stream);
+    if (math_mode == 1) {
+        const int rc = xsb_tc_conv_fwd(x, w, bias, y, g, ws, ws_floats, s, nullptr, 0, nullptr, 0);
+        if (rc == XSB_OK) return xsb_relu_fwd(y, act, nullptr, (int64_t)N * g.OH * g.OW * OC, stream);
+        if (rc != XSB_ERR_UNSUPPORTED) return rc;
+        xsb_tc_note_ffma();
+    } else if (math_mode != 0) {
+        xsb_set_error("unknown math_mode %d", math_mode);
+        return XSB_ERR_ARG;
+    }
+    const int P = N * g.OH * g.OW, J = KH * KW * C;
+    PatchA la{Patch{x, g, P, J, C % 4 == 0 && aligned16(x)}};
+    MatK lb{w, J, OC, J, J % 4 == 0 && aligned16(w)};
+    return launch(la, lb, y, OC, bias, P, OC, J, 0, true, ws, ws_floats, s, act);
 }
 
 // y (+)= conv(x, w) (+ bias): the forward convolution with the gradient kernels' accumulate flag. One product of the

@@ -22,12 +22,13 @@ struct GemmParams {
     int M, N, K;
     int kb_per_split;      // 32-wide k-blocks per grid.z slice
     int reduce;            // 1: TMA reduce-add into C (accumulate or split-K); 0: plain store
+    int act;               // 1: fused activation -- also store max(0, C) through tmAct (single split, plain store only)
 };
 
 template <bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAct, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int BN = 128;
     constexpr int TILE = BM * A_ROW_BYTES;      // 16 KB per operand and stage
@@ -144,6 +145,19 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     tma_store_2d(&tmC, stage, n0 + c0, m0 + q * 32);
                 bulk_commit();
             }
+            if (p.act) {    // Dense(..., activation='relu'): the rectified copy leaves from the same registers
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                stage_rows_sw128(stage, lane, o);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && m0 + q * 32 < p.M) {
+                    tma_store_2d(&tmAct, stage, n0 + c0, m0 + q * 32);
+                    bulk_commit();
+                }
+            }
         }
         if (lane == 0) bulk_wait_all<0>();
         tc_fence_before();
@@ -161,8 +175,8 @@ static bool gemm_map(CUtensorMap* m, const float* base, int rows, int cols, int 
 }
 
 template <bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmParams& p, dim3 grid,
-                       cudaStream_t s) {
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& act,
+                       const GemmParams& p, dim3 grid, cudaStream_t s) {
     constexpr int STAGES = 4;
     constexpr int smem = STAGES * 2 * BM * A_ROW_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
@@ -170,39 +184,43 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
         XSB_CUDA(cudaFuncSetAttribute(gemm_tc_k<A_MN, B_MN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    gemm_tc_k<A_MN, B_MN, STAGES><<<grid, kThreads, smem, s>>>(a, b, c, p);
+    gemm_tc_k<A_MN, B_MN, STAGES><<<grid, kThreads, smem, s>>>(a, b, c, act, p);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }
 
 // C[M,N] (+)= op(A) . op(B) (+ bias). transA: A stored [K,M]; transB: B stored [N,K]. XSB_ERR_UNSUPPORTED when a row
 // pitch is not a multiple of 16 bytes / a pointer is unaligned.
+// act (nullable): fused activation output, act[M,N] = max(0, C) -- then the whole K range is one split ("=" only).
 static int gemm_tf32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA, int transB,
-                     int accumulate, cudaStream_t s) {
+                     int accumulate, cudaStream_t s, float* act = nullptr) {
     const int lda = transA ? M : K, ldb = transB ? K : N;
     if (lda % 4 || ldb % 4 || N % 4 || !aligned16(A) || !aligned16(B) || !aligned16(C)) return XSB_ERR_UNSUPPORTED;
     if (M < 1 || N < 4 || K < 1) return XSB_ERR_UNSUPPORTED;
+    if (act && (accumulate || !aligned16(act))) return XSB_ERR_UNSUPPORTED;
     if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
-    CUtensorMap ta, tb, tc_;
+    CUtensorMap ta, tb, tc_, tact;
     const bool okA = transA ? gemm_map(&ta, A, K, M, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)     // [K rows][M cols]: MN-major
                             : gemm_map(&ta, A, M, K, BM, CU_TENSOR_MAP_SWIZZLE_128B);             // [M rows][K cols]: K-major
     const bool okB = transB ? gemm_map(&tb, B, N, K, 128, CU_TENSOR_MAP_SWIZZLE_128B)             // [N rows][K cols]: K-major
                             : gemm_map(&tb, B, K, N, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);    // [K rows][N cols]: MN-major
     if (!okA || !okB || !gemm_map(&tc_, C, M, N, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return XSB_ERR_UNSUPPORTED;
+    tact = tc_;
+    if (act && !gemm_map(&tact, act, M, N, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return XSB_ERR_UNSUPPORTED;
     const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + 127) / 128, total_kb = (K + 31) / 32;
     int splits = xsb_sm_count_cached() / (m_tiles * n_tiles);
     if (splits > total_kb / 2) splits = total_kb / 2;
-    if (splits < 1) splits = 1;
+    if (splits < 1 || act) splits = 1;      // an activation needs the finished sum in ONE epilogue
     const int kb_per = (total_kb + splits - 1) / splits;
     splits = (total_kb + kb_per - 1) / kb_per;
     const int reduce = (splits > 1 || accumulate) ? 1 : 0;
     if (splits > 1 && !accumulate) XSB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));
-    GemmParams p{bias, M, N, K, kb_per, reduce};
+    GemmParams p{bias, M, N, K, kb_per, reduce, act ? 1 : 0};
     dim3 grid(m_tiles, n_tiles, splits);
-    if (transA && !transB) return launch_gemm<true, true>(ta, tb, tc_, p, grid, s);
-    if (!transA && transB) return launch_gemm<false, false>(ta, tb, tc_, p, grid, s);
-    if (!transA && !transB) return launch_gemm<false, true>(ta, tb, tc_, p, grid, s);
-    return launch_gemm<true, false>(ta, tb, tc_, p, grid, s);
+    if (transA && !transB) return launch_gemm<true, true>(ta, tb, tc_, tact, p, grid, s);
+    if (!transA && transB) return launch_gemm<false, false>(ta, tb, tc_, tact, p, grid, s);
+    if (!transA && !transB) return launch_gemm<false, true>(ta, tb, tc_, tact, p, grid, s);
+    return launch_gemm<true, false>(ta, tb, tc_, tact, p, grid, s);
 }
 
 }  // namespace tc

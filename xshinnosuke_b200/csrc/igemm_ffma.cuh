@@ -155,7 +155,7 @@ struct DgradB {
 template <int BM, int BN, class LA, class LB>
 __global__ void __launch_bounds__(kThreads)
 igemm_ffma_k(const LA la, const LB lb, float* C, int64_t ldc, const float* __restrict__ bias, int M, int N, int K,
-             int k_per_split, int accumulate, float* part) {
+             int k_per_split, int accumulate, float* part, float* act) {
     constexpr int TM = BM / 16, TN = BN / 16;
     constexpr int APAD = 4;
     __shared__ __align__(16) float As[2][BK][BM + APAD];
@@ -307,6 +307,7 @@ igemm_ffma_k(const LA la, const LB lb, float* C, int64_t ldc, const float* __res
             if (!split) {
                 if (bias) v += __ldg(bias + n);
                 if (accumulate) v += *o;
+                if (act) act[(int64_t)m * ldc + n] = fmaxf(v, 0.f);     // fused activation: second output, same pitch
             }
             *o = v;
         }
@@ -315,7 +316,7 @@ igemm_ffma_k(const LA la, const LB lb, float* C, int64_t ldc, const float* __res
 
 // C (+)= sum_z part[z] (+ bias)
 static __global__ void splitk_reduce_k(const float* __restrict__ part, float* C, int64_t ldc, const float* __restrict__ bias,
-                                int M, int N, int splits, int accumulate) {
+                                int M, int N, int splits, int accumulate, float* act) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)M * N) return;
     const int m = (int)(t / N), n = (int)(t % N);
@@ -323,13 +324,15 @@ static __global__ void splitk_reduce_k(const float* __restrict__ part, float* C,
     for (int z = 0; z < splits; ++z) v += part[(int64_t)z * M * N + t];
     if (bias) v += bias[n];
     float* o = C + (int64_t)m * ldc + n;
-    *o = accumulate ? *o + v : v;
+    v = accumulate ? *o + v : v;
+    *o = v;
+    if (act) act[(int64_t)m * ldc + n] = fmaxf(v, 0.f);
 }
 
 // Host-side launcher. ws/ws_floats: scratch for split-K partials (may be null -> no split).
 template <class LA, class LB>
 int launch(const LA& la, const LB& lb, float* C, int64_t ldc, const float* bias, int M, int N, int K, int accumulate,
-           bool allow_split, float* ws, int64_t ws_floats, cudaStream_t s) {
+           bool allow_split, float* ws, int64_t ws_floats, cudaStream_t s, float* act = nullptr) {
     if (M <= 0 || N <= 0) return XSB_OK;
     if (K <= 0) {
         xsb_set_error("igemm: K must be positive");
@@ -359,13 +362,13 @@ int launch(const LA& la, const LB& lb, float* C, int64_t ldc, const float* bias,
         return XSB_ERR_ARG;
     }
     if (big)
-        igemm_ffma_k<128, 128, LA, LB><<<grid, kThreads, 0, s>>>(la, lb, C, ldc, bias, M, N, K, k_per, accumulate, part);
+        igemm_ffma_k<128, 128, LA, LB><<<grid, kThreads, 0, s>>>(la, lb, C, ldc, bias, M, N, K, k_per, accumulate, part, act);
     else
-        igemm_ffma_k<64, 64, LA, LB><<<grid, kThreads, 0, s>>>(la, lb, C, ldc, bias, M, N, K, k_per, accumulate, part);
+        igemm_ffma_k<64, 64, LA, LB><<<grid, kThreads, 0, s>>>(la, lb, C, ldc, bias, M, N, K, k_per, accumulate, part, act);
     XSB_LAUNCH_CHECK();
     if (splits > 1) {
         const int64_t tot = (int64_t)M * N;
-        splitk_reduce_k<<<(unsigned)ceil_div64(tot, 256), 256, 0, s>>>(part, C, ldc, bias, M, N, splits, accumulate);
+        splitk_reduce_k<<<(unsigned)ceil_div64(tot, 256), 256, 0, s>>>(part, C, ldc, bias, M, N, splits, accumulate, act);
         XSB_LAUNCH_CHECK();
     }
     return XSB_OK;

@@ -108,15 +108,31 @@ def add(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
 
 
 def _gemm_fwd(x, w, bias, y):
+    """y = x . w (+ bias), deferred by one op: a ReLU that consumes y (Dense(..., activation='relu'), xs/layers/linear.py:
+    43-60) asks the producer for the fused bias+ReLU epilogue -- y AND max(0, y) leave from one kernel."""
     m, k = x.shape
     n = w.shape[-1]
-    bptr = bias.ptr if bias is not None else None
-    if rt.math_mode == x3.MATH_FP32X3 and x3.gemm_ok(k, n):
-        x3.gemm(x.ptr, m * k, w.ptr, k * n, y.wptr, bptr, m, n, k, 0, 0, 0)
-        return
-    lib.xsb_gemm(x.ptr, w.ptr, y.wptr, bptr, m, n, k, 0, 0, 0, x3.c_mode(False), rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS,
-                 rt.stream())
-    rt.launches += 1
+    ybuf = y.buf
+    y.wptr  # noqa: B018 -- clears stale pending state of a reused (static) buffer
+
+    def run(mask=None, act_out=None, _x=x, _w=w, _b=bias):
+        bptr = _b.ptr if _b is not None else None
+        split = rt.math_mode == x3.MATH_FP32X3 and x3.gemm_ok(k, n)
+        if act_out is not None and not split:
+            lib.xsb_gemm_bias_relu(_x.ptr, _w.ptr, ybuf.data_ptr(), bptr, act_out, m, n, k, 0, 0, x3.c_mode(False),
+                                   rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS, rt.stream())
+            rt.launches += 1
+            return True
+        if split:
+            x3.gemm(_x.ptr, m * k, _w.ptr, k * n, ybuf.data_ptr(), bptr, m, n, k, 0, 0, 0)
+        else:
+            lib.xsb_gemm(_x.ptr, _w.ptr, ybuf.data_ptr(), bptr, m, n, k, 0, 0, 0, x3.c_mode(False), rt.ws_big.data_ptr(),
+                         rt.WS_BIG_FLOATS, rt.stream())
+            rt.launches += 1
+        return False
+    run.fusable_relu = False
+    run.fusable_act = True
+    y.pending_op = run
 
 
 def _as_matrix(t):
@@ -194,8 +210,15 @@ def relu(inputs: Tensor, inplace: bool = False, out: Tensor = None, _mask=None) 
         return inputs
     out, y = _out_arr(out, x.shape)
     y.cl = x.cl
-    lib.xsb_relu_fwd(x.ptr, y.wptr, mptr, x.size, rt.stream())
-    rt.launches += 1
+    producer = x.pending_op
+    fused = False
+    if producer is not None and getattr(producer, "fusable_act", False) and _mask is None:
+        # the producer (Dense / Conv2D with activation='relu') has not run yet: its epilogue writes x and max(0, x)
+        x.pending_op = None
+        fused = producer(act_out=y.wptr)
+    if not fused:
+        lib.xsb_relu_fwd(x.ptr, y.wptr, mptr, x.size, rt.stream())
+        rt.launches += 1
     return _wire(out, (inputs,), inputs.requires_grad, ReLUBackward)
 
 
@@ -272,10 +295,18 @@ def conv2d(inputs: Tensor, weight: Tensor, bias: Tensor = None, stride=(1, 1), p
     y.wptr  # noqa: B018 -- clears stale pending state of a reused (static) buffer
     barr = bias.arr if bias is not None else None
 
-    def run(mask=None, stats=False, _x=x, _w=w):
+    def run(mask=None, stats=False, act_out=None, _x=x, _w=w):
         # deferred by one op: a BatchNorm that consumes y asks for `stats` and the conv epilogue gathers the
-        # per-channel (count, mean, M2) partials on the way out -> no statistics pass over y (returns #partials)
-        if rt.math_mode == x3.MATH_FP32X3 and x3.conv_ok(c, oc):
+        # per-channel (count, mean, M2) partials on the way out -> no statistics pass over y (returns #partials);
+        # a ReLU layer that consumes y (Conv2D(..., activation='relu')) asks for `act_out`: y and max(0, y) in one call
+        split = rt.math_mode == x3.MATH_FP32X3 and x3.conv_ok(c, oc)
+        if act_out is not None and not split:
+            lib.xsb_conv2d_fwd_relu(_x.ptr, _w.ptr, barr.ptr if barr is not None else None, ybuf.data_ptr(), act_out, n, h, wd,
+                                    c, oc, kh, kw, sh, sw, padding, x3.c_mode(False), rt.ws_big.data_ptr(), rt.WS_BIG_FLOATS,
+                                    rt.stream())
+            rt.launches += 1
+            return True
+        if split:
             # 3xTF32: three accumulating tcgen05 passes; the x split is kept for the weight gradient
             xparts = x3.split(_x.ptr, _x.size)
             if GLOBAL.COMPUTE_GRAD and weight.requires_grad:
@@ -293,6 +324,7 @@ def conv2d(inputs: Tensor, weight: Tensor, bias: Tensor = None, stride=(1, 1), p
         lib.xsb_conv2d_fwd_stats(*args, rt.ws_stats.data_ptr(), rt.WS_STATS_FLOATS, ctypes.byref(nparts), rt.stream())
         return nparts.value
     run.fusable_relu = False
+    run.fusable_act = True
     run.conv_stats = True
     y.pending_op = run
     rg = inputs.requires_grad or weight.requires_grad or bool(bias is not None and bias.requires_grad)
