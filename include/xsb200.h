@@ -69,6 +69,34 @@ int xsb_fill(float* dst, float value, int64_t n, void* stream);
  * no-op on them): operands of the 3xTF32 split */
 int xsb_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 
+/* ---- SURVEY 8f-4 ops around the hot path (csrc/extra_ops.cu) ----
+ * Sigmoid / Tanh (kind 0 / 1). replaces xs/nn/td_functional.py:63-70 and xs/nn/grad_fn.py:161-170 (derivative written in y). */
+int xsb_unary_fwd(int kind, const float* x, float* y, int64_t n, void* stream);
+int xsb_unary_bwd(int kind, const float* dy, const float* y, float* dx, int64_t n, int accumulate, void* stream);
+/* Dropout2D. replaces xs/nn/functional.py:650-674 (y = x*mask/keep_prob) and xs/nn/grad_fn.py:319-325 (dx += dy*mask*scale,
+ * the reference passes scale = keep_prob). mask: 1 bit per element, set = kept. The draw is a stateless hash of
+ * (seed, *step_dev, element index) -- NOT NumPy's binomial stream (parity is defined given the mask). */
+int xsb_dropout_fwd(const float* x, float* y, uint8_t* mask, int64_t n, float keep_prob, int64_t seed,
+                    const int* step_dev /* nullable */, void* stream);
+int xsb_dropout_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, float scale, int accumulate, void* stream);
+/* ZeroPadding2D. replaces xs/nn/functional.py:629-647 and xs/nn/grad_fn.py:312-316 (channels-last tensors). */
+int xsb_pad2d_fwd(const float* x, float* y, int N, int H, int W, int C, int ph, int pw, void* stream);
+int xsb_pad2d_bwd(const float* dy, float* dx, int N, int H, int W, int C, int ph, int pw, int accumulate, void* stream);
+/* LayerNorm over rows of x[N, F] in LOGICAL (NCHW row-major) order, per-element gamma / beta [F]. replaces
+ * xs/nn/functional.py:743-775, xs/nn/grad_fn.py:414-447. mean / rstd [N] stand in for the cached xmu / sqrtvar. */
+int xsb_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int N,
+                      int64_t F, float eps, void* stream);
+int xsb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      float* dx /* nullable */, float* dgamma /* nullable */, float* dbeta /* nullable */, int N, int64_t F,
+                      int acc_dx, int acc_dgamma, int acc_dbeta, void* stream);
+/* GroupNorm on channels-last x[N, HW, C], G groups, per-channel gamma / beta. replaces xs/nn/functional.py:778-812,
+ * xs/nn/grad_fn.py:450-490. mean / rstd [N*G]. */
+int xsb_groupnorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int N,
+                      int HW, int C, int G, float eps, void* stream);
+int xsb_groupnorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      float* dx /* nullable */, float* dgamma /* nullable */, float* dbeta /* nullable */, int N, int HW, int C,
+                      int G, int acc_dx, int acc_dgamma, int acc_dbeta, void* stream);
+
 /* ---- mean/sum over one axis and its backward. replaces xs/nn/functional.py mean/sum + grad_fn.py:122-137 ---- */
 int xsb_reduce_axis(const float* x, float* y, int64_t outer, int64_t red, int64_t inner, float scale, void* stream);
 int xsb_broadcast_axis(const float* dy, float* dx, int64_t outer, int64_t red, int64_t inner, float scale,
@@ -181,8 +209,10 @@ int xsb_tc_config(int key, int value);
 /* ---- losses. replaces xs/nn/functional.py:984-1010 + xs/nn/td_functional.py:73-78,115-128 +
  *      xs/nn/grad_fn.py:604-620 (cross entropy; labels int64), xs/nn/functional.py:843-873 +
  *      xs/nn/grad_fn.py:503-520 (XS mse). reduction: 0 = mean, 1 = sum. ---- */
+/* bad_label (nullable, device int): a label outside [0, C) is never dereferenced -- the loss becomes NaN and *bad_label = 1
+ * (the reference's NumPy indexing raises IndexError, xs/nn/td_functional.py:119-127; the host raises it on the first read). */
 int xsb_softmax_xent_fwd(const float* logits, const int64_t* labels, float* probs, float* loss, int N, int C,
-                         int reduction, void* stream);
+                         int reduction, int* bad_label /* nullable */, void* stream);
 int xsb_softmax_xent_bwd(const float* probs, const int64_t* labels, const float* dloss, float* dlogits, int N, int C,
                          int reduction, int accumulate, void* stream);
 int xsb_mse_fwd(const float* a, const float* b, float* loss, int64_t n, int reduction, void* stream);

@@ -17,6 +17,8 @@ __all__ = [
     "batch_norm_bwd", "addmm_fwd", "addmm_bwd", "mm_bwd", "softmax", "cross_entropy_fwd",
     "cross_entropy_bwd", "mse_loss_fwd", "mse_loss_bwd", "sgd_step", "adam_step",
     "momentum_step", "rmsprop_step", "adagrad_step", "adadelta_step", "conv_out_size", "pool_out_size", "rel_err",
+    "sigmoid_fwd", "sigmoid_bwd", "tanh_fwd", "tanh_bwd", "pad2d_fwd", "pad2d_bwd", "dropout_fwd", "dropout_bwd",
+    "layer_norm_fwd", "layer_norm_bwd", "group_norm_fwd", "group_norm_bwd", "add_broadcast_bwd",
 ]
 
 
@@ -401,3 +403,104 @@ def adadelta_step(params, grads, state, rho=0.95, epsilon=1e-7):
         d = np.sqrt((x[i] + epsilon) / (s[i] + epsilon)) * g
         p -= d
         x[i] = rho * x[i] + (1 - rho) * np.power(d, 2)
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY 8f-4 ops around the hot path
+# --------------------------------------------------------------------------------------
+def sigmoid_fwd(x):
+    """xs/nn/td_functional.py:63-66."""
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def sigmoid_bwd(dy, y):
+    """xs/nn/grad_fn.py:161-164: dY * y * (1 - y)."""
+    return dy * y * (1 - y)
+
+
+def tanh_fwd(x):
+    """xs/nn/td_functional.py:69-70."""
+    return np.tanh(x)
+
+
+def tanh_bwd(dy, y):
+    """xs/nn/grad_fn.py:167-170: dY * (1 - y^2)."""
+    return dy * (1 - np.square(y))
+
+
+def pad2d_fwd(x, padding):
+    """xs/nn/functional.py:637-638."""
+    return np.pad(x, ((0, 0), (0, 0), (padding[0], padding[0]), (padding[1], padding[1])), "constant")
+
+
+def pad2d_bwd(dy, padding):
+    """xs/nn/grad_fn.py:312-316 (the interior of dY; the shipped slice [p:-p] is empty for p = 0)."""
+    ph, pw = padding
+    return dy[:, :, ph:dy.shape[2] - ph, pw:dy.shape[3] - pw]
+
+
+def dropout_fwd(x, mask, keep_prob):
+    """xs/nn/functional.py:658-661, given the 0/1 mask: x * mask / keep_prob."""
+    return x * mask / keep_prob
+
+
+def dropout_bwd(dy, mask, keep_prob):
+    """xs/nn/grad_fn.py:319-325 as written: mask * keep_prob * dY (it multiplies by keep_prob on the way back; the shipped
+    in-place multiply of the int64 mask raises a casting error, so this formula is pinned by reading, not by running)."""
+    return mask * keep_prob * dy
+
+
+def layer_norm_fwd(x, gamma, beta, epsilon=1e-10):
+    """xs/nn/functional.py:743-775 as intended (the shipped code raises at line 754: `np.subtract(x, mean, out=mean)` with a
+    keepdims mean -- PARITY UNPINNED for this op): statistics over every axis but 0, biased variance, per-element affine.
+    Returns (y, xhat, std)."""
+    axes = tuple(range(1, x.ndim))
+    xmu = x - np.mean(x, axis=axes, keepdims=True)
+    std = np.sqrt(np.var(x, axis=axes, keepdims=True) + epsilon)
+    xhat = xmu / std
+    return gamma * xhat + beta, xhat, std
+
+
+def layer_norm_bwd(dy, xhat, std, gamma):
+    """xs/nn/grad_fn.py:414-447: dgamma = sum_n dY*xhat, dbeta = sum_n dY; dX by the dvar / dmean chain (written out)."""
+    axes = tuple(range(1, dy.ndim))
+    dgamma, dbeta = np.sum(dy * xhat, axis=0), np.sum(dy, axis=0)
+    g = dy * gamma
+    n = np.prod(dy.shape[1:])
+    std_inv = 1.0 / std
+    xmu = xhat * std
+    dvar = -0.5 * np.sum(g * xmu, axis=axes, keepdims=True) * std_inv ** 3
+    dmean = -np.sum(g * std_inv, axis=axes, keepdims=True) - 2.0 * dvar * np.mean(xmu, axis=axes, keepdims=True)
+    return g * std_inv + (2.0 / n) * dvar * xmu + dmean / n, dgamma, dbeta
+
+
+def group_norm_fwd(x, gamma, beta, epsilon=1e-5, groups=16):
+    """xs/nn/functional.py:778-812 as intended (the shipped code raises at line 789 like layer_norm -- PARITY UNPINNED):
+    statistics per (sample, group) over (c/groups, h, w), per-channel affine. Returns (y, xhat [N,C,H,W], std [N,G,1,1,1])."""
+    n, c, h, w = x.shape
+    d = x.reshape(n, groups, c // groups, h, w)
+    xmu = d - np.mean(d, axis=(2, 3, 4), keepdims=True)
+    std = np.sqrt(np.var(d, axis=(2, 3, 4), keepdims=True) + epsilon)
+    xhat = (xmu / std).reshape(n, c, h, w)
+    return gamma.reshape(1, c, 1, 1) * xhat + beta.reshape(1, c, 1, 1), xhat, std
+
+
+def group_norm_bwd(dy, xhat, std, gamma, groups):
+    """xs/nn/grad_fn.py:450-490: dgamma / dbeta over (n, h, w); dX by the per-group dvar / dmean chain."""
+    n, c, h, w = dy.shape
+    dgamma, dbeta = np.sum(dy * xhat, axis=(0, 2, 3)), np.sum(dy, axis=(0, 2, 3))
+    g = (dy * gamma.reshape(1, c, 1, 1)).reshape(n, groups, c // groups, h, w)
+    xh = xhat.reshape(n, groups, c // groups, h, w)
+    m = c // groups * h * w
+    std_inv = 1.0 / std
+    xmu = xh * std
+    dvar = -0.5 * std_inv ** 3 * np.sum(g * xmu, axis=(2, 3, 4), keepdims=True)
+    dmean = np.sum(-g * std_inv, axis=(2, 3, 4), keepdims=True) + dvar * -2.0 / m * np.sum(xmu, axis=(2, 3, 4), keepdims=True)
+    dx = g * std_inv + dvar * 2.0 / m * xmu + dmean / m
+    return dx.reshape(n, c, h, w), dgamma, dbeta
+
+
+def add_broadcast_bwd(dy, shape):
+    """xs/nn/grad_fn.py:6-16: an operand whose shape differs gets dY summed over the FIRST mismatching axis."""
+    mism = [k for k, v in enumerate(dy.shape) if k >= len(shape) or v != shape[k]]
+    return np.sum(dy, axis=mism[0]) if mism else dy

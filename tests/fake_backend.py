@@ -311,9 +311,15 @@ class FakeLib:
         _store(f32(dw, OC * KH * KW * C).reshape(OC, KH, KW, C), g.transpose(0, 2, 3, 1), acc)
 
     # ---- losses
-    def _softmax_xent_fwd(self, z, labels, probs, loss, N, C, red, s):
+    def _softmax_xent_fwd(self, z, labels, probs, loss, N, C, red, bad, s):
         zv = f32(z, N * C).reshape(N, C).astype(np.float64)
-        l, p = X.cross_entropy_fwd(zv, i64(labels, N), "mean" if red == 0 else "sum")
+        lab = i64(labels, N)
+        if ((lab < 0) | (lab >= C)).any():
+            f32(loss, 1)[0] = np.nan
+            if bad:
+                i32(bad, 1)[0] = 1
+            return
+        l, p = X.cross_entropy_fwd(zv, lab, "mean" if red == 0 else "sum")
         f32(probs, N * C)[...] = p.reshape(-1)
         f32(loss, 1)[0] = l[0]
 
@@ -333,6 +339,76 @@ class FakeLib:
             _store(f32(da, n), g, acc_a)
         if db:
             _store(f32(db, n), -g, acc_b)
+
+    # ---- SURVEY 8f-4 ops
+    def _unary_fwd(self, kind, x, y, n, s):
+        v = f32(x, n).astype(np.float64)
+        f32(y, n)[...] = X.sigmoid_fwd(v) if kind == 0 else X.tanh_fwd(v)
+
+    def _unary_bwd(self, kind, dy, y, dx, n, acc, s):
+        g, o = f32(dy, n).astype(np.float64), f32(y, n).astype(np.float64)
+        _store(f32(dx, n), X.sigmoid_bwd(g, o) if kind == 0 else X.tanh_bwd(g, o), acc)
+
+    def _dropout_fwd(self, x, y, mask, n, keep, seed, step, s):
+        rs = np.random.RandomState(int(seed) % (2 ** 31))
+        m = (rs.rand(n) < keep)
+        bits = np.packbits(np.concatenate([m, np.zeros((-n) % 8, dtype=bool)]), bitorder="little")
+        u8(mask, len(bits))[...] = bits
+        f32(y, n)[...] = f32(x, n) * m / keep
+
+    def _dropout_bwd(self, dy, mask, dx, n, scale, acc, s):
+        m = np.unpackbits(u8(mask, (n + 7) // 8), bitorder="little")[:n]
+        _store(f32(dx, n), f32(dy, n).astype(np.float64) * m * scale, acc)
+
+    def _pad2d_fwd(self, x, y, N, H, W, C, ph, pw, s):
+        v = f32(x, N * H * W * C).reshape(N, H, W, C)
+        f32(y, N * (H + 2 * ph) * (W + 2 * pw) * C).reshape(N, H + 2 * ph, W + 2 * pw, C)[...] = \
+            np.pad(v, ((0, 0), (ph, ph), (pw, pw), (0, 0)), "constant")
+
+    def _pad2d_bwd(self, dy, dx, N, H, W, C, ph, pw, acc, s):
+        g = f32(dy, N * (H + 2 * ph) * (W + 2 * pw) * C).reshape(N, H + 2 * ph, W + 2 * pw, C)
+        _store(f32(dx, N * H * W * C).reshape(N, H, W, C), g[:, ph:ph + H, pw:pw + W, :].astype(np.float64), acc)
+
+    def _layernorm_fwd(self, x, gamma, beta, y, mean, rstd, N, F, eps, s):
+        v = f32(x, N * F).reshape(N, F).astype(np.float64)
+        out, xhat, std = X.layer_norm_fwd(v, f32(gamma, F).astype(np.float64), f32(beta, F).astype(np.float64), eps)
+        f32(y, N * F)[...] = out.reshape(-1)
+        f32(mean, N)[...] = v.mean(axis=1)
+        f32(rstd, N)[...] = 1.0 / std.reshape(-1)
+
+    def _layernorm_bwd(self, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, N, F, acc_dx, acc_g, acc_b, s):
+        v = f32(x, N * F).reshape(N, F).astype(np.float64)
+        g = f32(dy, N * F).reshape(N, F).astype(np.float64)
+        mu, rs = f32(mean, N).astype(np.float64).reshape(N, 1), f32(rstd, N).astype(np.float64).reshape(N, 1)
+        xhat = (v - mu) * rs
+        d, dg, db = X.layer_norm_bwd(g, xhat, 1.0 / rs, f32(gamma, F).astype(np.float64))
+        if dx:
+            _store(f32(dx, N * F).reshape(N, F), d, acc_dx)
+        if dgamma:
+            _store(f32(dgamma, F), dg, acc_g)
+        if dbeta:
+            _store(f32(dbeta, F), db, acc_b)
+
+    def _groupnorm_fwd(self, x, gamma, beta, y, mean, rstd, N, HW, C, G, eps, s):
+        v = f32(x, N * HW * C).reshape(N, HW, 1, C).transpose(0, 3, 1, 2).astype(np.float64)      # [N, C, HW, 1]
+        out, xhat, std = X.group_norm_fwd(v, f32(gamma, C).astype(np.float64), f32(beta, C).astype(np.float64), eps, G)
+        f32(y, N * HW * C).reshape(N, HW, 1, C)[...] = out.transpose(0, 2, 3, 1)
+        f32(mean, N * G)[...] = v.reshape(N, G, -1).mean(axis=2).reshape(-1)
+        f32(rstd, N * G)[...] = 1.0 / std.reshape(-1)
+
+    def _groupnorm_bwd(self, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, N, HW, C, G, acc_dx, acc_g, acc_b, s):
+        v = f32(x, N * HW * C).reshape(N, HW, 1, C).transpose(0, 3, 1, 2).astype(np.float64)
+        g = f32(dy, N * HW * C).reshape(N, HW, 1, C).transpose(0, 3, 1, 2).astype(np.float64)
+        mu = f32(mean, N * G).astype(np.float64).reshape(N, G, 1, 1, 1)
+        rs = f32(rstd, N * G).astype(np.float64).reshape(N, G, 1, 1, 1)
+        xhat = ((v.reshape(N, G, C // G, HW, 1) - mu) * rs).reshape(N, C, HW, 1)
+        d, dg, db = X.group_norm_bwd(g, xhat, 1.0 / rs, f32(gamma, C).astype(np.float64), G)
+        if dx:
+            _store(f32(dx, N * HW * C).reshape(N, HW, 1, C), d.transpose(0, 2, 3, 1), acc_dx)
+        if dgamma:
+            _store(f32(dgamma, C), dg, acc_g)
+        if dbeta:
+            _store(f32(dbeta, C), db, acc_b)
 
     # ---- optimizers
     def _sgd_step(self, p, g, n, lr, gscale, wd, s):

@@ -371,11 +371,67 @@ def gen_fit_configs():
     put("fit/mlp", losses=np.array(_profile_losses(prof)))
 
 
+# ------------------------------------------------------------------ SURVEY 8f-4 ops: sigmoid / tanh / pad / dropout / LN / GN / broadcast add
+def gen_extra_ops():
+    rs = np.random.RandomState(21)
+    for name, fn in (("sigmoid", F.sigmoid), ("tanh", F.tanh)):
+        x = rs.randn(3, 5, 4, 6).astype(np.float32)
+        tx = T(x, True)
+        y = fn(tx)
+        yv = y.eval.copy()
+        g = rs.randn(*yv.shape).astype(np.float32)
+        y.backward(gradients=g)
+        put(f"extra/{name}", x=x, g=g, y=yv, dx=tx.grad.eval)
+    # zero padding
+    x = rs.randn(2, 3, 5, 4).astype(np.float32)
+    tx = T(x, True)
+    y = F.pad2d(tx, (2, 1))
+    yv = y.eval.copy()
+    g = rs.randn(*yv.shape).astype(np.float32)
+    y.backward(gradients=g)
+    put("extra/pad2d", x=x, g=g, y=yv, dx=tx.grad.eval)
+    # dropout: the mask the reference drew is stored; parity is defined given the mask
+    x = rs.randn(4, 6, 3, 3).astype(np.float32)
+    tx = T(x, True)
+    np.random.seed(5)
+    y = F.dropout2d(tx, 0.7)
+    mask = np.array(y.cache["mask"])
+    yv = y.eval.copy()
+    # (the shipped Dropout2DBackward multiplies the int64 mask in place by keep_prob and raises a casting error,
+    # grad_fn.py:323: only the forward can be pinned; the backward formula is its own: dX += mask * keep_prob * dY)
+    put("extra/dropout", x=x, y=yv, mask=mask, keep_prob=np.array(0.7))
+    # layer_norm / group_norm cannot be pinned: as shipped both raise in the FORWARD (np.subtract(x, mean, out=mean) with a
+    # keepdims mean, functional.py:754 / :789) -- parity for them is against oracle/xs_numpy.py's restatement of the formulas
+    for fn, args in ((F.layer_norm, (T(rs.randn(2, 3, 2, 2)), T(np.ones((3, 2, 2))), T(np.zeros((3, 2, 2))))),
+                     (F.group_norm, (T(rs.randn(2, 4, 2, 2)), T(np.ones(4)), T(np.zeros(4)), 1e-5, 2))):
+        try:
+            fn(*args)
+            raise SystemExit(f"{fn.__name__} runs on this reference: pin it")
+        except ValueError:
+            pass
+    # broadcasting add: [M, N] + [1, N]
+    a, b = rs.randn(6, 5).astype(np.float32), rs.randn(1, 5).astype(np.float32)
+    ta, tb = T(a, True), T(b, True)
+    y = F.add(ta, tb)
+    yv = y.eval.copy()
+    g = rs.randn(6, 5).astype(np.float32)
+    y.backward(gradients=g)
+    put("extra/add_broadcast", a=a, b=b, g=g, y=yv, da=ta.grad.eval, db=tb.grad.eval)
+
+
 def _profile_losses(prof):
     return list(prof.data["train_loss"])  # xs/utils/toolkit.py:54-56
 
 
 if __name__ == "__main__":
+    if "--only-extra" in sys.argv:      # add the 8f-4 arrays to the existing file without re-running the long cases
+        path = os.path.join(HERE, "reference_vectors.npz")
+        old = np.load(path)
+        OUT.update({k: old[k] for k in old.files if not k.startswith("extra/")})
+        gen_extra_ops()
+        np.savez_compressed(path, **OUT)
+        print("wrote", path, len(OUT), "arrays", os.path.getsize(path) // 1024, "KiB")
+        sys.exit(0)
     gen_conv()
     gen_pool()
     gen_relu_add()
@@ -387,6 +443,7 @@ if __name__ == "__main__":
     gen_test_fc_run()
     gen_resnet()
     gen_fit_configs()
+    gen_extra_ops()
     path = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(path, **OUT)
     print("wrote", path, len(OUT), "arrays", os.path.getsize(path) // 1024, "KiB")

@@ -147,3 +147,46 @@ def test_fused_bias_relu_epilogue():
         yield view
         view.extend(fake.calls[start:])
     S.check_fused_bias_relu(TOL, spy)
+
+
+def test_cross_entropy_label_range():
+    S.check_label_range()
+
+
+def test_direct_writes_and_replaced_gradients():
+    """a direct write (`t.eval = a`, zero_, fill_) voids whatever was parked on the array (deferred producer,
+    postponed add); a gradient tensor the user swapped in after the optimizer flattened its buffers is still applied."""
+    import numpy as np
+    import xshinnosuke_b200 as xs
+    from xshinnosuke_b200 import nn
+    from xshinnosuke_b200.core.device import DevArray
+    from xshinnosuke_b200.nn import functional as F
+    ran = []
+    a = DevArray.empty((2, 3), pending_zero=True)
+    a.cl = False
+    assert a.defer_add(lambda acc: ran.append(acc))
+    a.pending_op = lambda m=None: ran.append("producer")
+    a.assign_numpy(np.full((2, 3), 7.0, dtype=np.float32))
+    assert np.array_equal(a.to_numpy(), np.full((2, 3), 7.0, dtype=np.float32)) and not ran
+    t = xs.tensor(np.ones((2, 2), dtype=np.float32), requires_grad=True)
+    t.zero_grad()
+    assert t.grad.arr.defer_add(lambda acc: ran.append(acc))
+    t.grad.zero_()
+    assert np.array_equal(t.grad.eval, np.zeros((2, 2), dtype=np.float32)) and not ran
+    # deferred conv output overwritten by hand: the producer must not run afterwards
+    x = xs.tensor(np.random.RandomState(0).randn(1, 2, 4, 4).astype(np.float32))
+    w = nn.Parameter(np.random.RandomState(1).randn(3, 2, 3, 3).astype(np.float32))
+    y = F.conv2d(x, w, None, (1, 1), 1)
+    y.eval = np.zeros((1, 3, 4, 4), dtype=np.float32)
+    assert np.array_equal(y.eval, np.zeros((1, 3, 4, 4), dtype=np.float32))
+    # replaced gradient
+    p = nn.Parameter(np.ones((4,), dtype=np.float32))
+    opt = xs.optim.SGD([p], lr=0.5)
+    opt.zero_grad()
+    p.grad = xs.tensor(np.array([1.0, 2.0, 3.0, 4.0], dtype=np.float32))
+    opt.step()
+    assert np.allclose(p.eval, 1.0 - 0.5 * np.array([1.0, 2.0, 3.0, 4.0]))
+
+
+def test_extra_ops(golden):
+    S.check_extra_ops(golden, TOL)

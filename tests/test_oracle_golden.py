@@ -186,3 +186,22 @@ def test_small_net_oracles_reproduce_the_reference_fit_trajectories(golden):
     net = ReadmeMLP()
     losses = [net.train_step(xd[i:i + 32], yd[i:i + 32], 0.05) for _ in range(2) for i in range(0, 80, 32)]
     np.testing.assert_allclose(losses, golden.case("fit/mlp")["losses"], rtol=1e-12)
+
+
+def test_extra_op_oracles_against_the_reference(golden):
+    """oracle restatements of the SURVEY 8f-4 ops against what the unmodified reference produced (sigmoid, tanh, pad2d,
+    dropout forward given the reference's mask, broadcasting add). layer_norm / group_norm are unpinned: the reference's
+    own implementations raise as shipped (asserted by tests/golden/make_golden.py)."""
+    from oracle import xs_numpy as X
+    for name, f, b in (("sigmoid", X.sigmoid_fwd, X.sigmoid_bwd), ("tanh", X.tanh_fwd, X.tanh_bwd)):
+        c = golden.case(f"extra/{name}")
+        y = f(c["x"].astype(np.float64))
+        assert X.rel_err(y, c["y"]) <= 1e-6
+        assert X.rel_err(b(c["g"].astype(np.float64), y), c["dx"]) <= 1e-6
+    c = golden.case("extra/pad2d")
+    assert np.array_equal(X.pad2d_fwd(c["x"], (2, 1)), c["y"]) and np.array_equal(X.pad2d_bwd(c["g"], (2, 1)), c["dx"])
+    c = golden.case("extra/dropout")
+    assert X.rel_err(X.dropout_fwd(c["x"].astype(np.float64), c["mask"], float(c["keep_prob"])), c["y"]) <= 1e-7
+    c = golden.case("extra/add_broadcast")
+    assert X.rel_err(c["a"] + c["b"], c["y"]) <= 1e-7
+    assert X.rel_err(X.add_broadcast_bwd(c["g"].astype(np.float64), c["b"].shape).reshape(-1), c["db"].reshape(-1)) <= 1e-6

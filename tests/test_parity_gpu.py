@@ -816,3 +816,14 @@ def test_fused_bias_relu_epilogue(mode, tol):
         S.check_fused_bias_relu(tol, spy)
     finally:
         xs.set_math_mode("fp32")
+
+
+def test_cross_entropy_label_range():
+    import parity_suite as S
+    S.check_label_range()
+
+
+def test_extra_ops(golden):
+    """Sigmoid / Tanh / Dropout / ZeroPadding2D / broadcasting add / LayerNorm / GroupNorm."""
+    import parity_suite as S
+    S.check_extra_ops(golden, TOL)

@@ -38,6 +38,7 @@ class Runtime:
         self._ws_small = None
         self._ws_big = None
         self._ws_stats = None
+        self._label_flag = None
         self.launches = 0          # kernel-launching C-ABI calls issued (bench.py reports it)
         # BatchNorm -> ReLU -> MaxPool as one kernel (xsb_bn_relu_maxpool_fwd). Measured on the R224 stem: 288 us against
         # 124 + 131 us for the two bandwidth kernels it replaces (the tiled kernel is latency-bound) -> off by default
@@ -82,6 +83,20 @@ class Runtime:
             self._ws_stats = torch().empty(self.WS_STATS_FLOATS, dtype=torch().float32, device=self.device)
         return self._ws_stats
 
+    @property
+    def label_flag(self):
+        """Device int the cross-entropy kernel sets when it meets a label outside [0, classes)."""
+        if self._label_flag is None:
+            self._label_flag = torch().zeros(1, dtype=torch().int32, device=self.device)
+        return self._label_flag
+
+    def take_label_error(self):
+        """-> True (and clears the flag) if a cross-entropy since the last call saw an out-of-range label."""
+        if self._label_flag is None or int(self._label_flag.item()) == 0:
+            return False
+        self._label_flag.zero_()
+        return True
+
     def synchronize(self):
         torch().cuda.current_stream().synchronize()
 
@@ -102,6 +117,14 @@ def set_math_mode(mode):
 
 def get_math_mode():
     return {MATH_FP32: "fp32", MATH_TF32: "tf32", MATH_FP32X3: "fp32x3"}[rt.math_mode]
+
+
+def fill_floats(buf, value, n=None):
+    """buf[:n] = value through libxsb200 (xsb_fill: a memset node for 0, a fill kernel otherwise) -- no torch kernel runs."""
+    n = buf.numel() if n is None else int(n)
+    if n > 0:
+        lib.xsb_fill(buf.data_ptr(), float(value), n, rt.stream())
+        rt.launches += 1
 
 
 def _prod(shape):
@@ -183,8 +206,21 @@ class DevArray:
 
     def _materialize_zero(self):
         root = self if self._root is None else self._root
-        root.buf.zero_()
+        if root.dtype == "float32":
+            fill_floats(root.buf, 0.0)
+        else:
+            root.buf.zero_()
         self._pz[0] = False
+
+    def _drop_deferred(self):
+        """Everything parked on this array is void once its contents are overwritten directly: the deferred producer, the
+        postponed add, the lazily masked alias (an alias is never written through: it gets its own buffer)."""
+        if self.lazy_mask is not None:
+            self.lazy_mask = None
+            self.buf = rt.empty(max(self.size, 1))
+        self._pz[1] = None
+        self._pz[2] = None
+        self.pending_zero = False
 
     # ---- construction
     @staticmethod
@@ -195,15 +231,24 @@ class DevArray:
 
     @staticmethod
     def zeros(shape, dtype="float32"):
-        a = DevArray.empty(shape, dtype)
-        a.buf.zero_()
-        return a
+        return DevArray.full(shape, 0.0, dtype)
 
     @staticmethod
     def full(shape, value, dtype="float32"):
         a = DevArray.empty(shape, dtype)
-        a.buf.fill_(value)
+        if dtype == "float32":
+            fill_floats(a.buf, value)
+        else:
+            a.buf.fill_(value)
         return a
+
+    def fill(self, value):
+        """Direct overwrite with a constant (Tensor.zero_ / fill_)."""
+        self._drop_deferred()
+        if self.dtype == "float32":
+            fill_floats(self.buf, value, max(self.size, 1))
+        else:
+            self.buf[: max(self.size, 1)].fill_(value)
 
     @staticmethod
     def from_numpy(a):
@@ -258,12 +303,7 @@ class DevArray:
     @property
     def wptr(self):
         """Pointer for a kernel that fully OVERWRITES the contents."""
-        if self.lazy_mask is not None:       # never write through an alias
-            self.lazy_mask = None
-            self.buf = rt.empty(max(self.size, 1))
-        self._pz[1] = None
-        self._pz[2] = None
-        self.pending_zero = False
+        self._drop_deferred()
         return self.buf.data_ptr()
 
     def take_acc(self):
@@ -317,8 +357,10 @@ class DevArray:
         new = DevArray.from_numpy(a)
         if new.dtype != self.dtype:
             raise TypeError(f"cannot assign {new.dtype} data to a {self.dtype} tensor")
+        if new.cl != self.cl:                        # a 4-D array whose layout flag was forced: match it
+            new = new.as_cl() if self.cl else new.logical_rowmajor()
+        self._drop_deferred()
         self.buf[: max(self.size, 1)].copy_(new.buf[: max(self.size, 1)])
-        self.pending_zero = False
 
     # ---- views / copies
     def prefix(self, n):

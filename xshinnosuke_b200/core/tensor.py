@@ -237,24 +237,24 @@ class Tensor(object):
 
     def item(self):
         assert self._arr.size == 1
-        return self.eval.reshape(-1)[0].item()
+        v = self.eval.reshape(-1)[0].item()
+        if v != v and self._cache.get("label_check") and rt.take_label_error():
+            # the reference's NumPy indexing raises at the call (xs/nn/td_functional.py:119-127); here at the first read
+            raise IndexError("cross_entropy: a label is outside [0, number of classes)")
+        return v
 
     def long_(self):
         if self._arr.dtype != "int64":
             self._arr = DevArray.from_numpy(self._arr.to_numpy().astype(np.int64))
 
     def zero_(self):
-        self.arr.pending_op = None
-        self.arr.buf.zero_()
-        self.arr.pending_zero = False
+        self.arr.fill(0.0)
 
     def ones_(self):
         self.fill_(1.0)
 
     def fill_(self, value):
-        self.arr.pending_op = None
-        self.arr.buf.fill_(value)
-        self.arr.pending_zero = False
+        self.arr.fill(value)
 
     def zero_grad(self):
         """Logical zeroing: no memset, the first kernel that writes the gradient overwrites it."""

@@ -25,7 +25,7 @@ __device__ double block_sum_d(double v, double* smem) {
 // one warp per row (looping); probs[N,C] written; loss[0] = | -sum_i log p[i, y_i] / denom |
 __global__ void __launch_bounds__(1024)
 softmax_xent_fwd_k(const float* __restrict__ z, const int64_t* __restrict__ labels, float* __restrict__ probs,
-                   float* __restrict__ loss, int N, int C, float inv_denom) {
+                   float* __restrict__ loss, int N, int C, float inv_denom, int* bad_label) {
     __shared__ double s_part[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double acc = 0.0;
@@ -42,7 +42,12 @@ softmax_xent_fwd_k(const float* __restrict__ z, const int64_t* __restrict__ labe
         for (int j = lane; j < C; j += 32) pr[j] = expf(zr[j] - m) * inv;
         if (lane == 0) {
             const int64_t y = labels[row];
-            acc += (double)(zr[y] - m) - log((double)s);
+            if (y < 0 || y >= C) {      // the reference's NumPy indexing raises IndexError here: never read out of bounds,
+                acc = NAN;              // poison the loss and leave a flag the host turns into that IndexError
+                if (bad_label) *bad_label = 1;
+            } else {
+                acc += (double)(zr[y] - m) - log((double)s);
+            }
         }
     }
     const double tot = block_sum_d(acc, s_part);
@@ -87,12 +92,12 @@ extern "C" {
 
 // reduction: 0 = mean (divide by N = logits.shape[0]), 1 = sum
 int xsb_softmax_xent_fwd(const float* logits, const int64_t* labels, float* probs, float* loss, int N, int C,
-                         int reduction, void* stream) {
+                         int reduction, int* bad_label, void* stream) {
     XSB_CHECK_ARG(N > 0 && C > 0, "xent: empty input");
     const float inv = reduction == 0 ? 1.0f / (float)N : 1.0f;
     // one CTA (deterministic row order in the final sum), one warp per row: 32 warps for the usual N >= 32
     const int threads = N >= 32 ? 1024 : N >= 16 ? 512 : kThreads;
-    softmax_xent_fwd_k<<<1, threads, 0, xsb_stream(stream)>>>(logits, labels, probs, loss, N, C, inv);
+    softmax_xent_fwd_k<<<1, threads, 0, xsb_stream(stream)>>>(logits, labels, probs, loss, N, C, inv, bad_label);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

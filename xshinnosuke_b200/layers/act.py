@@ -88,11 +88,31 @@ class Activation(Layer):
         return self._data
 
 
+class _Unary(Layer):
+    _fn = None
+
+    def call(self, x, *args, **kwargs):
+        out = self._data if (self._data is not None and self._data.is_static) else None
+        self._data = type(self)._fn(x, out)
+        return self._data
+
+
+class Sigmoid(_Unary):
+    """xs/layers/activators.py:62-65."""
+    _fn = staticmethod(F.sigmoid)
+
+
+class Tanh(_Unary):
+    """xs/layers/activators.py:68-71."""
+    _fn = staticmethod(F.tanh)
+
+
 def get_activator(activator):
     if isinstance(activator, str):
-        if activator.lower() == "relu":
-            return ReLU()
-        raise NotImplementedError(f"activation {activator!r} is outside the hot path (relu only)")
+        known = {"relu": ReLU, "sigmoid": Sigmoid, "tanh": Tanh}
+        if activator.lower() in known:
+            return known[activator.lower()]()
+        raise NotImplementedError(f"activation {activator!r} is not provided (relu, sigmoid, tanh)")
     if isinstance(activator, Layer):
         return copy.deepcopy(activator)
     raise TypeError("unknown activator type!")

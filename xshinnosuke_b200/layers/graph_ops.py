@@ -40,6 +40,23 @@ class Reshape(Layer):
         return self._shape
 
 
+class ZeroPadding2D(Layer):
+    """xs/layers/ops.py:26-37: zero padding of H and W by padding = (ph, pw) on both sides."""
+
+    def __init__(self, padding, **kwargs):
+        self.padding = (padding, padding) if isinstance(padding, int) else tuple(padding)
+        super().__init__(**kwargs)
+
+    def call(self, x, *args, **kwargs):
+        out = self._data if (self._data is not None and self._data.is_static) else None
+        self._data = F.pad2d(x, self.padding, out)
+        return self._data
+
+    def compute_output_shape(self, input_shape=None):
+        self._shape = (input_shape[0], input_shape[1] + 2 * self.padding[0], input_shape[2] + 2 * self.padding[1])
+        return self._shape
+
+
 class Add(Layer):
     """Residual merge of the static graph (xs/layers/ops.py:40-82): out = sum of inbound layer outputs."""
 

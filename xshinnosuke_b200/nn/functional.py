@@ -18,8 +18,9 @@ from ..utils.common import initialize_ops_grad, pair
 from .._lib import lib
 from . import x3
 from .grad_fn import (AddBackward, AddmmBackward, Avgpool2DBackward, BatchNormBackward, Conv2DBackward,
-                      CrossEntropyLossBackward, FlattenBackward, Maxpool2DBackward, MeanBackward, MMBackward,
-                      MSELossBackward, ReLUBackward, SumBackward, ViewBackward)
+                      CrossEntropyLossBackward, Dropout2DBackward, FlattenBackward, GroupNormBackward, LayerNormBackward,
+                      Maxpool2DBackward, MeanBackward, MMBackward, MSELossBackward, Pad2DBackward, ReLUBackward,
+                      SigmoidBackward, SumBackward, TanhBackward, ViewBackward)
 
 
 def _mark_inputs(t):
@@ -87,7 +88,7 @@ def add(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
     _mark_inputs(lhs)
     a, b = lhs.arr, rhs.arr
     if tuple(a.shape) != tuple(b.shape):
-        raise NotImplementedError(f"add: broadcasting {a.shape} + {b.shape} is outside the hot path")
+        return _add_rowvector(lhs, rhs, out)
     if a.cl != b.cl:
         b = b.as_cl() if a.cl else b.logical_rowmajor()
     out, y = _out_arr(out, a.shape)
@@ -105,6 +106,34 @@ def add(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
     run.fusable_relu = n % 8 == 0
     y.pending_op = run
     return _wire(out, (lhs, rhs), lhs.requires_grad or rhs.requires_grad, AddBackward)
+
+
+def _add_rowvector(lhs, rhs, out):
+    """lhs [..., N] + rhs broadcast along the leading axes (rhs = [1, N] / [N] / [1, C, H, W]: numpy's `add(lhs, rhs,
+    out=empty_like(lhs))`, xs/nn/functional.py:6-21). The result has lhs's shape, in logical row-major order."""
+    a = lhs.arr.logical_rowmajor()
+    b = rhs.arr.logical_rowmajor()
+    tail = tuple(s for s in b.shape)
+    while tail and tail[0] == 1:
+        tail = tail[1:]
+    if not tail or tuple(a.shape[len(a.shape) - len(tail):]) != tail:
+        raise ValueError(f"add: operands could not be broadcast together with shapes {a.shape} {b.shape}")
+    cols = b.size
+    rows = a.size // cols
+    tmp = DevArray.empty(a.shape)
+    tmp.cl = False
+    lib.xsb_broadcast_axis(b.ptr, tmp.wptr, 1, rows, cols, 1.0, 0, rt.stream())
+    out, y = _out_arr(out, a.shape)
+    ycl = y.cl
+    y.cl = False
+    lib.xsb_add(a.ptr, tmp.ptr, y.wptr, a.size, rt.stream())
+    rt.launches += 2
+    if ycl and len(a.shape) == 4:        # a preallocated 4-D buffer keeps channels-last storage
+        conv = y.as_cl()
+        if conv is not y:
+            y.buf[: y.size].copy_(conv.buf[: y.size])
+        y.cl = True
+    return _wire(out, (lhs, rhs), lhs.requires_grad or rhs.requires_grad, AddBackward, cache={"broadcast": (rows, cols)})
 
 
 def _gemm_fwd(x, w, bias, y):
@@ -446,6 +475,124 @@ def batch_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, moving_mean: Tensor,
                  cache={"axis_field": axis_field, "save_mean": save_mean, "save_invstd": save_invstd})
 
 
+# ---------------------------------------------------------------------------------------------- SURVEY 8f-4 ops
+def _unary(inputs, out, kind, grad_fn):
+    _mark_inputs(inputs)
+    x = inputs.arr
+    out, y = _out_arr(out, x.shape)
+    y.cl = x.cl
+    lib.xsb_unary_fwd(kind, x.ptr, y.wptr, x.size, rt.stream())
+    rt.launches += 1
+    return _wire(out, (inputs,), inputs.requires_grad, grad_fn)
+
+
+def sigmoid(inputs: Tensor, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:316-329: y = 1 / (1 + exp(-x))."""
+    return _unary(inputs, out, 0, SigmoidBackward)
+
+
+def tanh(inputs: Tensor, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:332-345."""
+    return _unary(inputs, out, 1, TanhBackward)
+
+
+class DeviceBitMask:
+    """`cache['mask']` of dropout2d: one bit per element on the device (bit set = kept); np.asarray(...) yields the
+    reference's 0/1 array in the tensor's PHYSICAL element order."""
+
+    def __init__(self, dev, count):
+        self.dev, self.count = dev, count
+
+    def __array__(self, dtype=None, copy=None):
+        bits = np.unpackbits(self.dev.cpu().numpy(), bitorder="little")[: self.count]
+        return bits if dtype is None else bits.astype(dtype)
+
+
+_DROPOUT_CALLS = [0]
+
+
+def dropout2d(inputs: Tensor, keep_prob: float = 0.5, out: Tensor = None, seed: int = None) -> Tensor:
+    """xs/nn/functional.py:650-674. Training: y = x * mask / keep_prob with mask ~ Bernoulli(keep_prob) per element, drawn
+    by a stateless device hash of (seed, call counter, element index) -- not NumPy's binomial stream, so parity is defined
+    GIVEN the mask (`out.cache['mask']`). Not training: the input passes through; without grad tracking it is returned."""
+    _mark_inputs(inputs)
+    if not GLOBAL.COMPUTE_GRAD:
+        return inputs
+    x = inputs.arr
+    out, y = _out_arr(out, x.shape)
+    y.cl = x.cl
+    mask = None
+    if GLOBAL.TRAINING:
+        mask = rt.empty((x.size + 7) // 8, "uint8")
+        _DROPOUT_CALLS[0] += 1
+        base = int(np.random.get_state()[1][0]) if seed is None else int(seed)     # follows np.random.seed(...)
+        lib.xsb_dropout_fwd(x.ptr, y.wptr, mask.data_ptr(), x.size, float(keep_prob),
+                            (base * 1000003 + _DROPOUT_CALLS[0]) & 0x7FFFFFFFFFFFFFFF, None, rt.stream())
+        rt.launches += 1
+    else:
+        x.flush()
+        y.wptr  # noqa: B018
+        y.buf[: max(x.size, 1)].copy_(x.buf[: max(x.size, 1)])
+    cache = {"mask": DeviceBitMask(mask, x.size) if mask is not None else None, "keep_prob": keep_prob}
+    return _wire(out, (inputs,), inputs.requires_grad, Dropout2DBackward, cache=cache)
+
+
+def pad2d(inputs: Tensor, padding: tuple, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:629-647: zero padding of the two spatial axes by (padding[0], padding[1]) on both sides."""
+    _mark_inputs(inputs)
+    x = inputs.arr.as_cl()
+    n, c, h, w = x.shape
+    ph, pw = int(padding[0]), int(padding[1])
+    out, y = _out_arr(out, (n, c, h + 2 * ph, w + 2 * pw))
+    y.cl = True
+    lib.xsb_pad2d_fwd(x.ptr, y.wptr, n, h, w, c, ph, pw, rt.stream())
+    rt.launches += 1
+    return _wire(out, (inputs,), inputs.requires_grad, Pad2DBackward, cache={"padding": (ph, pw)})
+
+
+def layer_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, epsilon: float = 1e-10, out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:743-775: statistics over every axis but 0 (biased variance), per-element gamma / beta of the
+    sample's shape. Computed on the logical (NCHW row-major) order, where a sample is one contiguous row."""
+    _mark_inputs(inputs)
+    x = inputs.arr.logical_rowmajor()
+    n = x.shape[0]
+    f = x.size // n
+    if gamma.arr.size != f or beta.arr.size != f:
+        raise ValueError(f"layer_norm: gamma / beta must have the sample's {f} elements")
+    out, y = _out_arr(out, x.shape)
+    want_cl = y.cl and len(x.shape) == 4 and out is not None and out.is_static
+    y.cl = False
+    mean, rstd = DevArray.empty((n,)), DevArray.empty((n,))
+    lib.xsb_layernorm_fwd(x.ptr, gamma.arr.logical_rowmajor().ptr, beta.arr.logical_rowmajor().ptr, y.wptr, mean.wptr, rstd.wptr,
+                          n, f, float(epsilon), rt.stream())
+    rt.launches += 1
+    if want_cl:
+        conv = y.as_cl()
+        if conv is not y:
+            y.buf[: y.size].copy_(conv.buf[: y.size])
+        y.cl = True
+    rg = inputs.requires_grad or gamma.requires_grad or beta.requires_grad
+    return _wire(out, (inputs, gamma, beta), rg, LayerNormBackward, cache={"mean": mean, "rstd": rstd})
+
+
+def group_norm(inputs: Tensor, gamma: Tensor, beta: Tensor, epsilon: float = 1e-5, groups: int = 16,
+               out: Tensor = None) -> Tensor:
+    """xs/nn/functional.py:778-812: statistics per (sample, group of C/groups channels) over (c, h, w), per-channel affine."""
+    _mark_inputs(inputs)
+    x = inputs.arr.as_cl()
+    n, c, h, w = x.shape
+    if c % groups != 0:
+        raise ValueError(f"group_norm: {c} channels are not divisible into {groups} groups")
+    out, y = _out_arr(out, x.shape)
+    y.cl = True
+    mean, rstd = DevArray.empty((n * groups,)), DevArray.empty((n * groups,))
+    lib.xsb_groupnorm_fwd(x.ptr, gamma.arr.ptr, beta.arr.ptr, y.wptr, mean.wptr, rstd.wptr, n, h * w, c, int(groups),
+                          float(epsilon), rt.stream())
+    rt.launches += 1
+    rg = inputs.requires_grad or gamma.requires_grad or beta.requires_grad
+    return _wire(out, (inputs, gamma, beta), rg, GroupNormBackward, cache={"mean": mean, "rstd": rstd, "groups": int(groups)})
+
+
 # ---------------------------------------------------------------------------------------------- losses
 def _loss_out(out, reduction):
     if reduction not in ("mean", "sum"):
@@ -477,14 +624,17 @@ def cross_entropy(x1: Tensor, x2: Tensor, reduction: str = "mean", out: Tensor =
     z = x1.arr.logical_rowmajor()
     c = z.shape[-1]
     rows = z.size // c
+    if x2.arr.size != rows:
+        raise ValueError(f"cross_entropy: {rows} rows of logits but {x2.arr.size} labels")
     sm = x1.cache.get("softmax")
     if sm is None or sm._arr is None or tuple(sm.arr.shape) != tuple(z.shape):
         sm = Tensor(DevArray.empty(z.shape))
         sm._arr.cl = False
     x1.cache["softmax"] = sm
     lib.xsb_softmax_xent_fwd(z.ptr, x2.arr.ptr, sm.arr.wptr, y.wptr, rows, c, 0 if reduction == "mean" else 1,
-                             rt.stream())
+                             rt.label_flag.data_ptr(), rt.stream())
     rt.launches += 1
+    out.cache["label_check"] = True     # a NaN loss is looked up against the kernel's bad-label flag on its first read
     if rows != z.shape[0] and reduction == "mean":
         raise NotImplementedError("cross_entropy 'mean' over >2-D logits")
     out.requires_grad = x1.requires_grad or x2.requires_grad

@@ -8,7 +8,7 @@ separate `+=` pass is ever run.
 """
 import ctypes
 
-from ..core.device import DevArray, rt
+from ..core.device import DevArray, fill_floats, rt
 from ..core.tensor import Parameter, Tensor
 from .._lib import lib
 
@@ -41,7 +41,7 @@ def accumulate_into(t, src):
         lib.xsb_axpy(g.peek_ptr(), src.ptr, 1.0, g.size, rt.stream())
         rt.launches += 1
     elif src.pending_zero:
-        g.buf[: g.size].zero_()
+        fill_floats(g.buf, 0.0, g.size)
     else:
         src.flush()
         g.buf[: g.size].copy_(src.buf[: g.size])   # first write: a plain device-to-device copy
@@ -67,6 +67,25 @@ def AddBackward(outputs: Tensor, relu_mask=None):
     operand instead of mask-in-place + copies."""
     dy = outputs.grad.arr
     targets = [t for t in outputs.in_bounds if t.requires_grad]
+    bcast = outputs.cache.get("broadcast")
+    if bcast is not None:
+        # a row-vector operand ([M, N] + [1, N] or [N]): its gradient is dY summed over the first mismatching axis
+        # (xs/nn/grad_fn.py:9-12); the full-shape operand takes dY itself
+        if relu_mask is not None:
+            lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), dy.peek_ptr(), dy.size, 0, rt.stream())
+            rt.launches += 1
+        rows, cols = bcast
+        for t in targets:
+            if t.arr.size == dy.size:
+                accumulate_into(t, dy)
+            else:
+                g = _grad_arr(t)
+                src = dy.logical_rowmajor()
+                tmp = DevArray.empty((cols,))
+                lib.xsb_reduce_axis(src.ptr, tmp.wptr, 1, rows, cols, 1.0, rt.stream())
+                rt.launches += 1
+                accumulate_into(t, DevArray(tmp.buf, g.shape, g.dtype, cl=g.cl))
+        return
     if relu_mask is not None:
         if all(_grad_arr(t).cl == dy.cl for t in targets):
             for t in targets:
@@ -97,9 +116,11 @@ def ReLUBackward(outputs: Tensor):
         mask = outputs.cache["mask"]
         fn = outputs.cache["grad_fn"].pop()
         outputs.grad_fn = fn
-        if fn is BatchNormBackward or fn is AddBackward:
+        if (fn is BatchNormBackward or fn is AddBackward) and outputs.is_dynamic:
             fn(outputs, relu_mask=mask)      # the producer's backward kernels apply the mask on the fly
             return
+        # (static graph: the producer LAYER runs the restored closure once more after this one -- reference behaviour,
+        # xs/layers/base.py:126-134 -- so the gradient itself must carry the mask, as the reference's in-place masking does)
         g = outputs.grad.arr
         lib.xsb_relu_bwd_mask(g.ptr, mask.data_ptr(), g.peek_ptr(), g.size, 0, rt.stream())
         rt.launches += 1
@@ -365,3 +386,91 @@ def MSELossBackward(outputs: Tensor):
                     gb.peek_ptr() if gb is not None else None, a.size, red,
                     ga.take_acc() if ga is not None else 0, gb.take_acc() if gb is not None else 0, rt.stream())
     rt.launches += 1
+
+
+# ------------------------------------------------------------------ SURVEY 8f-4 ops around the hot path
+def _unary_backward(kind):
+    def closure(outputs: Tensor):
+        inputs, = outputs.in_bounds
+        if inputs.requires_grad:
+            g = _grad_arr(inputs)
+            y, dy = _same_layout(outputs.arr, g), _same_layout(outputs.grad.arr, g)
+            lib.xsb_unary_bwd(kind, dy.ptr, y.ptr, g.peek_ptr(), g.size, g.take_acc(), rt.stream())
+            rt.launches += 1
+    return closure
+
+
+SigmoidBackward = _unary_backward(0)      # xs/nn/grad_fn.py:161-164: dX += dY * y * (1 - y)
+SigmoidBackward.__name__ = "SigmoidBackward"
+TanhBackward = _unary_backward(1)         # xs/nn/grad_fn.py:167-170: dX += dY * (1 - y^2)
+TanhBackward.__name__ = "TanhBackward"
+
+
+def Dropout2DBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:319-325: dX += mask * keep_prob * dY (the reference multiplies by keep_prob here; kept)."""
+    inputs, = outputs.in_bounds
+    if inputs.requires_grad:
+        g = _grad_arr(inputs)
+        dy = _same_layout(outputs.grad.arr, outputs.arr)
+        if g.cl != outputs.arr.cl:
+            raise NotImplementedError("dropout backward across layouts")
+        lib.xsb_dropout_bwd(dy.ptr, outputs.cache["mask"].dev.data_ptr(), g.peek_ptr(), g.size, float(outputs.cache["keep_prob"]),
+                            g.take_acc(), rt.stream())
+        rt.launches += 1
+
+
+def Pad2DBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:312-316: dX += the un-padded interior of dY."""
+    inputs, = outputs.in_bounds
+    if inputs.requires_grad:
+        ph, pw = outputs.cache["padding"]
+        n, c, h, w = inputs.shape
+        g = _grad_arr(inputs)
+        assert g.cl
+        lib.xsb_pad2d_bwd(outputs.grad.arr.as_cl().ptr, g.peek_ptr(), n, h, w, c, ph, pw, g.take_acc(), rt.stream())
+        rt.launches += 1
+
+
+def LayerNormBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:414-447: dgamma += sum_n dY*xhat, dbeta += sum_n dY, dX = closed form of the dvar / dmean chain.
+    (As shipped the reference reads `inputs.cache['normalized_x']` at line 418 and raises KeyError whenever gamma is
+    trainable; the formulas are its own.)"""
+    inputs, gamma, beta = outputs.in_bounds
+    x = inputs.arr.logical_rowmajor()
+    dy = outputs.grad.arr.logical_rowmajor()
+    n = x.shape[0]
+    f = x.size // n
+    gx = DevArray.empty(x.shape) if inputs.requires_grad else None
+    if gx is not None:
+        gx.cl = False
+    gg = _grad_arr(gamma) if gamma.requires_grad else None
+    gb = _grad_arr(beta) if beta.requires_grad else None
+    lib.xsb_layernorm_bwd(dy.ptr, x.ptr, gamma.arr.logical_rowmajor().ptr, outputs.cache["mean"].ptr, outputs.cache["rstd"].ptr,
+                          gx.wptr if gx is not None else None, gg.peek_ptr() if gg is not None else None,
+                          gb.peek_ptr() if gb is not None else None, n, f, 0, gg.take_acc() if gg is not None else 0,
+                          gb.take_acc() if gb is not None else 0, rt.stream())
+    rt.launches += 2
+    if gx is not None:
+        accumulate_rowmajor_into(inputs, gx)
+    _done(gamma)
+    _done(beta)
+
+
+def GroupNormBackward(outputs: Tensor):
+    """xs/nn/grad_fn.py:450-490 (per-channel dgamma / dbeta over (n, h, w); the shipped code adds a keepdims [1,C,1,1] sum
+    into a (C,) gradient and fails to broadcast -- the sums are its own)."""
+    inputs, gamma, beta = outputs.in_bounds
+    x = inputs.arr.as_cl()
+    dy = outputs.grad.arr.as_cl()
+    n, c, h, w = x.shape
+    gx = _grad_arr(inputs) if inputs.requires_grad else None
+    gg = _grad_arr(gamma) if gamma.requires_grad else None
+    gb = _grad_arr(beta) if beta.requires_grad else None
+    lib.xsb_groupnorm_bwd(dy.ptr, x.ptr, gamma.arr.ptr, outputs.cache["mean"].ptr, outputs.cache["rstd"].ptr,
+                          gx.peek_ptr() if gx is not None else None, gg.peek_ptr() if gg is not None else None,
+                          gb.peek_ptr() if gb is not None else None, n, h * w, c, outputs.cache["groups"],
+                          gx.take_acc() if gx is not None else 0, gg.take_acc() if gg is not None else 0,
+                          gb.take_acc() if gb is not None else 0, rt.stream())
+    rt.launches += 2
+    _done(gamma)
+    _done(beta)

@@ -14,7 +14,7 @@ buffer and passes grad_scale = 1/world.
 """
 import numpy as np
 
-from ..core.device import DevArray, rt, torch
+from ..core.device import DevArray, fill_floats, rt, torch
 from ..core.tensor import Tensor
 from .._lib import lib
 
@@ -36,6 +36,7 @@ class FlatState:
         self.flat_p = t.zeros(max(off, 1), dtype=t.float32, device=rt.device)
         self.flat_g = t.zeros(max(off, 1), dtype=t.float32, device=rt.device)
         self.extra = [t.zeros(max(off, 1), dtype=t.float32, device=rt.device) for _ in range(n_extra)]
+        self.gviews = []
         for p, o in zip(self.params, self.offsets):
             n = p.numel()
             old = p._arr
@@ -44,6 +45,7 @@ class FlatState:
             old.buf = view
             old.pending_zero = False
             gview = self.flat_g[o:o + n]
+            self.gviews.append(gview)
             pending = True
             if p._grad is not None and p._grad._arr is not None and not p._grad._arr.pending_zero:
                 gview.copy_(p._grad._arr.buf[:n])
@@ -126,9 +128,21 @@ class Optimizer:
             p.pending_uses = 0              # forwards whose backward never ran (e.g. validation) are forgotten here
 
     def _materialize_grads(self):
-        for p in self.flat.params:
+        for p, gview in zip(self.flat.params, self.flat.gviews):
+            g = p._grad._arr if p._grad is not None else None
+            if g is None or g.buf.data_ptr() != gview.data_ptr():
+                # the user replaced the gradient tensor (p.grad = Tensor(...)): bring it back into the flat buffer the
+                # fused kernel reads, and rebind the view
+                if g is not None and not g.pending_zero:
+                    src = g if g.cl == p._arr.cl else (g.as_cl() if p._arr.cl else g.logical_rowmajor())
+                    src.flush()
+                    gview.copy_(src.buf[: p.numel()])
+                    pending = False
+                else:
+                    pending = True
+                p._grad = Tensor(DevArray(gview, p._arr.shape, "float32", cl=p._arr.cl, pending_zero=pending))
             if p._grad._arr.pending_zero:      # parameter received no gradient this step
-                p._grad._arr.buf.zero_()
+                fill_floats(p._grad._arr.buf, 0.0)
                 p._grad._arr.pending_zero = False
 
     def step(self):
