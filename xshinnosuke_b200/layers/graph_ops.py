@@ -5,7 +5,7 @@ from ..nn import functional as F
 from ..nn.grad_fn import accumulate_into
 from ..utils.common import initialize_ops_grad
 from .._lib import lib
-from .base import Layer
+from .base import Layer, StaticOutput
 
 
 class Input(Layer):
@@ -69,13 +69,7 @@ class Add(Layer):
 
     def init_layer_out_tensor(self, x=None):
         x = self._in_bounds[0].data if x is None else x
-        if self._data is None or x.shape[0] > self._data.shape_capacity[0] or \
-                (x.shape[0] < self._data.shape_capacity[0] and not GLOBAL.TRAINING):
-            self._data = self._new_static(x, self.shape, [b.data for b in self._in_bounds])
-        elif x.shape[0] < self._data.shape_capacity[0]:
-            self._data.slices(slice(None, x.shape[0], None))
-        else:
-            self._data.slices(slice(None, None, None))
+        self._data = StaticOutput.fit(self._data, x.shape[0], self.shape, self.trainable, [b.data for b in self._in_bounds])
 
     def forward(self, x=None, *args, **kwargs):
         ins = [b.data for b in self._in_bounds]
