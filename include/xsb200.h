@@ -44,6 +44,9 @@ int xsb_version(void);
 const char* xsb_last_error(void);
 int xsb_init(int device);
 int xsb_device_sm_count(void);
+/* n > 0: the grid-sized (persistent, one CTA per SM) kernels plan for n SMs, leaving the rest to a concurrent collective
+ * (data parallelism: NCCL's all-reduce CTAs); 0: all SMs. */
+int xsb_set_sm_budget(int n);
 int xsb_stream_sync(void* stream);
 int xsb_memcpy_h2d(void* dst_dev, const void* src_host, int64_t bytes, void* stream);
 int xsb_memcpy_d2h(void* dst_host, const void* src_dev, int64_t bytes, void* stream);

@@ -26,6 +26,12 @@ def test_plan_buckets_walks_backwards_and_covers_everything():
     assert sorted(i for x in b for i in x[2]) == [0, 1, 2, 3, 4]
     assert plan_buckets([0], [5], 64, 10 ** 9) == [(0, 64, [0])]
     assert plan_buckets([], [], 0, 10) == []
+    # small tail bucket: the first-created parameters (their gradients come last) are reduced on their own
+    t = plan_buckets(offsets, sizes, 1280, 512, tail_floats=128)
+    assert [x[:2] for x in t] == [(128, 1280), (0, 128)] and t[-1][2] == [1, 0]
+    t = plan_buckets(offsets, sizes, 1280, 10 ** 9, tail_floats=100)
+    assert [x[:2] for x in t] == [(64, 1280), (0, 64)] and t[-1][2] == [0]
+    assert sorted(i for x in t for i in x[2]) == [0, 1, 2, 3, 4]
 
 
 @pytest.mark.parametrize("optimizer", ["sgd", "adam"])

@@ -1,5 +1,6 @@
 // libxsb200 runtime: error string, device init, small utilities.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -15,7 +16,16 @@ void xsb_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// SMs the grid-sized (persistent / one-wave) kernels may plan for. Under data parallelism NCCL's all-reduce CTAs run next to
+// the backward kernels: a kernel that needs EVERY SM for its one CTA per SM then waits for the collective's CTAs to leave
+// (the all-reduce is exposed although it "overlaps"); planning for 148 - k SMs leaves the collective its own.
+static int g_sm_budget = -1;      // -1: read XSB_SM_BUDGET on first use; 0: all SMs
+
 int xsb_sm_count_cached() {
+    if (g_sm_budget < 0) {
+        const char* e = getenv("XSB_SM_BUDGET");
+        g_sm_budget = e ? atoi(e) : 0;
+    }
     if (g_sm_count == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -24,7 +34,7 @@ int xsb_sm_count_cached() {
         }
         if (g_sm_count == 0) g_sm_count = 148;
     }
-    return g_sm_count;
+    return (g_sm_budget > 0 && g_sm_budget < g_sm_count) ? g_sm_budget : g_sm_count;
 }
 
 extern "C" {
@@ -50,6 +60,13 @@ int xsb_init(int device) {
 }
 
 int xsb_device_sm_count(void) { return xsb_sm_count_cached(); }
+
+// n > 0: grid-sized kernels plan for n SMs (see g_sm_budget); 0: all of them
+int xsb_set_sm_budget(int n) {
+    XSB_CHECK_ARG(n >= 0, "sm budget must be >= 0");
+    g_sm_budget = n;
+    return XSB_OK;
+}
 
 int xsb_stream_sync(void* stream) {
     XSB_CUDA(cudaStreamSynchronize(xsb_stream(stream)));
