@@ -1408,8 +1408,13 @@ static int tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvG
     static const int wg_halo = [] { const char* e = getenv("XSB_TC_WGRAD_HALO"); return (e && e[0] == '0') ? 0 : 1; }();
     if (wg_halo && halo_enabled()) {
         if (!accumulate) XSB_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.OC * g.KH * g.KW * g.C * sizeof(float), s));
-        const int rc = wgrad_halo(dy, x, dw, g, s);
+        int rc = wgrad_halo(dy, x, dw, g, s);
         if (rc != XSB_ERR_UNSUPPORTED) return rc;
+        static const int wg_strip = [] { const char* e = getenv("XSB_TC_WGRAD_STRIP"); return (e && e[0] == '0') ? 0 : 1; }();
+        if (wg_strip) {
+            rc = wgrad_strip(dy, x, dw, g, s);
+            if (rc != XSB_ERR_UNSUPPORTED) return rc;
+        }
     }
     const int P = g.N * g.OH * g.OW;
     static const int wg_bn_cap = [] { const char* e = getenv("XSB_TC_WG_BN"); return e ? atoi(e) : 128; }();   // measured: 128-wide tiles + 64-pixel k-blocks beat 256 x 32 (layer4 93 -> 73 us)

@@ -297,6 +297,211 @@ static int wgrad_halo(const float* dy, const float* x, float* dw, const ConvGeom
     return XSB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ row-strip wgrad (C, OC >= 128)
+// conv_wgrad_tc_k needs 128 B/clk of L2 -> SM traffic per SM to keep the tensor pipe busy (a 64 KB stage per 8 MMAs of
+// 128 x 128 x 8) against the ~55 B/clk an SM ingests: the wgrad of layers 2-4 of ResNet-18 sits at 415-430 TFLOP/s.
+// Here the K (pixel) dimension of one MMA chain is a STRIP of TH whole image rows, stored exactly as TMA delivers it:
+//   A = x halo strip  {32 ch, WX = W + 2*pad columns from w = -pad, TH rows from h0 + kh - pad}  -> TH*WX rows of 128 B
+//   B = dY strip      {32 oc, WX columns from ow = 0 (columns >= OW are out of bounds = 0), TH rows from h0}
+// so pixel (r, j) of the strip is row k = r*WX + j of BOTH blocks, and the operand of filter column kw is the A block viewed
+// kw rows (kw * 128 B) further: x[h0+r+kh-pad, j+kw-pad] pairs with dY[h0+r, j]. Rows of a view that run past an image row
+// (j + kw >= WX) or past the block meet dY's zero columns, so they contribute nothing (the A slack rows only have to hold
+// finite numbers: shared memory is zeroed once). One load of A and B feeds KW accumulators (KW * BN <= 512 TMEM columns);
+// M = 128 channels = four 32-channel blocks (descriptor LBO = block pitch), N = BN output channels.
+// 2.7 KB of operands per MMA instead of 8 KB. A pass = (filter row kh, 128-channel tile, BN-wide oc tile); the CTAs of a pass
+// split the strips (split-K) and leave with TMA reduce-adds, as conv_wgrad_halo_k does.
+struct WgradStripParams {
+    int n_tiles, tiles_h, TH, WX, K8;   // K8 = ceil(TH*WX / 8) MMAs (K = 8 pixels each) per filter column and strip
+    int KH, KW, pad, C;
+    int n_c_tiles, n_oc_tiles;          // C / 128, OC / BN
+    int a_cb_bytes, b_box_bytes, stage_bytes, n_stages, tx_bytes;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_strip_k(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                   const __grid_constant__ CUtensorMap tmW, const WgradStripParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int MAXS = 8;
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* ring = smem;                                             // [stage]: 4 A blocks, then BN/32 B blocks
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + p.n_stages * p.stage_bytes);
+    uint64_t* empty = full + MAXS;
+    uint64_t* tmem_full = empty + MAXS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.n_stages;
+    // pass -> (kh, channel tile, oc tile)
+    const int pass = blockIdx.y;
+    const int oc_t = pass % p.n_oc_tiles, c_t = (pass / p.n_oc_tiles) % p.n_c_tiles, kh = pass / (p.n_oc_tiles * p.n_c_tiles);
+    const int oc0 = oc_t * BN, cblk0 = c_t * 4;
+    const int t_begin = (int)((int64_t)blockIdx.x * p.n_tiles / gridDim.x);
+    const int t_end = (int)((int64_t)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
+
+    // zero the operand ring once: dY's slack rows must read as 0, the A slack rows as finite numbers
+    for (int i = threadIdx.x; i < p.n_stages * p.stage_bytes / 16; i += kThreads)
+        reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async_smem();
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmDy);
+        prefetch_tmap(&tmW);
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        int n_img = t_begin / p.tiles_h, th = t_begin - n_img * p.tiles_h;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int h0 = th * p.TH;
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one()) {
+                uint8_t* st = ring + s * p.stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)p.tx_bytes);
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb)
+                    tma_load_4d(st + cb * p.a_cb_bytes, &tmX, &full[s], (cblk0 + cb) * 32, -p.pad, h0 + kh - p.pad, n_img);
+#pragma unroll
+                for (int b = 0; b < BN / 32; ++b)
+                    tma_load_4d(st + 4 * p.a_cb_bytes + b * p.b_box_bytes, &tmDy, &full[s], oc0 + b * 32, 0, h0, n_img);
+            }
+            __syncwarp();
+            if (++th == p.tiles_h) { th = 0; ++n_img; }
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+        const uint32_t hi = desc_hi(512, kLayoutSW128Base32B);
+        const uint32_t ring_u32 = smem_u32(ring);
+        int s = 0;
+        uint32_t ph = 0, fresh = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_lo = desc_lo(ring_u32 + s * p.stage_bytes, (uint32_t)p.a_cb_bytes);
+                const uint32_t b_lo = desc_lo(ring_u32 + s * p.stage_bytes + 4 * p.a_cb_bytes, (uint32_t)p.b_box_bytes);
+                for (int kw = 0; kw < p.KW; ++kw) {
+                    const uint32_t tacc = tmem_base + (uint32_t)(kw * BN);
+                    for (int k8 = 0; k8 < p.K8; ++k8)          // K = 8 pixels = 8 rows of 128 B = 1024 B of both operands
+                        umma_tf32_split(tacc, a_lo + (uint32_t)(kw * 8 + k8 * 64), hi, b_lo + (uint32_t)(k8 * 64), hi, idesc,
+                                        k8 ? 1u : fresh);
+                }
+                umma_commit(&empty[s]);
+            }
+            __syncwarp();
+            fresh = 1;
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
+    } else {
+        // warp q reads TMEM lanes 32q..32q+31 = input channels (cblk0 + q)*32 + lane of the pass
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (t_end > t_begin) {
+            float* stage = reinterpret_cast<float*>(ring + q * 4096);    // the ring is idle: [32 oc][32 c] per warp
+            for (int kw = 0; kw < p.KW; ++kw) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * BN + c0), v);
+                    tmem_wait_ld();
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stage[j * 32 + lane] = __uint_as_float(v[j]);   // row = oc, column = c
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tmW, stage, (kh * p.KW + kw) * p.C + (cblk0 + q) * 32, oc0 + c0);
+                        bulk_commit();
+                    }
+                }
+            }
+            if (lane == 0) bulk_wait_all<0>();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dw must hold the value to accumulate onto (zeros for "="). XSB_ERR_UNSUPPORTED outside the envelope.
+static int wgrad_strip(const float* dy, const float* x, float* dw, const ConvGeom& g, cudaStream_t s) {
+    constexpr int BN = 128;
+    if (g.sh != 1 || g.sw != 1 || g.C % 128 != 0 || g.OC % BN != 0 || g.KW < 1 || g.KW * BN > 512 || g.KH > 16)
+        return XSB_ERR_UNSUPPORTED;
+    const int WX = g.W + 2 * g.pad;
+    if (WX != g.OW + g.KW - 1 || WX > 64 || WX < 1) return XSB_ERR_UNSUPPORTED;
+    // rows per strip: K = TH*WX <= 64 pixels, little padding to the next multiple of 8, few rows past the image bottom
+    int TH = 0;
+    double best = -1.0;
+    for (int th = 1; th * WX <= 64 && th <= g.OH; ++th) {
+        const int k8 = (th * WX + 7) / 8, tiles = (g.OH + th - 1) / th;
+        const double eff = (double)(th * WX) / (k8 * 8) * g.OH / ((double)tiles * th);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && th > TH)) { best = eff; TH = th; }
+    }
+    if (TH == 0) return XSB_ERR_UNSUPPORTED;
+    const int K8 = (TH * WX + 7) / 8;
+    const int tiles_h = (g.OH + TH - 1) / TH, n_tiles = g.N * tiles_h;
+    const int n_c_tiles = g.C / 128, n_oc_tiles = g.OC / BN;
+    const int passes = g.KH * n_c_tiles * n_oc_tiles;
+    const int S = xsb_sm_count_cached();
+    if (passes > S) return XSB_ERR_UNSUPPORTED;
+    int ctas = S / passes;
+    if (ctas > n_tiles) ctas = n_tiles;
+    if (ctas < 1) return XSB_ERR_UNSUPPORTED;
+    const int a_cb_bytes = (K8 * 8 + 8) * A_ROW_BYTES;        // + 8 slack rows: the views of kw > 0 and the K padding
+    const int b_box_bytes = K8 * 8 * A_ROW_BYTES;
+    const int stage_bytes = 4 * a_cb_bytes + (BN / 32) * b_box_bytes;
+    int stages = (227 * 1024 - 1024 - 512) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2 || stages * stage_bytes < 4 * 4096) return XSB_ERR_UNSUPPORTED;
+    if (!load_driver_entry_points()) return XSB_ERR_UNSUPPORTED;
+    CUtensorMap tx, tdy, tw;
+    cuuint64_t xd[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t xs_[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.W * g.C * 4, (cuuint64_t)g.H * g.W * g.C * 4};
+    cuuint32_t xb[4] = {32, (cuuint32_t)WX, (cuuint32_t)TH, 1};
+    cuuint64_t dd[4] = {(cuuint64_t)g.OC, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+    cuuint64_t ds[3] = {(cuuint64_t)g.OC * 4, (cuuint64_t)g.OW * g.OC * 4, (cuuint64_t)g.OH * g.OW * g.OC * 4};
+    cuuint32_t db[4] = {32, (cuuint32_t)WX, (cuuint32_t)TH, 1};
+    if (!make_map_tiled(&tx, x, 4, xd, xs_, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map_tiled(&tdy, dy, 4, dd, ds, db, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map_2d(&tw, dw, (uint64_t)g.OC, (uint64_t)g.KH * g.KW * g.C, 32, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return XSB_ERR_UNSUPPORTED;
+    WgradStripParams p{n_tiles, tiles_h, TH, WX, K8, g.KH, g.KW, g.pad, g.C, n_c_tiles, n_oc_tiles,
+                       a_cb_bytes, b_box_bytes, stage_bytes, stages, (4 + BN / 32) * TH * WX * A_ROW_BYTES};
+    const int smem = 1024 + stages * stage_bytes + 512;
+    static bool configured = false;
+    if (!configured) {
+        XSB_CUDA(cudaFuncSetAttribute(conv_wgrad_strip_k<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    conv_wgrad_strip_k<BN><<<dim3(ctas, passes), kThreads, smem, s>>>(tx, tdy, tw, p);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
 // Stem (C <= 4): xp is the zero-bordered 4-channel copy of the input ([N, Hp, Wp, 4], see stem_pad_c4_k); a row of the
 // A operand is the 32 floats (8 pixels x 4 channels) starting at pixel (oh*sh + kh, ow*sw): the tensor map walks
 // OVERLAPPING rows {32 floats, OW (stride sw pixels), Hp, N}. dw must already hold the value to accumulate onto.
