@@ -320,6 +320,9 @@ def parity_check(wl, args, xs, nn):
     return errs
 
 
+KERNEL_LIST = []     # (C-ABI call signature, device kernel name, eager us, graph-replay us) of one step, launch order
+
+
 def kernel_timeline(eager_step, graphed, lib, torch, n_replays=3):
     """Per C-ABI call kernel time measured INSIDE the CUDA-graph replay.
 
@@ -354,7 +357,7 @@ def kernel_timeline(eager_step, graphed, lib, torch, n_replays=3):
     import bisect
     evs = list(prof.events())
     ranges = sorted((ev.time_range.start, ev.time_range.end, int(ev.name.split("::")[1])) for ev in evs
-                    if ev.name.startswith("xsbcall::"))
+                    if ev.name.startswith("xsbcall::") and ev.device_type == DeviceType.CPU)   # (not the GPU-side twin)
     starts = [r[0] for r in ranges]
     launch_t = {ev.id: ev.time_range.start for ev in evs
                 if ev.device_type == DeviceType.CPU and ev.name.startswith(("cudaLaunch", "cuLaunch"))}
@@ -400,6 +403,7 @@ def kernel_timeline(eager_step, graphed, lib, torch, n_replays=3):
     by_call = {}
     for (idx, _, _), d in zip(eager_kernels, durs):
         by_call[idx] = by_call.get(idx, 0.0) + d
+    KERNEL_LIST[:] = [(signature(calls[idx][0], calls[idx][1]), kname, ed, d) for (idx, kname, ed), d in zip(eager_kernels, durs)]
     return [(calls[i][0], calls[i][1], by_call.get(i, 0.0) * 1e-6) for i in range(len(calls))], how
 
 
@@ -594,6 +598,11 @@ def run_ours(args, wl):
     out["kernel_timing"] = dict(how=how, kernels_sum_ms=total_s * 1e3, ms_per_step=ms / args.steps,
                                 sum_over_step=(total_s * 1e3) / (ms / args.steps) if ms else None,
                                 hbm_bound_share=h_share, top_shapes=top_shapes)
+    if args.dump_kernels:
+        with open(args.dump_kernels, "w") as f:
+            f.write("call\tkernel\teager_us\treplay_us\n")
+            for sig, kname, ed, d in KERNEL_LIST:
+                f.write(f"{sig}\t{kname[:90]}\t{ed:.1f}\t{d:.1f}\n")
     if parity is not None:
         out["parity_checked"] = parity
     if cpu is not None:
@@ -636,6 +645,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
+    ap.add_argument("--dump-kernels", default="", help="write the per-kernel list of one step (launch order, graph-replay us) here")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step (incl. the bucketed all-reduce) as one CUDA graph; auto = on")
     args = ap.parse_args()

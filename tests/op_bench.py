@@ -147,6 +147,13 @@ def main():
         if "conv_fwd" in ops:
             args = (x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr()) + g + (mode, ws, wsn, st)
             report("conv_fwd", lname, "xsb_conv2d_fwd", args, timed(lambda: lib.xsb_conv2d_fwd(*args), a.iters))
+        if "conv_fwd_stats" in ops:
+            import ctypes
+            stats, nparts = torch.zeros(rt.WS_STATS_FLOATS, device=rt.device), ctypes.c_int(0)
+            args = (x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr()) + g + (mode, ws, wsn)
+            tail = (stats.data_ptr(), rt.WS_STATS_FLOATS, ctypes.byref(nparts), st)
+            report("conv_fwd_st", lname, "xsb_conv2d_fwd_stats", args + (st,),
+                   timed(lambda: lib.xsb_conv2d_fwd_stats(*args, *tail), a.iters), f"(partials {nparts.value})")
         if "conv_dgrad" in ops and C >= 32:   # (the first layer's input needs no gradient)
             args = (dy.data_ptr(), w.data_ptr(), dx.data_ptr()) + g + (0, mode, ws, wsn, st)
             report("conv_dgrad", lname, "xsb_conv2d_dgrad", args, timed(lambda: lib.xsb_conv2d_dgrad(*args), a.iters))

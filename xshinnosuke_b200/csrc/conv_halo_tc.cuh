@@ -200,14 +200,26 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // epilogue warp q owns accumulator rows 32q..32q+31 = output rows 4q..4q+3 of the tile (8 pixels each): TMEM ->
         // registers (+bias) -> swizzled staging block -> ONE TMA store (or reduce-add) of a {32 ch, 8 w, 4 h} box; the
-        // tensor map clips rows / columns past the image, so partial tiles need no predication
+        // tensor map clips rows / columns past the image, so partial tiles need no predication. The TMEM load of chunk
+        // i+1 is in flight while chunk i is staged. (Measured: a second staging block per warp -- store i-1 still reading
+        // while chunk i is staged -- changes nothing on the stem and costs the 64-channel 3x3 layers 3 us: their MMAs are
+        // bound by the same shared-memory port the faster epilogue then competes for.)
         const int q = warp & 3;
         uint8_t* stage = sOut + q * 4096;
         int buf = 0;
         uint32_t tph = 0;
-        Moments run[BN / 32];   // lane j: running statistics of columns 32*i + j over this warp's rows of every tile
+        // BatchNorm statistics. REG_STATS (BN = 64): every thread keeps sum / sum of squares of ITS accumulator row for all
+        // 64 columns over all tiles of the CTA in registers (bias-free values: the bias is the pivot) -- no shared-memory
+        // reads, no dependent chains; lanes and warps are merged ONCE per CTA. Otherwise: per-chunk column moments from
+        // the staged block, Chan-merged per tile.
+        constexpr bool REG_STATS = (BN == 64);
+        constexpr int NRS = REG_STATS ? BN : 1, NRUN = REG_STATS ? 1 : BN / 32;
+        float rs1[NRS], rs2[NRS], rcnt = 0.f;
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) run[i] = Moments{0.f, 0.f, 0.f};
+        for (int i = 0; i < NRS; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
+        Moments run[NRUN];   // lane j: running statistics of columns 32*i + j over this warp's rows of every tile
+#pragma unroll
+        for (int i = 0; i < NRUN; ++i) run[i] = Moments{0.f, 0.f, 0.f};
         int n_img = blockIdx.x / tiles_per_img, rem = blockIdx.x - n_img * tiles_per_img;
         const int step_img = gridDim.x / tiles_per_img, step_rem = gridDim.x - step_img * tiles_per_img;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -220,16 +232,32 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int h = 0; h < 4; ++h)
                     if (oh0 + h < p.OH) vm |= wmask << (8 * h);
             }
+            const bool mine = (vm >> lane) & 1u;
+            if (REG_STATS && mine) rcnt += 1.f;
             mbar_wait(&tmem_full[buf], tph);
             tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+            uint32_t v[2][32];
+            tmem_ld32(t0, v[0]);
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+            for (int ci = 0; ci < BN / 32; ++ci) {
+                const int c0 = ci * 32;
+                uint32_t (&r)[32] = v[ci & 1];
                 tmem_wait_ld();
+                tmem_regs_ready(r);
+                if (ci + 1 < BN / 32) tmem_ld32(t0 + (uint32_t)(c0 + 32), v[(ci + 1) & 1]);
                 float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+                if (REG_STATS) {
+                    if (mine) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            rs1[(REG_STATS ? c0 : 0) + j] += o[j];
+                            rs2[(REG_STATS ? c0 : 0) + j] = fmaf(o[j], o[j], rs2[(REG_STATS ? c0 : 0) + j]);
+                        }
+                    }
+                }
                 if (p.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -242,14 +270,17 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 stage_rows_sw128(stage, lane, o);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0 && oh0 < p.OH) {
-                    if (p.accumulate)
-                        tma_reduce_add_4d(&tmO, stage, c0, ow0, oh0, n_img);
-                    else
-                        tma_store_4d(&tmO, stage, c0, ow0, oh0, n_img);
+                if (lane == 0) {
+                    if (oh0 < p.OH) {
+                        if (p.accumulate)
+                            tma_reduce_add_4d(&tmO, stage, c0, ow0, oh0, n_img);
+                        else
+                            tma_store_4d(&tmO, stage, c0, ow0, oh0, n_img);
+                    }
                     bulk_commit();
                 }
-                if (p.stats) run[c0 / 32] = merge_moments(run[c0 / 32], stage_col_moments(stage, lane, vm));
+                if (!REG_STATS && p.stats)
+                    run[REG_STATS ? 0 : ci] = merge_moments(run[REG_STATS ? 0 : ci], stage_col_moments(stage, lane, vm));
             }
             tc_fence_before();
             __syncwarp();
@@ -265,11 +296,52 @@ conv_halo_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             epilogue_bar();   // ... once EVERY warp's last store has finished reading its staging block
             float* sStat = reinterpret_cast<float*>(sOut);
+            if (REG_STATS) {
+                // thread -> (n, mean, M2) per column (n is the same for all columns of a thread), then a transposing
+                // butterfly over the warp: level l exchanges half of the remaining columns with lane ^ (16 >> l), so
+                // after 5 levels lane L holds columns 2L, 2L+1 merged over all 32 lanes (62 merges, not 64 x 5)
+                float n = rcnt;
+                const float inv = n > 0.f ? 1.f / n : 0.f;
 #pragma unroll
-            for (int i = 0; i < BN / 32; ++i) {
-                sStat[q * 3 * BN + i * 32 + lane] = run[i].n;
-                sStat[(q * 3 + 1) * BN + i * 32 + lane] = run[i].mean;
-                sStat[(q * 3 + 2) * BN + i * 32 + lane] = run[i].m2;
+                for (int i = 0; i < NRS; ++i) {
+                    const float mean = rs1[i] * inv;
+                    rs2[i] = fmaxf(rs2[i] - rs1[i] * mean, 0.f);
+                    rs1[i] = mean;
+                }
+#pragma unroll
+                for (int lvl = 0; lvl < 5; ++lvl) {
+                    const int mask = 16 >> lvl, half = (NRS / 2) >> lvl;
+                    const bool up = (lane & mask) != 0;
+                    const float n_o = __shfl_xor_sync(0xFFFFFFFFu, n, mask);
+                    const float n_t = n + n_o;
+                    const float f = n_t > 0.f ? n_o / n_t : 0.f;     // weight of the partner's half
+                    const float nf = n * f;
+#pragma unroll
+                    for (int i = 0; i < half; ++i) {
+                        const float keep_m = up ? rs1[i + half] : rs1[i], send_m = up ? rs1[i] : rs1[i + half];
+                        const float keep_q = up ? rs2[i + half] : rs2[i], send_q = up ? rs2[i] : rs2[i + half];
+                        const float om = __shfl_xor_sync(0xFFFFFFFFu, send_m, mask);
+                        const float oq = __shfl_xor_sync(0xFFFFFFFFu, send_q, mask);
+                        const float d = om - keep_m;
+                        rs1[i] = keep_m + d * f;
+                        rs2[i] = keep_q + oq + d * d * nf;
+                    }
+                    n = n_t;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int col = 2 * lane + i;
+                    sStat[q * 3 * BN + col] = n;
+                    sStat[(q * 3 + 1) * BN + col] = rs1[REG_STATS ? i : 0] + (p.bias ? __ldg(p.bias + col) : 0.f);
+                    sStat[(q * 3 + 2) * BN + col] = rs2[REG_STATS ? i : 0];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NRUN; ++i) {
+                    sStat[q * 3 * BN + i * 32 + lane] = run[i].n;
+                    sStat[(q * 3 + 1) * BN + i * 32 + lane] = run[i].mean;
+                    sStat[(q * 3 + 2) * BN + i * 32 + lane] = run[i].m2;
+                }
             }
             epilogue_bar();
             for (int col = q * 32 + lane; col < BN; col += 128) {

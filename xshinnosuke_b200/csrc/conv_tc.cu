@@ -54,68 +54,87 @@ struct FpropParams {
 };
 
 // Non-strided epilogue shared by the 1-CTA and 2-CTA im2col kernels. Every MMA has completed, so the operand ring is
-// idle: its first 16 KB become four SWIZZLE_128B staging blocks (one per epilogue warp); a warp's 32 rows x 32 columns
+// idle: its first 32 KB become eight SWIZZLE_128B staging blocks (TWO per epilogue warp); a warp's 32 rows x 32 columns
 // leave as ONE TMA store / reduce-add of a {32 ch, 32 pixel} box of out[M, ldo] (rows >= M are clipped by the tensor
-// map); optional BatchNorm partial statistics are gathered from the staged block.
+// map); optional BatchNorm partial statistics are gathered from the staged block. This epilogue is EXPOSED (one tile per
+// CTA), so it is software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is staged, and chunk i is
+// staged while the TMA store of chunk i-1 still reads the other staging block (one store may stay pending).
+constexpr int EPI_STAGE_BYTES = 8 * 4096;     // staging blocks; the statistics scratch ([4][3][BN] floats) follows
+template <int BN>
+__device__ __forceinline__ void epilogue_chunk(const FpropParams& p, const CUtensorMap& tmO, uint8_t* sA, uint8_t* stage,
+                                               uint32_t (&r)[32], int q, int lane, int m0, int n0, int c0) {
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+            o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+        }
+    }
+    if (lane == 0) bulk_wait_read<1>();      // the store that last used THIS block (two chunks ago) has read it
+    __syncwarp();
+    stage_rows_sw128(stage, lane, o);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && m0 + q * 32 < p.M) {
+        if (p.accumulate)
+            tma_reduce_add_2d(&tmO, stage, n0 + c0, m0 + q * 32);
+        else
+            tma_store_2d(&tmO, stage, n0 + c0, m0 + q * 32);
+    }
+    if (lane == 0) bulk_commit();            // (an empty group keeps the wait_group<1> bookkeeping uniform)
+    if (p.stats) {   // this warp's 32 rows of columns c0..c0+31 -> (n, mean, M2) per column
+        const int left = p.M - (m0 + q * 32);
+        const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? ((1u << left) - 1u) : 0u);
+        const Moments mo = stage_col_moments(stage, lane, vm);
+        float* sStat = reinterpret_cast<float*>(sA + EPI_STAGE_BYTES) + q * 3 * BN + c0 + lane;
+        sStat[0] = mo.n;
+        sStat[BN] = mo.mean;
+        sStat[2 * BN] = mo.m2;
+    }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_store_tma(const FpropParams& p, const CUtensorMap* tmOp, uint32_t tmem_base,
                                                    uint8_t* sA, int q, int lane, int m_tile, int m0, int n0, int ncols) {
     const CUtensorMap& tmO = *tmOp;
     const int row = q * 32 + lane;
-        uint8_t* stage = sA + q * 4096;
+    uint8_t* stage0 = sA + q * 8192;
+    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t ra[32], rb[32];
+    tmem_ld32(t0, ra);
 #pragma unroll 1
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    for (int c0 = 0; c0 < ncols; c0 += 64) {
+        tmem_wait_ld();
+        tmem_regs_ready(ra);
+        const bool has_b = c0 + 32 < ncols;
+        if (has_b) tmem_ld32(t0 + (uint32_t)(c0 + 32), rb);
+        epilogue_chunk<BN>(p, tmO, sA, stage0, ra, q, lane, m0, n0, c0);
+        if (has_b) {
             tmem_wait_ld();
-            float o[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
-            if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-                    o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
-                }
-            }
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
-            stage_rows_sw128(stage, lane, o);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && m0 + q * 32 < p.M) {
-                if (p.accumulate)
-                    tma_reduce_add_2d(&tmO, stage, n0 + c0, m0 + q * 32);
-                else
-                    tma_store_2d(&tmO, stage, n0 + c0, m0 + q * 32);
-                bulk_commit();
-            }
-            if (p.stats) {   // this warp's 32 rows of columns c0..c0+31 -> (n, mean, M2) per column
-                const int left = p.M - (m0 + q * 32);
-                const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? ((1u << left) - 1u) : 0u);
-                const Moments mo = stage_col_moments(stage, lane, vm);
-                float* sStat = reinterpret_cast<float*>(sA + 16384) + q * 3 * BN + c0 + lane;
-                sStat[0] = mo.n;
-                sStat[BN] = mo.mean;
-                sStat[2 * BN] = mo.m2;
-            }
+            tmem_regs_ready(rb);
+            if (c0 + 64 < ncols) tmem_ld32(t0 + (uint32_t)(c0 + 64), ra);
+            epilogue_chunk<BN>(p, tmO, sA, stage0 + 4096, rb, q, lane, m0, n0, c0 + 32);
         }
-        if (lane == 0) bulk_wait_all<0>();
-        if (p.stats) {   // merge the four warps, one partial per CTA and column
-            epilogue_bar();
-            const float* sStat = reinterpret_cast<const float*>(sA + 16384);
-            for (int col = row; col < ncols; col += 128) {
-                Moments acc{0.f, 0.f, 0.f};
+    }
+    if (lane == 0) bulk_wait_all<0>();
+    if (p.stats) {   // merge the four warps, one partial per CTA and column
+        epilogue_bar();
+        const float* sStat = reinterpret_cast<const float*>(sA + EPI_STAGE_BYTES);
+        for (int col = row; col < ncols; col += 128) {
+            Moments acc{0.f, 0.f, 0.f};
 #pragma unroll
-                for (int w4 = 0; w4 < 4; ++w4)
-                    acc = merge_moments(acc, Moments{sStat[w4 * 3 * BN + col], sStat[(w4 * 3 + 1) * BN + col],
-                                                     sStat[(w4 * 3 + 2) * BN + col]});
-                float* dst = p.stats + (int64_t)m_tile * 3 * p.ldo + n0 + col;
-                dst[0] = acc.n;
-                dst[p.ldo] = acc.mean;
-                dst[2 * p.ldo] = acc.m2;
-            }
+            for (int w4 = 0; w4 < 4; ++w4)
+                acc = merge_moments(acc, Moments{sStat[w4 * 3 * BN + col], sStat[(w4 * 3 + 1) * BN + col],
+                                                 sStat[(w4 * 3 + 2) * BN + col]});
+            float* dst = p.stats + (int64_t)m_tile * 3 * p.ldo + n0 + col;
+            dst[0] = acc.n;
+            dst[p.ldo] = acc.mean;
+            dst[2 * p.ldo] = acc.m2;
         }
+    }
 }
 
 template <int BN, int STAGES, int OCC>
@@ -125,6 +144,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     constexpr int A_BYTES = BM * A_ROW_BYTES;
     constexpr int B_BYTES = BN * A_ROW_BYTES;
+    static_assert(STAGES * A_BYTES >= EPI_STAGE_BYTES + 12 * BN * 4, "epilogue staging + statistics scratch live in the A ring");
     uint8_t* smem = align1024(smem_raw);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -1396,7 +1416,6 @@ int xsb_tc_conv_dgrad(const float* dy, const float* w, float* dx, const ConvGeom
                       int64_t ws_floats, cudaStream_t s) {
     return counted(tc_conv_dgrad(dy, w, dx, g, accumulate, ws, ws_floats, s));
 }
-
 static int tc_conv_wgrad(const float* dy, const float* x, float* dw, const ConvGeom& g, int accumulate, float* ws,
                          int64_t ws_floats, cudaStream_t s) {
     if (stem_ok(g) && aligned16(dy) && aligned16(x)) return stem_wgrad(dy, x, dw, g, accumulate, ws, ws_floats, s);

@@ -223,14 +223,28 @@ __device__ __forceinline__ Moments stage_col_moments(const uint8_t* stage, int l
     const int cl = lane >> 2, ci = lane & 3;
     const int r0 = __ffs(vm) - 1;
     const float K = sf[r0 * 32 + (((cl ^ (r0 & 7)) << 2) | ci)];
-    float s1 = 0.f, s2 = 0.f;
+    float s1, s2;
+    if (vm == 0xFFFFFFFFu) {   // full block (the common case): four independent chains instead of one of 32 links
+        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < 32; ++r)
-        if ((vm >> r) & 1u) {
+        for (int r = 0; r < 32; ++r) {
             const float d = sf[r * 32 + (((cl ^ (r & 7)) << 2) | ci)] - K;
-            s1 += d;
-            s2 = fmaf(d, d, s2);
+            a1[r & 3] += d;
+            a2[r & 3] = fmaf(d, d, a2[r & 3]);
         }
+        s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+        s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+    } else {
+        s1 = 0.f;
+        s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+            if ((vm >> r) & 1u) {
+                const float d = sf[r * 32 + (((cl ^ (r & 7)) << 2) | ci)] - K;
+                s1 += d;
+                s2 = fmaf(d, d, s2);
+            }
+    }
     m.n = (float)__popc(vm);
     const float inv = 1.f / m.n;
     m.mean = K + s1 * inv;
@@ -304,6 +318,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are defined only after wait::ld. When a load is left in flight
+// across other work (software-pipelined epilogues), this empty asm pins the first use of the registers BEHIND the wait
+// (asm volatile statements keep their order; plain register reads would otherwise be free to move above it).
+__device__ __forceinline__ void tmem_regs_ready(uint32_t (&r)[32]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                      "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
 // zero 32 columns of this warp's 32 TMEM lanes (accumulators are always accumulated INTO: see kThreads2)
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
     const uint32_t z = 0u;
