@@ -153,6 +153,15 @@ int xsb_bn_bwd_dxsum(const float* dy, const float* x, const float* gamma, const 
                      int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
                      const uint8_t* relu_mask /* nullable */, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done,
                      void* stream);
+/* xsb_bn_bwd_dxsum for a BatchNorm whose (in-place rectified) output feeds a 3x3 / stride 2 / pad 1 max-pool: dy is the
+ * pool's backward gather of dpool[N,OH,OW,C] through argmax (xs/nn/grad_fn.py:206-235), masked by relu_mask
+ * (xs/nn/grad_fn.py:146-157) -- formed on the fly in both passes, the full-size dy[N,H,W,C] is never written.
+ * x, dx: [N,H,W,C]. dxsum nullable. XSB_ERR_UNSUPPORTED (3): nothing launched, run xsb_maxpool2d_bwd + xsb_bn_bwd. */
+int xsb_bn_bwd_pool_dxsum(const float* dpool, const uint8_t* argmax, const float* x, const float* gamma,
+                          const float* save_mean, const float* save_invstd, float* dx, float* dgamma /* nullable */,
+                          float* dbeta /* nullable */, int N, int H, int W, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
+                          const uint8_t* relu_mask /* nullable */, float* ws, float* dxsum /* nullable */, int acc_dxsum,
+                          void* stream);
 /* batch statistics from the per-CTA (count, mean, M2) partials a convolution's epilogue left (xsb_conv2d_fwd_stats):
  * same outputs and running-statistics update as xsb_bn_stats (xs/nn/functional.py:689-706), no pass over x. */
 int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* running_mean, float* running_var,

@@ -215,6 +215,19 @@ class FakeLib:
         _store(f32(dxsum, C), contrib.sum(axis=0), acc_dxsum)
         done._obj.value = 1
 
+    def _bn_bwd_pool_dxsum(self, dpool, amax, x, gamma, smean, sinv, dx, dgamma, dbeta, N, H, W, C, acc_dx, acc_dg, acc_db,
+                           rmask, ws, dxsum, acc_dxsum, s):
+        # contract: xsb_maxpool2d_bwd (3x3, stride 2, pad 1) into a scratch dy, then xsb_bn_bwd(_dxsum) on it
+        R = N * H * W
+        dy = torch.zeros(R * C, dtype=torch.float32)
+        self._maxpool2d_bwd(dpool, amax, dy.data_ptr(), N, H, W, C, 3, 2, 2, 1, 0, s)
+        before = f32(dx, R * C).reshape(R, C).astype(np.float64).copy() if acc_dx else 0.0
+        self._bn_bwd(dy.data_ptr(), x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, rmask, ws, s)
+        if dxsum:
+            contrib = f32(dx, R * C).reshape(R, C).astype(np.float64) - before
+            _store(f32(dxsum, C), contrib.sum(axis=0), acc_dxsum)
+        return 0
+
     def _bn_finalize(self, part, P, R, C, rm, rv, smean, sinv, eps, mom, s):
         pv = f32(part, P * 3 * C).reshape(P, 3, C).astype(np.float64)
         n, mean, m2 = pv[:, 0], pv[:, 1], pv[:, 2]

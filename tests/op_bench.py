@@ -55,7 +55,7 @@ def timed(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ops", default="conv_fwd,conv_dgrad,conv_wgrad,bn_fwd,bn_bwd,relu_fwd,relu_bwd,add,maxpool_fwd,"
-                                     "maxpool_bwd,colsum,sgd,adam")
+                                     "maxpool_bwd,bnpool,colsum,sgd,adam")
     ap.add_argument("--shapes", default="r224")
     ap.add_argument("--math", default="tf32")
     ap.add_argument("--iters", type=int, default=20)
@@ -199,7 +199,7 @@ def main():
                 if "maxpool_bwd" in ops:
                     report("maxpool_bwd", f"{lname}p{pk_}", "xsb_maxpool2d_bwd", args2, timed(lambda: lib.xsb_maxpool2d_bwd(*args2), a.iters))
                 del py, am, xr
-        if not a.sweep and lname == "stem" and ("maxpool_fwd" in ops or "maxpool_bwd" in ops):
+        if not a.sweep and lname == "stem" and ("maxpool_fwd" in ops or "maxpool_bwd" in ops or "bnpool" in ops):
             PH = (OH + 2 - 3) // 2 + 1
             py, am = dev(N, PH, PH, OC), torch.zeros(N * PH * PH * OC, dtype=torch.uint8, device=rt.device)
             yr = torch.relu(y)
@@ -210,6 +210,17 @@ def main():
             args2 = (py.data_ptr(), am.data_ptr(), dy.data_ptr(), N, OH, OH, OC, 3, 2, 2, 1, 0, st)
             if "maxpool_bwd" in ops:
                 report("maxpool_bwd", lname, "xsb_maxpool2d_bwd", args2, timed(lambda: lib.xsb_maxpool2d_bwd(*args2), a.iters))
+            if "bnpool" in ops:      # the stem's BN -> ReLU -> pool as fused kernels (forward: one launch, backward: two)
+                del yr
+                args3 = (y.data_ptr(), sm.data_ptr(), si.data_ptr(), gam.data_ptr(), bet.data_ptr(), py.data_ptr(), am.data_ptr(),
+                         mask.data_ptr(), N, OH, OH, OC, 3, 2, 2, 1, st)
+                report("bnpool_fwd", lname, "xsb_bn_relu_maxpool_fwd", args3,
+                       timed(lambda: lib.xsb_bn_relu_maxpool_fwd(*args3), a.iters), "(replaces bn_apply+relu and maxpool_fwd)")
+                dxo, dg, db = dev(N, OH, OH, OC), dev(OC), dev(OC)
+                args4 = (py.data_ptr(), am.data_ptr(), y.data_ptr(), gam.data_ptr(), sm.data_ptr(), si.data_ptr(), dxo.data_ptr(),
+                         dg.data_ptr(), db.data_ptr(), N, OH, OH, OC, 0, 0, 0, mask.data_ptr(), wss, None, 0, st)
+                report("bnpool_bwd", lname, "xsb_bn_bwd_pool_dxsum", args4,
+                       timed(lambda: lib.xsb_bn_bwd_pool_dxsum(*args4), a.iters), "(replaces maxpool_bwd and bn_bwd)")
         del x, w, y, dy, dx, dw
         torch.cuda.empty_cache()
     P = 11232612 // 64 * 64 + 64 * 82

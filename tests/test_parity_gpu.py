@@ -400,7 +400,8 @@ def test_conv_cta_pair_kernels_tf32(n, c, h, oc, k, s, p):
         xs.set_math_mode("fp32")
 
 
-@pytest.mark.parametrize("n,c,h,k,s,p", [(4, 64, 20, 3, 2, 1), (3, 8, 17, 3, 2, 1), (2, 16, 12, 2, 2, 0), (2, 64, 9, 3, 1, 1)])
+@pytest.mark.parametrize("n,c,h,k,s,p", [(4, 64, 20, 3, 2, 1), (3, 8, 17, 3, 2, 1), (2, 16, 12, 2, 2, 0), (2, 64, 9, 3, 1, 1),
+                                         (2, 64, 30, 3, 2, 1), (5, 32, 13, 3, 2, 1), (1, 128, 7, 3, 2, 1)])
 def test_bn_relu_maxpool_fused_equals_unfused(n, c, h, k, s, p):
     """BatchNormalization -> ReLU(inplace) -> MaxPooling2D: the fused kernel (pool straight from the BN input, the
     rectified tensor never materialised) must give bit-identical pooled values, arg-max, ReLU mask effect and input
@@ -414,13 +415,18 @@ def test_bn_relu_maxpool_fused_equals_unfused(n, c, h, k, s, p):
     x = rs.randn(n, c, h, h).astype(np.float32)
     g = None
     res = []
+    keep = (xs.runtime.fuse_bn_relu_pool, xs.runtime.fuse_pool_bn_bwd)
+    bwd_calls = []
     for fuse in (True, False):
-        xs.runtime.fuse_bn_relu_pool = fuse     # opt-in fusion (off by default: measured no faster)
+        xs.runtime.fuse_bn_relu_pool = "all" if fuse else False     # forward: BN apply + ReLU + mask + pool in one kernel
+        xs.runtime.fuse_pool_bn_bwd = fuse      # backward: the BatchNorm kernels gather the pool's gradient (3x3/2 only)
         np.random.seed(0)
         bn, relu, pool = BatchNormalization(), ReLU(True), MaxPooling2D(k, s, p)
         calls = []
         orig = lib.xsb_bn_relu_maxpool_fwd
         lib.xsb_bn_relu_maxpool_fwd = lambda *a: (calls.append(1), orig(*a))[1]
+        orig_b = lib.xsb_bn_bwd_pool_dxsum
+        lib.xsb_bn_bwd_pool_dxsum = lambda *a: (bwd_calls.append(fuse), orig_b(*a))[1]
         try:
             tx = xs.tensor(x, requires_grad=True)
             z = relu(bn(tx))
@@ -433,9 +439,11 @@ def test_bn_relu_maxpool_fused_equals_unfused(n, c, h, k, s, p):
             res.append((yv, am, tx.grad.eval, bn.parameters()[0].grad.eval, len(calls)))
         finally:
             lib.xsb_bn_relu_maxpool_fwd = orig
-            xs.runtime.fuse_bn_relu_pool = False
+            lib.xsb_bn_bwd_pool_dxsum = orig_b
+            xs.runtime.fuse_bn_relu_pool, xs.runtime.fuse_pool_bn_bwd = keep
     (y1, a1, dx1, dg1, c1), (y0, a0, dx0, dg0, c0) = res
     assert c1 == 1 and c0 == 0
+    assert bwd_calls == ([True] if (k, s, p) == (3, 2, 1) else [])
     assert np.array_equal(y1, y0) and np.array_equal(a1, a0)
     # (the BatchNorm backward sums use atomics: summation order, hence the last bits, vary from run to run)
     assert X.rel_err(dx1, dx0) <= 1e-6 and X.rel_err(dg1, dg0) <= 1e-6

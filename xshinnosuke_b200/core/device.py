@@ -40,9 +40,15 @@ class Runtime:
         self._ws_stats = None
         self._label_flag = None
         self.launches = 0          # kernel-launching C-ABI calls issued (bench.py reports it)
-        # BatchNorm -> ReLU -> MaxPool as one kernel (xsb_bn_relu_maxpool_fwd). Measured on the R224 stem: 288 us against
-        # 124 + 131 us for the two bandwidth kernels it replaces (the tiled kernel is latency-bound) -> off by default
-        self.fuse_bn_relu_pool = False
+        # BatchNorm -> in-place ReLU -> MaxPool as one kernel (xsb_bn_relu_maxpool_fwd): True = the 3x3 / stride 2 / pad 1
+        # pool of the ResNet stem (direct kernel: 165 us against 135 + 90 us for the two bandwidth kernels it replaces on
+        # the R224 stem), "all" = any geometry (shared-memory tile kernel, measured no faster: 288 us), False = never
+        self.fuse_bn_relu_pool = {"0": False, "all": "all"}.get(os.environ.get("XSB_FUSE_BN_RELU_POOL", "1"), True)
+        # ... and its backward: the BatchNorm backward gathers the 3x3/2 pool's gradient on the fly (xsb_bn_bwd_pool_dxsum)
+        # instead of reading a scattered copy twice. The gather (~350 instructions per 2x2 quad) is paid twice and the
+        # kernels are instruction-bound: 396 us against 88 + 311 us back to back on L2-warm tensors, but -42 us inside the
+        # training step (5.419 -> 5.377 ms), where the 411 MB scattered copy is cold
+        self.fuse_pool_bn_bwd = os.environ.get("XSB_FUSE_POOL_BN_BWD", "1") != "0"
 
     def ensure(self):
         if self.ready:

@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x, float* dx, const float* __restrict__ mean,
                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ sums,
                        float invM, int64_t nvec, int CV, const uint8_t* __restrict__ rmask, float* dgamma, float* dbeta,
-                       int acc_gamma, int acc_beta, float* dxsum, float* sums_rw, unsigned* ticket) {
+                       int acc_gamma, int acc_beta, float* dxsum, float* sums_rw, unsigned* ticket, int rev) {
     __shared__ float4 s_a[kThreads];
     __shared__ unsigned s_last;
     constexpr int U = kPersistUnroll;
@@ -723,7 +723,12 @@ bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x
     const float4 kg = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t stride = (int64_t)gridDim.x * (kThreads * U);
-    for (int64_t base = (int64_t)blockIdx.x * (kThreads * U) + tid; base < nvec; base += stride) {
+    // LAST chunk first: the sums pass that ran just before walked the tensor front to back, so its tail is what the L2
+    // still holds -- walking back to front turns the first ~100 MB of re-reads into L2 hits (rev: A/B switch)
+    const int64_t b0 = (int64_t)blockIdx.x * (kThreads * U);
+    const int64_t nit = b0 < nvec ? (nvec - b0 + stride - 1) / stride : 0;
+    for (int64_t it = 0; it < nit; ++it) {
+        const int64_t base = b0 + (rev ? nit - 1 - it : it) * stride + tid;
         float4 g[U], xv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -778,6 +783,237 @@ bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x
     }
     // every block read `sums` before its loop; the LAST block to get here zeroes them for the next BatchNorm backward
     // (self-cleaning scratch: no memset node per call)
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        for (int ch = tid; ch < 2 * C; ch += kThreads) sums_rw[ch] = 0.f;
+        if (tid == 0) *ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------ BatchNorm backward fed by a max-pool backward
+// In BatchNorm -> in-place ReLU -> MaxPool(3x3, stride 2, pad 1) (the ResNet stem) the BatchNorm's dy IS the pool's
+// backward gather. Written out it is 4x the pooled gradient, and the two BatchNorm passes read it twice. Here both passes
+// gather it on the fly instead: one thread owns a 2x2 input quad x 4 channels, loads the <= 4 windows that touch the quad
+// once ((arg-max, dpool) pairs), forms the four pixels' gradients with the constant window slots of k = 3 / pad = 1 (same
+// visiting order as maxpool_bwd_s2_k: bit-identical to the materialised gradient), clears what the ReLU bits clear and
+// carries on like col_sums_atomic_k / bn_bwd_apply_persist_k. HBM traffic 2 x (x + dpool + argmax + mask) + dx instead
+// of (dpool + argmax + dy) + 2 x (dy + x + mask) + dx: 1.5 GB instead of 2.6 GB on the 128 x 112 x 112 x 64 stem.
+#ifndef XSB_POOL_OCC
+#define XSB_POOL_OCC 3
+#endif
+constexpr int kPoolOcc = XSB_POOL_OCC;      // resident blocks per SM the two kernels are compiled for
+struct PoolGeom {
+    int N, H, W, C, OH, OW, QH, QW, cvshift;
+};
+// everything one quad needs, fetched before anything is computed (16 independent loads in flight per thread)
+struct QuadIn {
+    uchar4 am[4];     // window (dh, dw) at [dh * 2 + dw]
+    float4 gp[4];
+    float4 xv[4];     // pixel (a, b) at [a * 2 + b]
+    unsigned mk[4];
+    bool ok[4];
+};
+
+__device__ __forceinline__ void pool_quad_load(const float* __restrict__ dpool, const uint8_t* __restrict__ amax,
+                                               const float* __restrict__ x, const uint8_t* __restrict__ rmask,
+                                               const PoolGeom& pg, unsigned item, int cv, const float4& xfill, QuadIn& in, int& n,
+                                               int& qi, int& qj) {
+    const unsigned quad = item >> pg.cvshift;
+    const unsigned r = quad / (unsigned)pg.QW;
+    qj = (int)(quad - r * (unsigned)pg.QW);
+    n = (int)(r / (unsigned)pg.QH);
+    qi = (int)(r - (unsigned)n * (unsigned)pg.QH);
+    const int CV = pg.C >> 2;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) {
+            const int oh = qi + dh, ow = qj + dw;
+            const bool live = oh < pg.OH && ow < pg.OW;
+            const int64_t o = (((int64_t)n * pg.OH + (live ? oh : 0)) * pg.OW + (live ? ow : 0)) * pg.C + (int64_t)cv * 4;
+            in.am[dh * 2 + dw] = __ldg(reinterpret_cast<const uchar4*>(amax + o));
+            in.gp[dh * 2 + dw] = __ldg(reinterpret_cast<const float4*>(dpool + o));
+            if (!live) in.am[dh * 2 + dw] = make_uchar4(255, 255, 255, 255);
+        }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int h = 2 * qi + a, w = 2 * qj + b;
+            const bool ok = h < pg.H && w < pg.W;
+            in.ok[a * 2 + b] = ok;
+            in.xv[a * 2 + b] = xfill;
+            in.mk[a * 2 + b] = 0u;
+            if (ok) {
+                const int64_t pix = ((int64_t)n * pg.H + h) * pg.W + w;
+                in.xv[a * 2 + b] = ldg_stream(reinterpret_cast<const float4*>(x) + pix * CV + cv);
+                if (rmask) {
+                    const int64_t e0 = pix * pg.C + (int64_t)cv * 4;
+                    in.mk[a * 2 + b] = ((unsigned)__ldg(rmask + (e0 >> 3)) >> (e0 & 4)) & 0xFu;
+                }
+            }
+        }
+}
+
+// the four pixels' gradients: constant window slots of k = 3 / pad = 1, windows visited in maxpool_bwd_s2_k's order
+__device__ __forceinline__ void pool_quad_grad(const QuadIn& in, float4 (&g)[4]) {
+    float acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[p][i] = 0.f;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) {
+            const uchar4 am = in.am[dh * 2 + dw];
+            const float4 gp = in.gp[dh * 2 + dw];
+            const int a4[4] = {am.x, am.y, am.z, am.w};
+            const float g4[4] = {gp.x, gp.y, gp.z, gp.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const int yy = 1 - 2 * dh + a, xx = 1 - 2 * dw + b;      // window-relative position of the pixel
+                        if (yy >= 0 && yy < 3 && xx >= 0 && xx < 3 && a4[i] == yy * 3 + xx) acc[a * 2 + b][i] += g4[i];
+                    }
+        }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float4 v = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+        const unsigned m = in.ok[p] ? in.mk[p] : 0xFu;
+        if (m & 1u) v.x = 0.f;
+        if (m & 2u) v.y = 0.f;
+        if (m & 4u) v.z = 0.f;
+        if (m & 8u) v.w = 0.f;
+        g[p] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, kPoolOcc)
+pool_bn_sums_k(const float* __restrict__ dpool, const uint8_t* __restrict__ amax, const float* __restrict__ x,
+               const float* __restrict__ mean, const float* __restrict__ invstd, const PoolGeom pg, unsigned nitems, float* sums,
+               const uint8_t* __restrict__ rmask, float* zero_me) {
+    __shared__ float4 s_a[kThreads], s_b[kThreads];
+    const int tid = threadIdx.x;
+    const int CV = pg.C / 4;
+    const int cv = tid & (CV - 1);
+    const int c = cv * 4, C = pg.C;
+    if (zero_me && blockIdx.x == 0)
+        for (int ch = tid; ch < C; ch += kThreads) zero_me[ch] = 0.f;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    const unsigned stride = gridDim.x * kThreads;
+    for (unsigned item = blockIdx.x * kThreads + tid; item < nitems; item += stride) {
+        QuadIn in;
+        int n, qi, qj;
+        pool_quad_load(dpool, amax, x, rmask, pg, item, cv, mu, in, n, qi, qj);
+        float4 g[4];
+        pool_quad_grad(in, g);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            sa.x += g[p].x; sa.y += g[p].y; sa.z += g[p].z; sa.w += g[p].w;
+            sb.x = fmaf(g[p].x, (in.xv[p].x - mu.x) * is.x, sb.x);
+            sb.y = fmaf(g[p].y, (in.xv[p].y - mu.y) * is.y, sb.y);
+            sb.z = fmaf(g[p].z, (in.xv[p].z - mu.z) * is.z, sb.z);
+            sb.w = fmaf(g[p].w, (in.xv[p].w - mu.w) * is.w, sb.w);
+        }
+    }
+    s_a[tid] = sa;
+    s_b[tid] = sb;
+    __syncthreads();
+    for (int st = kThreads / 2; st >= CV; st >>= 1) {
+        if (tid < st) {
+            float4 a = s_a[tid], b = s_a[tid + st];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            s_a[tid] = a;
+            float4 p = s_b[tid], q = s_b[tid + st];
+            p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+            s_b[tid] = p;
+        }
+        __syncthreads();
+    }
+    if (tid < CV) {
+        const float4 a = s_a[tid], b = s_b[tid];
+        atomicAdd(sums + c, a.x); atomicAdd(sums + c + 1, a.y); atomicAdd(sums + c + 2, a.z); atomicAdd(sums + c + 3, a.w);
+        atomicAdd(sums + C + c, b.x); atomicAdd(sums + C + c + 1, b.y); atomicAdd(sums + C + c + 2, b.z);
+        atomicAdd(sums + C + c + 3, b.w);
+    }
+}
+
+template <bool kAcc>
+__global__ void __launch_bounds__(kThreads, kPoolOcc)
+pool_bn_apply_k(const float* __restrict__ dpool, const uint8_t* __restrict__ amax, const float* __restrict__ x, float* dx,
+                const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                const float* __restrict__ sums, float invM, const PoolGeom pg, unsigned nitems, const uint8_t* __restrict__ rmask,
+                float* dgamma, float* dbeta, int acc_gamma, int acc_beta, float* dxsum, float* sums_rw, unsigned* ticket) {
+    __shared__ float4 s_a[kThreads];
+    __shared__ unsigned s_last;
+    const int tid = threadIdx.x;
+    const int CV = pg.C / 4;
+    const int cv = tid & (CV - 1);
+    const int c = cv * 4, C = pg.C;
+    if (blockIdx.x == 0) {
+        for (int ch = tid; ch < C; ch += kThreads) {
+            if (dbeta) dbeta[ch] = acc_beta ? dbeta[ch] + sums[ch] : sums[ch];
+            if (dgamma) dgamma[ch] = acc_gamma ? dgamma[ch] + sums[C + ch] : sums[C + ch];
+        }
+    }
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    float4 k1 = *reinterpret_cast<const float4*>(sums + c), k2 = *reinterpret_cast<const float4*>(sums + C + c);
+    k1.x *= invM; k1.y *= invM; k1.z *= invM; k1.w *= invM;
+    k2.x *= invM; k2.y *= invM; k2.z *= invM; k2.w *= invM;
+    const float4 kg = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned stride = gridDim.x * kThreads;
+    for (unsigned item = blockIdx.x * kThreads + tid; item < nitems; item += stride) {
+        QuadIn in;
+        int n, qi, qj;
+        pool_quad_load(dpool, amax, x, rmask, pg, item, cv, mu, in, n, qi, qj);
+        float4 g[4];
+        pool_quad_grad(in, g);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (!in.ok[p]) continue;
+            const int h = 2 * qi + (p >> 1), w = 2 * qj + (p & 1);
+            float4 o;
+            o.x = kg.x * (g[p].x - k1.x - (in.xv[p].x - mu.x) * is.x * k2.x);
+            o.y = kg.y * (g[p].y - k1.y - (in.xv[p].y - mu.y) * is.y * k2.y);
+            o.z = kg.z * (g[p].z - k1.z - (in.xv[p].z - mu.z) * is.z * k2.z);
+            o.w = kg.w * (g[p].w - k1.w - (in.xv[p].w - mu.w) * is.w * k2.w);
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            float4* q = reinterpret_cast<float4*>(dx) + (((int64_t)n * pg.H + h) * pg.W + w) * CV + cv;
+            if (kAcc) {
+                const float4 d = *q;
+                o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
+            }
+            stg_stream(q, o);
+        }
+    }
+    if (dxsum) {
+        s_a[tid] = acc;
+        __syncthreads();
+        for (int st = kThreads / 2; st >= CV; st >>= 1) {
+            if (tid < st) {
+                float4 a = s_a[tid], b = s_a[tid + st];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                s_a[tid] = a;
+            }
+            __syncthreads();
+        }
+        if (tid < CV) {
+            const float4 a = s_a[tid];
+            atomicAdd(dxsum + c, a.x); atomicAdd(dxsum + c + 1, a.y); atomicAdd(dxsum + c + 2, a.z); atomicAdd(dxsum + c + 3, a.w);
+        }
+    }
+    // every block read `sums` before its loop; the LAST block to get here zeroes them for the next BatchNorm backward
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
@@ -1200,14 +1436,15 @@ static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, cons
                                                                       (dxsum && !acc_dxsum) ? dxsum : nullptr);
         XSB_LAUNCH_CHECK();
         const float invM = 1.0f / (float)R;
+        static const int rev = [] { const char* e = getenv("XSB_BN_BWD_REV"); return (e && e[0] == '0') ? 0 : 1; }();
         if (acc_dx)
             bn_bwd_apply_persist_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
                                                                               nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
-                                                                              acc_dbeta, dxsum, sums, ticket);
+                                                                              acc_dbeta, dxsum, sums, ticket, rev);
         else
             bn_bwd_apply_persist_k<false><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
                                                                                nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
-                                                                               acc_dbeta, dxsum, sums, ticket);
+                                                                               acc_dbeta, dxsum, sums, ticket, rev);
         XSB_LAUNCH_CHECK();
         if (dxsum && dxsum_done) *dxsum_done = 1;
         return XSB_OK;
@@ -1246,6 +1483,52 @@ static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, cons
 }
 
 // out[c] (+)= sum_r x[r, c]   (bias gradients: conv db over N*OH*OW rows, Dense db over N rows)
+// BatchNorm backward whose dy is the backward gather of the 3x3 / stride 2 / pad 1 max-pool that follows the BatchNorm's
+// in-place ReLU (see pool_quad_grad): xsb_maxpool2d_bwd + xsb_bn_bwd_dxsum without the full-size dy in between.
+// XSB_ERR_UNSUPPORTED (nothing launched) outside the envelope: the caller materialises dy and runs the plain kernels.
+int xsb_bn_bwd_pool_dxsum(const float* dpool, const uint8_t* argmax, const float* x, const float* gamma,
+                          const float* save_mean, const float* save_invstd, float* dx, float* dgamma, float* dbeta, int N,
+                          int H, int W, int C, int acc_dx, int acc_dgamma, int acc_dbeta, const uint8_t* relu_mask, float* ws,
+                          float* dxsum, int acc_dxsum, void* stream) {
+    const int CV4 = C / 4;
+    if (C % 4 != 0 || CV4 > kThreads || (CV4 & (CV4 - 1)) != 0 || !dx || !aligned16(dpool) || !aligned16(x) || !aligned16(dx) ||
+        !aligned16(save_mean) || !aligned16(save_invstd) || !aligned16(gamma) || ((uintptr_t)argmax & 3u) != 0 ||
+        2 * C > kSumsFloats || N < 1 || H < 1 || W < 1)
+        return XSB_ERR_UNSUPPORTED;
+    cudaStream_t s = xsb_stream(stream);
+    PoolGeom pg;
+    pg.N = N; pg.H = H; pg.W = W; pg.C = C;
+    pg.OH = (H + 2 - 3) / 2 + 1; pg.OW = (W + 2 - 3) / 2 + 1;
+    pg.QH = (H + 1) / 2; pg.QW = (W + 1) / 2;
+    pg.cvshift = 0;
+    while ((1 << pg.cvshift) < CV4) ++pg.cvshift;
+    const int64_t nitems64 = (int64_t)N * pg.QH * pg.QW * CV4;
+    if (nitems64 >= ((int64_t)1 << 31)) return XSB_ERR_UNSUPPORTED;
+    const unsigned nitems = (unsigned)nitems64;
+    float* sums = ws + kCounterSlots;
+    unsigned* ticket = reinterpret_cast<unsigned*>(ws) + (kCounterSlots - 1);
+    // >= 8 quads per thread (a block ends with 2C (+C) atomics), many more blocks than SMs: the block scheduler keeps
+    // every SM at 3 blocks and there is no persistent-loop tail
+    int64_t blocks = ceil_div64(nitems64, (int64_t)kThreads * 8);
+    const int64_t cap = (int64_t)xsb_sm_count_cached() * 24;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    pool_bn_sums_k<<<(unsigned)blocks, kThreads, 0, s>>>(dpool, argmax, x, save_mean, save_invstd, pg, nitems, sums, relu_mask,
+                                                        (dxsum && !acc_dxsum) ? dxsum : nullptr);
+    XSB_LAUNCH_CHECK();
+    const float invM = 1.0f / ((float)N * (float)H * (float)W);
+    if (acc_dx)
+        pool_bn_apply_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dpool, argmax, x, dx, save_mean, save_invstd, gamma, sums, invM, pg,
+                                                                   nitems, relu_mask, dgamma, dbeta, acc_dgamma, acc_dbeta, dxsum,
+                                                                   sums, ticket);
+    else
+        pool_bn_apply_k<false><<<(unsigned)blocks, kThreads, 0, s>>>(dpool, argmax, x, dx, save_mean, save_invstd, gamma, sums, invM, pg,
+                                                                    nitems, relu_mask, dgamma, dbeta, acc_dgamma, acc_dbeta, dxsum,
+                                                                    sums, ticket);
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
 int xsb_colsum(const float* x, float* out, int64_t R, int C, int accumulate, float* ws, void* stream) {
     XSB_CHECK_ARG(R > 0 && C > 0, "colsum: empty input");
     cudaStream_t s = xsb_stream(stream);

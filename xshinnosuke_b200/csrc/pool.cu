@@ -342,6 +342,119 @@ bn_relu_maxpool_fwd_k(const float* __restrict__ x, const float* __restrict__ mea
     }
 }
 
+// The same fusion for k = 3, stride 2, pad 1 (the ResNet stem pool) WITHOUT the shared-memory tile: one thread = one
+// output pixel x 4 channels, the 3x3 window read straight from x (9 float4 loads in flight; the re-reads by the
+// neighbouring windows hit L1 / L2 exactly as in maxpool_fwd_k), BatchNorm + ReLU applied in registers. The thread OWNS
+// the input pixels (2oh, 2oh+1) x (2ow, 2ow+1) -- window slots {1,2} x {1,2} -- and their mask nibbles; lane pairs
+// (even, odd channel group of one pixel: C % 8 == 0) join theirs into the mask BYTE with one shuffle. HBM traffic: x once +
+// pooled y + argmax + mask instead of x, z (write), z (read), y, argmax, mask.
+// The kernel is INSTRUCTION-bound (ncu: 69 % issue-active, top stall math-pipe throttle), so:
+//  * interior windows (all but the first output row / column) run a separate, check-free instantiation (a real branch:
+//    a warp holds two output pixels, it is uniform everywhere but at the image border);
+//  * no per-element ReLU: max / first-argmax are taken over the raw BN values (padding = 0) -- if that maximum is > 0
+//    it is also the rectified maximum at the same tap, otherwise every rectified value is 0 and the first tap wins.
+template <bool INTERIOR>
+__device__ __forceinline__ void bn_relu_pool_window(const float4* __restrict__ img, int H, int W, unsigned CV, int cv, int h0,
+                                                    int w0, const float4& mu, const float4& is, const float4& ga,
+                                                    const float4& be, float (&best)[4], int (&arg)[4], unsigned& nibs) {
+    float4 q[9];
+    if (INTERIOR) {
+        const float4* p0 = img + (unsigned)((h0 * W + w0) * (int)CV + cv);
+        const unsigned row = (unsigned)W * CV;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) q[ky * 3 + kx] = __ldg(p0 + (ky * row + kx * CV));
+    } else {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int h = h0 + ky, w = w0 + kx;
+                q[ky * 3 + kx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (h >= 0 && h < H && w >= 0 && w < W) q[ky * 3 + kx] = __ldg(img + (unsigned)((h * W + w) * (int)CV + cv));
+            }
+    }
+    nibs = 0;     // nibble of owned pixel (ky - 1) * 2 + (kx - 1) at bits 8 * that index
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int tp = ky * 3 + kx;
+            const float4 v = q[tp];
+            float z[4];
+            // same arithmetic as bn_apply; zero PADDING stays zero and takes part in the max
+            z[0] = fmaf((v.x - mu.x) * is.x, ga.x, be.x);
+            z[1] = fmaf((v.y - mu.y) * is.y, ga.y, be.y);
+            z[2] = fmaf((v.z - mu.z) * is.z, ga.z, be.z);
+            z[3] = fmaf((v.w - mu.w) * is.w, ga.w, be.w);
+            if (!INTERIOR) {
+                const bool inside = h0 + ky >= 0 && h0 + ky < H && w0 + kx >= 0 && w0 + kx < W;
+                if (!inside) z[0] = z[1] = z[2] = z[3] = 0.f;
+            }
+            if (ky >= 1 && kx >= 1) {
+                const unsigned nib = (z[0] < 0.f ? 1u : 0u) | (z[1] < 0.f ? 2u : 0u) | (z[2] < 0.f ? 4u : 0u) |
+                                     (z[3] < 0.f ? 8u : 0u);
+                nibs |= nib << (8 * ((ky - 1) * 2 + (kx - 1)));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (tp == 0 || z[i] > best[i]) { best[i] = z[i]; arg[i] = tp; }    // first maximum wins
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (!(best[i] > 0.f)) { best[i] = 0.f; arg[i] = 0; }      // every rectified value of the window is 0
+}
+
+__global__ void __launch_bounds__(256, 4)
+bn_relu_maxpool_k3s2_k(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                       uint8_t* __restrict__ amax, uint8_t* __restrict__ rmask, int N, int H, int W, int C, int OH, int OW) {
+    const unsigned CV = C / 4;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < (unsigned)OW * CV;      // (dead lanes stay for the shuffle; blockDim and CV are even)
+    const int cv = live ? (int)(t % CV) : 0;
+    const int ow = live ? (int)(t / CV) : 0;
+    const int oh = blockIdx.y;
+    const int n = blockIdx.z;
+    const int h0 = 2 * oh - 1, w0 = 2 * ow - 1;
+    const float4* img = reinterpret_cast<const float4*>(x) + (int64_t)n * H * W * CV;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + cv);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cv);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cv);
+    unsigned nibs;
+    float best[4] = {0.f, 0.f, 0.f, 0.f};
+    int arg[4] = {0, 0, 0, 0};
+    if (h0 >= 0 && w0 >= 0 && h0 + 3 <= H && w0 + 3 <= W)
+        bn_relu_pool_window<true>(img, H, W, CV, cv, h0, w0, mu, is, ga, be, best, arg, nibs);
+    else
+        bn_relu_pool_window<false>(img, H, W, CV, cv, h0, w0, mu, is, ga, be, best, arg, nibs);
+    if (live) {
+        const int64_t o = (((int64_t)n * OH + oh) * OW + ow) * C + (int64_t)cv * 4;
+        *reinterpret_cast<float4*>(y + o) = make_float4(best[0], best[1], best[2], best[3]);
+        if (amax)
+            *reinterpret_cast<uchar4*>(amax + o) =
+                make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
+    }
+    if (rmask) {
+        const unsigned hi = __shfl_down_sync(0xffffffffu, nibs, 1);     // the odd channel group of the same pixel
+        if (live && (cv & 1) == 0) {
+            const unsigned bytes4 = nibs | (hi << 4);
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int h = 2 * oh + a, w = 2 * ow + b;
+                    if (h < H && w < W) {
+                        const int64_t e0 = (((int64_t)n * H + h) * W + w) * C + (int64_t)cv * 4;
+                        rmask[e0 >> 3] = (uint8_t)((bytes4 >> (8 * (a * 2 + b))) & 0xFFu);
+                    }
+                }
+        }
+    }
+}
+
 // avg pool (padding == 0 only: the reference's padded variant is broken). V channels per thread.
 template <int V>
 __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int OH,
@@ -464,6 +577,13 @@ int xsb_bn_relu_maxpool_fwd(const float* x, const float* mean, const float* invs
     if (!covered || C % 8 != 0 || !aligned16(x) || !aligned16(y) || !aligned16(mean) || !aligned16(invstd) ||
         !aligned16(gamma) || !aligned16(beta) || (argmax && ((uintptr_t)argmax & 3u) != 0) || N > 65535 || OH > 65535)
         return XSB_ERR_UNSUPPORTED;
+    if (k == 3 && sh == 2 && sw == 2 && pad == 1 && (int64_t)H * W * (C / 4) < ((int64_t)1 << 31)) {
+        dim3 grid((unsigned)ceil_div64((int64_t)OW * (C / 4), 256), OH, N);
+        bn_relu_maxpool_k3s2_k<<<grid, 256, 0, xsb_stream(stream)>>>(x, mean, invstd, gamma, beta, y, argmax, relu_mask, N, H, W,
+                                                                    C, OH, OW);
+        XSB_LAUNCH_CHECK();
+        return XSB_OK;
+    }
     const int rows = (FP_TOH - 1) * sh + k, cols = (FP_TOW - 1) * sw + k;
     const size_t smem = (size_t)rows * cols * C * sizeof(float);
     if (smem > 48 * 1024 || (OH + FP_TOH - 1) / FP_TOH > 65535 || 256 % (C / 4) != 0) return XSB_ERR_UNSUPPORTED;

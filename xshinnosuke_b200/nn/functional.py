@@ -381,7 +381,7 @@ def max_pool2d(inputs: Tensor, kernel_size: int = 2, stride=None, padding: int =
     # (BN apply + ReLU + mask + pool in one pass, the rectified tensor is never written unless someone else reads it)
     fused = False
     br = getattr(x.pending_op, "bn_relu", None) if x is inputs.arr else None
-    if br is not None and br["x"].cl:
+    if br is not None and br["x"].cl and (rt.fuse_bn_relu_pool == "all" or (k, sh, sw, padding) == (3, 2, 2, 1)):
         rc = lib.xsb_bn_relu_maxpool_fwd(br["x"].ptr, br["mean"].peek_ptr(), br["invstd"].peek_ptr(), br["gamma"].ptr,
                                          br["beta"].ptr, y.wptr, aptr, br["mask"].data_ptr(), n, h, w, c, k, sh, sw, padding,
                                          rt.stream())

@@ -280,9 +280,22 @@ def Maxpool2DBackward(outputs: Tensor):
         n, c, h, w = inputs.shape
         g = _grad_arr(inputs)
         dy = outputs.grad.arr.as_cl()
-        lib.xsb_maxpool2d_bwd(dy.ptr, amax.data_ptr(), g.peek_ptr(), n, h, w, c, k, sh, sw, pad, g.take_acc(),
-                              rt.stream())
-        rt.launches += 1
+        dy_ptr = dy.ptr
+
+        def scatter(acc, _keep=(dy.buf, amax)):
+            lib.xsb_maxpool2d_bwd(dy_ptr, amax.data_ptr(), g.peek_ptr(), n, h, w, c, k, sh, sw, pad, acc, rt.stream())
+            rt.launches += 1
+
+        # BatchNorm -> in-place ReLU -> this 3x3/2 pool (the ResNet stem): the BatchNorm backward can gather the pool's
+        # gradient on the fly (xsb_bn_bwd_pool_dxsum) -- 4x less to read than the scattered copy, which is then never
+        # written. Parked like a postponed add: anyone else who reads the gradient gets the scattered copy first.
+        stack = inputs.cache.get("grad_fn")
+        if (rt.fuse_pool_bn_bwd and k == 3 and (sh, sw) == (2, 2) and pad == 1 and inputs.cache.get("inplace") and stack
+                and stack[-1] is BatchNormBackward and inputs.is_dynamic and len(inputs.out_bounds) == 1 and g.cl):
+            scatter.pool = (dy_ptr, amax.data_ptr(), (n, h, w, c))
+            if g.defer_add(scatter):
+                return
+        scatter(g.take_acc())
 
 
 def Avgpool2DBackward(outputs: Tensor):
@@ -305,6 +318,37 @@ def BatchNormBackward(outputs: Tensor, relu_mask=None):
     inputs, gamma, beta = outputs.in_bounds
     dy = outputs.grad.arr
     x = inputs.arr
+    # dy is the still-parked gradient of a 3x3/2 max-pool (Maxpool2DBackward): gather it inside the BatchNorm kernels
+    parked = dy._pz[2] if dy.pending_zero else None
+    pool = getattr(parked, "pool", None)
+    if pool is not None and inputs.requires_grad and x.ndim == 4 and x.cl and dy.cl and dy.lazy_mask is None:
+        dpool_ptr, amax_ptr, (pn, ph, pw, pc) = pool
+        gx = _grad_arr(inputs)
+        gg = _grad_arr(gamma) if gamma.requires_grad else None
+        gb = _grad_arr(beta) if beta.requires_grad else None
+        cb = None
+        if (inputs.grad_fn is Conv2DBackward and inputs.is_dynamic and len(inputs.out_bounds) == 1 and gx.pending_zero):
+            conv_bias = inputs.in_bounds[2]
+            if conv_bias is not None and conv_bias.requires_grad:
+                cb = _grad_arr(conv_bias)
+        rc = lib.xsb_bn_bwd_pool_dxsum(
+            dpool_ptr, amax_ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
+            gx.peek_ptr(), gg.peek_ptr() if gg is not None else None, gb.peek_ptr() if gb is not None else None,
+            pn, ph, pw, pc, 0 if gx.pending_zero else 1, 0 if (gg is None or gg.pending_zero) else 1,
+            0 if (gb is None or gb.pending_zero) else 1, relu_mask.data_ptr() if relu_mask is not None else None,
+            rt.ws_small.data_ptr(), cb.peek_ptr() if cb is not None else None,
+            0 if (cb is None or cb.pending_zero) else 1, rt.stream())
+        if rc == 0:
+            dy._pz[2] = None           # consumed: the scattered copy is never made (dy stays logically zero)
+            for a in (gx, gg, gb, cb):
+                if a is not None:
+                    a.pending_zero = False
+            if cb is not None:
+                inputs.cache["bias_grad_done"] = True
+            rt.launches += 2
+            _done(gamma)
+            _done(beta)
+            return
     if dy.lazy_mask is not None and relu_mask is None and (x.ndim != 4 or (x.cl and dy.cl)):
         relu_mask, dy_ptr = dy.lazy_mask, dy.buf.data_ptr()     # masked alias of the add's dZ (see AddBackward)
     else:

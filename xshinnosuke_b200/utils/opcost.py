@@ -71,6 +71,12 @@ def cost(name, a):
         return "byte", 12.0 * a[4] + a[4] / 8.0
     if name in ("xsb_bn_bwd", "xsb_bn_bwd_dxsum"):
         return "byte", (20.0 if a[5] else 8.0) * a[8] * a[9]
+    if name == "xsb_bn_bwd_pool_dxsum":
+        # two passes over (x, dpool, argmax, mask) + dx; the scattered dy the unfused pair writes and reads twice is gone
+        N, H, W, C = a[9:13]
+        OH, OW = _pool_out(H, W, 3, 2, 2, 1)
+        n, m = float(N) * H * W * C, float(N) * OH * OW * C
+        return "byte", 2.0 * (4.0 * n + 5.0 * m + (n / 8.0 if a[16] else 0.0)) + 4.0 * n
     if name == "xsb_bn_finalize":
         return "byte", 12.0 * a[1] * a[3]      # P partials x {n, mean, M2} x C
     if name == "xsb_colsum":
