@@ -806,6 +806,7 @@ bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x
 constexpr int kPoolOcc = XSB_POOL_OCC;      // resident blocks per SM the two kernels are compiled for
 struct PoolGeom {
     int N, H, W, C, OH, OW, QH, QW, cvshift;
+    int fast;     // C % 8 == 0 and every 32-bit index of the fast path fits
 };
 // everything one quad needs, fetched before anything is computed (16 independent loads in flight per thread)
 struct QuadIn {
@@ -816,16 +817,40 @@ struct QuadIn {
     bool ok[4];
 };
 
+// FAST: the quad is interior (its four windows and four pixels all exist) and C % 8 == 0 -- no existence checks, every
+// address is one base + a constant (the kernels are instruction-bound: a quad costs ~350 instructions to gather)
+template <bool FAST>
 __device__ __forceinline__ void pool_quad_load(const float* __restrict__ dpool, const uint8_t* __restrict__ amax,
                                                const float* __restrict__ x, const uint8_t* __restrict__ rmask,
-                                               const PoolGeom& pg, unsigned item, int cv, const float4& xfill, QuadIn& in, int& n,
-                                               int& qi, int& qj) {
-    const unsigned quad = item >> pg.cvshift;
-    const unsigned r = quad / (unsigned)pg.QW;
-    qj = (int)(quad - r * (unsigned)pg.QW);
-    n = (int)(r / (unsigned)pg.QH);
-    qi = (int)(r - (unsigned)n * (unsigned)pg.QH);
+                                               const PoolGeom& pg, int n, int qi, int qj, int cv, const float4& xfill,
+                                               QuadIn& in) {
     const int CV = pg.C >> 2;
+    if (FAST) {
+        const unsigned o00 = (unsigned)(((n * pg.OH + qi) * pg.OW + qj) * CV + cv);      // float4 / uchar4 index
+        const unsigned orow = (unsigned)(pg.OW * CV);
+        const uchar4* ap = reinterpret_cast<const uchar4*>(amax);
+        const float4* gpp = reinterpret_cast<const float4*>(dpool);
+        in.am[0] = __ldg(ap + o00); in.am[1] = __ldg(ap + o00 + CV);
+        in.am[2] = __ldg(ap + o00 + orow); in.am[3] = __ldg(ap + o00 + orow + CV);
+        in.gp[0] = __ldg(gpp + o00); in.gp[1] = __ldg(gpp + o00 + CV);
+        in.gp[2] = __ldg(gpp + o00 + orow); in.gp[3] = __ldg(gpp + o00 + orow + CV);
+        const unsigned p00 = (unsigned)((n * pg.H + 2 * qi) * pg.W + 2 * qj);              // pixel index
+        const unsigned x00 = p00 * (unsigned)CV + (unsigned)cv, xrow = (unsigned)(pg.W * CV);
+        const float4* xp = reinterpret_cast<const float4*>(x);
+        in.xv[0] = ldg_stream(xp + x00); in.xv[1] = ldg_stream(xp + x00 + CV);
+        in.xv[2] = ldg_stream(xp + x00 + xrow); in.xv[3] = ldg_stream(xp + x00 + xrow + CV);
+        in.ok[0] = in.ok[1] = in.ok[2] = in.ok[3] = true;
+        in.mk[0] = in.mk[1] = in.mk[2] = in.mk[3] = 0u;
+        if (rmask) {
+            const unsigned C8 = (unsigned)(pg.C >> 3);
+            const unsigned m00 = p00 * C8 + (unsigned)(cv >> 1), mrow = (unsigned)pg.W * C8, sh = (unsigned)(cv & 1) * 4u;
+            in.mk[0] = ((unsigned)__ldg(rmask + m00) >> sh) & 0xFu;
+            in.mk[1] = ((unsigned)__ldg(rmask + m00 + C8) >> sh) & 0xFu;
+            in.mk[2] = ((unsigned)__ldg(rmask + m00 + mrow) >> sh) & 0xFu;
+            in.mk[3] = ((unsigned)__ldg(rmask + m00 + mrow + C8) >> sh) & 0xFu;
+        }
+        return;
+    }
 #pragma unroll
     for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
@@ -855,6 +880,16 @@ __device__ __forceinline__ void pool_quad_load(const float* __restrict__ dpool, 
                 }
             }
         }
+}
+
+// item -> (image, quad row, quad column); -> true when the quad is interior and the fast path applies
+__device__ __forceinline__ bool pool_quad_of(const PoolGeom& pg, unsigned item, int& n, int& qi, int& qj) {
+    const unsigned quad = item >> pg.cvshift;
+    const unsigned r = quad / (unsigned)pg.QW;
+    qj = (int)(quad - r * (unsigned)pg.QW);
+    n = (int)(r / (unsigned)pg.QH);
+    qi = (int)(r - (unsigned)n * (unsigned)pg.QH);
+    return pg.fast && qi + 1 < pg.OH && qj + 1 < pg.OW && 2 * qi + 1 < pg.H && 2 * qj + 1 < pg.W;
 }
 
 // the four pixels' gradients: constant window slots of k = 3 / pad = 1, windows visited in maxpool_bwd_s2_k's order
@@ -912,7 +947,10 @@ pool_bn_sums_k(const float* __restrict__ dpool, const uint8_t* __restrict__ amax
     for (unsigned item = blockIdx.x * kThreads + tid; item < nitems; item += stride) {
         QuadIn in;
         int n, qi, qj;
-        pool_quad_load(dpool, amax, x, rmask, pg, item, cv, mu, in, n, qi, qj);
+        if (pool_quad_of(pg, item, n, qi, qj))      // (a warp holds two neighbouring quads: uniform away from the borders)
+            pool_quad_load<true>(dpool, amax, x, rmask, pg, n, qi, qj, cv, mu, in);
+        else
+            pool_quad_load<false>(dpool, amax, x, rmask, pg, n, qi, qj, cv, mu, in);
         float4 g[4];
         pool_quad_grad(in, g);
 #pragma unroll
@@ -976,7 +1014,10 @@ pool_bn_apply_k(const float* __restrict__ dpool, const uint8_t* __restrict__ ama
     for (unsigned item = blockIdx.x * kThreads + tid; item < nitems; item += stride) {
         QuadIn in;
         int n, qi, qj;
-        pool_quad_load(dpool, amax, x, rmask, pg, item, cv, mu, in, n, qi, qj);
+        if (pool_quad_of(pg, item, n, qi, qj))      // (a warp holds two neighbouring quads: uniform away from the borders)
+            pool_quad_load<true>(dpool, amax, x, rmask, pg, n, qi, qj, cv, mu, in);
+        else
+            pool_quad_load<false>(dpool, amax, x, rmask, pg, n, qi, qj, cv, mu, in);
         float4 g[4];
         pool_quad_grad(in, g);
 #pragma unroll
@@ -1502,6 +1543,7 @@ int xsb_bn_bwd_pool_dxsum(const float* dpool, const uint8_t* argmax, const float
     pg.QH = (H + 1) / 2; pg.QW = (W + 1) / 2;
     pg.cvshift = 0;
     while ((1 << pg.cvshift) < CV4) ++pg.cvshift;
+    pg.fast = (C % 8 == 0 && (int64_t)N * H * W * CV4 < ((int64_t)1 << 31)) ? 1 : 0;
     const int64_t nitems64 = (int64_t)N * pg.QH * pg.QW * CV4;
     if (nitems64 >= ((int64_t)1 << 31)) return XSB_ERR_UNSUPPORTED;
     const unsigned nitems = (unsigned)nitems64;
