@@ -1551,8 +1551,15 @@ int xsb_bn_bwd_pool_dxsum(const float* dpool, const uint8_t* argmax, const float
     unsigned* ticket = reinterpret_cast<unsigned*>(ws) + (kCounterSlots - 1);
     // >= 8 quads per thread (a block ends with 2C (+C) atomics), many more blocks than SMs: the block scheduler keeps
     // every SM at 3 blocks and there is no persistent-loop tail
-    int64_t blocks = ceil_div64(nitems64, (int64_t)kThreads * 8);
-    const int64_t cap = (int64_t)xsb_sm_count_cached() * 24;
+    // (small tensors: one quad per thread until every SM holds 6 blocks -- 49 blocks of 8 quads per thread took 25 us per
+    // pass on the 32 x 28 x 28 x 64 stem of the 56 x 56 configuration)
+    const int64_t sms = xsb_sm_count_cached();
+    int64_t blocks = ceil_div64(nitems64, (int64_t)kThreads);
+    if (blocks > sms * 6) {
+        blocks = ceil_div64(nitems64, (int64_t)kThreads * 8);
+        if (blocks < sms * 6) blocks = sms * 6;
+    }
+    const int64_t cap = sms * 24;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     pool_bn_sums_k<<<(unsigned)blocks, kThreads, 0, s>>>(dpool, argmax, x, save_mean, save_invstd, pg, nitems, sums, relu_mask,

@@ -51,6 +51,11 @@ struct FpropParams {
     // job tap (kh', kw') starts at float column b_col0 - kh'*b_step_h - kw'*b_step_w (the flipped / sub-sampled tap of the
     // forward filter this parity class meets): no transposed copy of the filter is made.
     int b_mn, b_col0, b_step_h, b_step_w;
+    // split-K (ksplit > 1, gridDim.z = ksplit): CTA z multiplies k-blocks [num_kb*z/ksplit, num_kb*(z+1)/ksplit) and ADDS its
+    // partial tile into out (TMA reduce-add; the launcher zero-fills out first when the call is not accumulating; z = 0
+    // carries the bias; no BatchNorm statistics). For launches of a handful of tiles with a long K (the 2x2 / 4x4 feature
+    // maps of the 56 x 56 configuration: 16 CTAs x 144 k-blocks = 18 us of pure latency on 11 % of the SMs).
+    int ksplit;
 };
 
 // Non-strided epilogue shared by the 1-CTA and 2-CTA im2col kernels. Every MMA has completed, so the operand ring is
@@ -61,15 +66,16 @@ struct FpropParams {
 // staged while the TMA store of chunk i-1 still reads the other staging block (one store may stay pending).
 constexpr int EPI_STAGE_BYTES = 8 * 4096;     // staging blocks; the statistics scratch ([4][3][BN] floats) follows
 template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const FpropParams& p, const CUtensorMap& tmO, uint8_t* sA, uint8_t* stage,
-                                               uint32_t (&r)[32], int q, int lane, int m0, int n0, int c0) {
+__device__ __forceinline__ void epilogue_chunk(const FpropParams& p, const float* __restrict__ bias, const CUtensorMap& tmO,
+                                               uint8_t* sA, uint8_t* stage, uint32_t (&r)[32], int q, int lane, int m0, int n0,
+                                               int c0) {
     float o[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
-    if (p.bias) {
+    if (bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
             o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
         }
     }
@@ -97,8 +103,9 @@ __device__ __forceinline__ void epilogue_chunk(const FpropParams& p, const CUten
 }
 
 template <int BN>
-__device__ __forceinline__ void epilogue_store_tma(const FpropParams& p, const CUtensorMap* tmOp, uint32_t tmem_base,
-                                                   uint8_t* sA, int q, int lane, int m_tile, int m0, int n0, int ncols) {
+__device__ __forceinline__ void epilogue_store_tma(const FpropParams& p, const float* __restrict__ bias,
+                                                   const CUtensorMap* tmOp, uint32_t tmem_base, uint8_t* sA, int q, int lane,
+                                                   int m_tile, int m0, int n0, int ncols) {
     const CUtensorMap& tmO = *tmOp;
     const int row = q * 32 + lane;
     uint8_t* stage0 = sA + q * 8192;
@@ -111,12 +118,12 @@ __device__ __forceinline__ void epilogue_store_tma(const FpropParams& p, const C
         tmem_regs_ready(ra);
         const bool has_b = c0 + 32 < ncols;
         if (has_b) tmem_ld32(t0 + (uint32_t)(c0 + 32), rb);
-        epilogue_chunk<BN>(p, tmO, sA, stage0, ra, q, lane, m0, n0, c0);
+        epilogue_chunk<BN>(p, bias, tmO, sA, stage0, ra, q, lane, m0, n0, c0);
         if (has_b) {
             tmem_wait_ld();
             tmem_regs_ready(rb);
             if (c0 + 64 < ncols) tmem_ld32(t0 + (uint32_t)(c0 + 64), ra);
-            epilogue_chunk<BN>(p, tmO, sA, stage0 + 4096, rb, q, lane, m0, n0, c0 + 32);
+            epilogue_chunk<BN>(p, bias, tmO, sA, stage0 + 4096, rb, q, lane, m0, n0, c0 + 32);
         }
     }
     if (lane == 0) bulk_wait_all<0>();
@@ -158,6 +165,9 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int num_kb = p.KH * p.KW * cblocks;
     const int m_tile = p.m_tile0 + blockIdx.x;
     const int m0 = m_tile * BM, n0 = p.part_n0[blockIdx.y], ncols = p.part_cols[blockIdx.y];
+    // this CTA's k-blocks (split-K: gridDim.z parts; else all of them)
+    const int kb_begin = p.ksplit > 1 ? (int)((int64_t)num_kb * blockIdx.z / p.ksplit) : 0;
+    const int kb_end = p.ksplit > 1 ? (int)((int64_t)num_kb * (blockIdx.z + 1) / p.ksplit) : num_kb;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -185,11 +195,11 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n_img = m0 / hw, rem = m0 - n_img * hw;
         const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
         const int w0 = ow0 * p.sw - p.pad_w, h0 = oh0 * p.sh - p.pad_h;
-        int s = 0, kb = 0;
+        int s = 0;
         uint32_t ph = 0;
-        for (int kh = 0; kh < p.KH; ++kh)
-            for (int kw = 0; kw < p.KW; ++kw)
-                for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+        const int tap0 = kb_begin / cblocks;
+        int cb = kb_begin - tap0 * cblocks, kh = tap0 / p.KW, kw = tap0 - (tap0 / p.KW) * p.KW;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     if (elect_one()) {
                         if (p.b_mn) {
@@ -205,6 +215,10 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (++cb == cblocks) {        // next k-block: (kh, kw, cb) in filter order
+                        cb = 0;
+                        if (++kw == p.KW) { kw = 0; ++kh; }
+                    }
                 }
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(ncols, 0, p.b_mn ? 1 : 0);   // N = this CTA's column count (the B tile holds BN >= N rows)
@@ -212,7 +226,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t b_kstep = p.b_mn ? 64u : 2u;     // K = 8 advance: 8 rows of 128 B (MN-major) / 32 B (K-major)
         int s = 0;
         uint32_t ph = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (elect_one()) {
@@ -221,7 +235,8 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                            : make_desc(b_base + s * B_BYTES, 16, 1024);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // 4 x (K = 8 tf32 = 32 B) per 128-byte row
-                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * b_kstep), idesc, (kb | k) != 0);
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * b_kstep), idesc,
+                              ((kb - kb_begin) | k) != 0);
                 umma_commit(&empty[s]);
             }
             __syncwarp();
@@ -236,7 +251,7 @@ conv_fprop_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row = q * 32 + lane;
         const int m = m0 + row;
         if (!p.o_strided) {
-            epilogue_store_tma<BN>(p, &tmO, tmem_base, sA, q, lane, m_tile, m0, n0, ncols);
+            epilogue_store_tma<BN>(p, blockIdx.z == 0 ? p.bias : nullptr, &tmO, tmem_base, sA, q, lane, m_tile, m0, n0, ncols);
         } else {
             const int hw = p.OH * p.OW;
             const int n_img = m / hw, rem = m - n_img * hw;
@@ -372,7 +387,7 @@ conv_fprop_tc2_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        if (m0 < p.M) epilogue_store_tma<BN>(p, &tmO, tmem_base, sA, q, lane, m_tile, m0, n0, ncols);
+        if (m0 < p.M) epilogue_store_tma<BN>(p, p.bias, &tmO, tmem_base, sA, q, lane, m_tile, m0, n0, ncols);
         tc_fence_before();
     }
     __syncthreads();
@@ -799,7 +814,7 @@ static int launch_fprop(const CUtensorMap& a, const CUtensorMap& b, const CUtens
         XSB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_k<BN, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid(m_tiles, n_parts);
+    dim3 grid(m_tiles, n_parts, p.ksplit > 1 ? p.ksplit : 1);
     conv_fprop_tc_k<BN, STAGES, OCC><<<grid, kThreads, smem, s>>>(a, b, o, p);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
@@ -947,7 +962,22 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
             int parts = S / m_tiles;
             if (parts > j.OCx / 32) parts = j.OCx / 32;
             if (parts > 16) parts = 16;
-            if (parts > n_tiles) return launch_parts(0, m_tiles, parts);
+            if (parts > n_tiles) {
+                // still only a fraction of the SMs, each CTA with a long serial K loop: split K as well
+                static const int splitk_on = [] { const char* e = getenv("XSB_TC_SPLITK"); return (e && e[0] == '0') ? 0 : 1; }();
+                const int ctas = m_tiles * parts, num_kb = j.KH * j.KW * (j.Cx / 32);
+                int ks = S / ctas;
+                if (ks > num_kb / 4) ks = num_kb / 4;
+                if (ks > 32) ks = 32;
+                if (splitk_on && !j.o_strided && ctas * 2 <= S && num_kb >= 16 && ks >= 2) {
+                    if (!j.accumulate) XSB_CUDA(cudaMemsetAsync(j.out, 0, (size_t)p.M * j.OCx * sizeof(float), s));
+                    p.accumulate = 1;
+                    p.ksplit = ks;
+                    p.stats = nullptr;
+                    if (j.n_partials) *j.n_partials = 0;
+                }
+                return launch_parts(0, m_tiles, parts);
+            }
         } else if (n_tiles == 1 && units % S != 0 && (units % S) * 10 < (int64_t)S * 7) {
             const int main_tiles = (int)(units / S) * S, tail = m_tiles - main_tiles;
             int parts = S / tail;
