@@ -51,7 +51,9 @@ static Geom make_geom(int64_t R, int C, bool vec4, int max_blocks = kMaxRowBlock
     g.chunks = (g.CV + g.LX - 1) / g.LX;
     // >= kRowsPerThread rows per thread: below that the serial merge of the per-block partials costs more than
     // the extra CTAs win; above it up to max_blocks CTAs keep enough loads in flight for the big tensors
-    int64_t nb = R / ((int64_t)g.LY * kRowsPerThread);
+    // (small tensors: 8 rows per thread = one round of loads, so that a 512-row tensor still spreads over 8 row blocks)
+    const int rpt = R / ((int64_t)g.LY * kRowsPerThread) < 8 ? 8 : kRowsPerThread;
+    int64_t nb = R / ((int64_t)g.LY * rpt);
     const int64_t cap = max_blocks / g.chunks > 8 ? max_blocks / g.chunks : 8;
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;

@@ -952,11 +952,12 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
         return launch_parts2(0, m_tiles, n_tiles);
     }
     static const int wave_aware = [] { const char* e = getenv("XSB_TC_WAVES"); return (e && e[0] == '0') ? 0 : 1; }();
-    if (BN == 256 && wave_aware) {
+    if (wave_aware && (BN == 256 || (int64_t)m_tiles * (j.OCx / BN) * 2 <= S)) {
         // One CTA per SM: tile counts that are not a multiple of the SM count leave SMs idle (98 tiles on 148 SMs =
         // 66 %, 196 tiles = two waves at 66 %). Fewer tiles than SMs: split every tile's columns into floor(S/tiles)
-        // parts. A short tail wave after full waves (OC = 256): the tail m-tiles are split the same way.
-        const int n_tiles = j.OCx / 256;
+        // parts (any tile width when the launch would fill less than half of the SMs: the 14x14 / 7x7 maps of the 56x56
+        // configuration). A short tail wave after full waves (OC = 256): the tail m-tiles are split the same way.
+        const int n_tiles = j.OCx / BN;
         const int64_t units = (int64_t)m_tiles * n_tiles;
         if (units < S) {
             int parts = S / m_tiles;
@@ -978,7 +979,7 @@ static int fprop_dispatch(const FpropJob& j, cudaStream_t s) {
                 }
                 return launch_parts(0, m_tiles, parts);
             }
-        } else if (n_tiles == 1 && units % S != 0 && (units % S) * 10 < (int64_t)S * 7) {
+        } else if (BN == 256 && n_tiles == 1 && units % S != 0 && (units % S) * 10 < (int64_t)S * 7) {
             const int main_tiles = (int)(units / S) * S, tail = m_tiles - main_tiles;
             int parts = S / tail;
             if (parts > j.OCx / 32) parts = j.OCx / 32;
