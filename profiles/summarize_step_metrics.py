@@ -18,7 +18,7 @@ def short(name):
 def family(k):
     if k.startswith(("conv_", "gemm_tc", "igemm", "stem_", "gather_subfilters", "zero_class")):
         return "conv family (xsb_conv2d_fwd + dgrad + wgrad)"
-    if k.startswith(("col_sums_atomic", "bn_bwd")):
+    if k.startswith(("col_sums_atomic", "bn_bwd", "pool_bn")):
         return "xsb_bn_bwd_dxsum"
     if k.startswith("bn_apply"):
         return "xsb_bn_apply"
