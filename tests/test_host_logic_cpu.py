@@ -190,3 +190,53 @@ def test_direct_writes_and_replaced_gradients():
 
 def test_extra_ops(golden):
     S.check_extra_ops(golden, TOL)
+
+
+def test_stem_pool_fusions_host_logic():
+    """BatchNormalization -> ReLU(inplace) -> MaxPooling2D(3, 2, 1): forward through xsb_bn_relu_maxpool_fwd (the rectified
+    tensor stays un-materialised), backward with the pool's gradient PARKED on the ReLU tensor's gradient and consumed by
+    xsb_bn_bwd_pool_dxsum; a reader that gets to the parked gradient first receives the scattered copy (plain kernels)."""
+    import numpy as np
+    import xshinnosuke_b200 as xs
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.layers import BatchNormalization, MaxPooling2D, ReLU
+    rs = np.random.RandomState(5)
+    x = rs.randn(3, 8, 11, 11).astype(np.float32)
+    g = None
+    out = {}
+    keep = (xs.runtime.fuse_bn_relu_pool, xs.runtime.fuse_pool_bn_bwd)
+    try:
+        for mode in ("fused", "peek", "plain"):
+            xs.runtime.fuse_bn_relu_pool = mode != "plain"
+            xs.runtime.fuse_pool_bn_bwd = mode != "plain"
+            np.random.seed(0)
+            bn, relu, pool = BatchNormalization(), ReLU(True), MaxPooling2D(3, 2, 1)
+            tx = xs.tensor(x, requires_grad=True)
+            n0 = len(lib.calls)
+            z = relu(bn(tx))
+            y = pool(z)
+            yv = y.eval                                   # (backward releases the graph's intermediate tensors)
+            if g is None:
+                g = rs.randn(*yv.shape).astype(np.float32)
+            if mode == "peek":
+                # run the pool's closure by hand, then READ the gradient it parked before the BatchNorm closure runs
+                y.grad = xs.tensor(g)
+                y.grad_fn(y)
+                parked = z.grad.arr._pz[2]
+                assert parked is not None and hasattr(parked, "pool")
+                dz = z.grad.eval                          # a reader: the scattered copy is made now
+                assert z.grad.arr._pz[2] is None and np.abs(dz).sum() > 0
+                z.grad_fn(z)
+            else:
+                y.backward(gradients=g)
+            calls = lib.calls[n0:]
+            out[mode] = (yv, tx.grad.eval, bn.parameters()[0].grad.eval, bn.parameters()[1].grad.eval, calls)
+    finally:
+        xs.runtime.fuse_bn_relu_pool, xs.runtime.fuse_pool_bn_bwd = keep
+    f, p, q = out["fused"], out["peek"], out["plain"]
+    assert "xsb_bn_relu_maxpool_fwd" in f[4] and "xsb_bn_bwd_pool_dxsum" in f[4] and "xsb_maxpool2d_bwd" not in f[4]
+    assert "xsb_bn_bwd_pool_dxsum" not in p[4] and "xsb_maxpool2d_bwd" in p[4]
+    assert "xsb_bn_relu_maxpool_fwd" not in q[4] and "xsb_bn_bwd_pool_dxsum" not in q[4]
+    for a in (f, p):
+        for u, v in zip(a[:4], q[:4]):
+            assert np.abs(u - v).max() <= TOL * max(1.0, np.abs(v).max())
