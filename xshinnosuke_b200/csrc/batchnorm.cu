@@ -291,6 +291,74 @@ bn_stats_k(const float* __restrict__ x, int64_t R, int C, int LX, int LY, int ro
     }
 }
 
+// ------------------------------------------------------------------ forward statistics, small tensors (R <= 4096 rows)
+// bn_stats_k on a 100 KB - 1 MB tensor is three dependent latencies (row loads; fence + ticket; the last block's reload and
+// merge of the partials): 10 us. Here one 1024-thread block owns 8 float4 columns (32 channels) over ALL rows -- 128 row
+// lanes, <= 32 rows per thread in batches of 8 independent loads -- so nothing crosses a block: deviations from a common
+// pivot per channel (row 0, an actual sample: no E[x^2]-E[x]^2 cancellation) are plain sums, reduced by shuffles inside a
+// warp (4 row lanes x 8 columns) and once through shared memory over the 32 warps.
+constexpr int kSmallStatsThreads = 1024;
+constexpr int kSmallStatsMaxRows = 4096;
+
+__global__ void __launch_bounds__(kSmallStatsThreads)
+bn_stats_small_k(const float* __restrict__ x, int R, int C, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                 float* running_mean, float* running_var, float eps, float momentum) {
+    __shared__ float4 s_1[32][8], s_2[32][8];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;        // a warp = 4 row lanes x 8 columns
+    const int CV = C >> 2;
+    const int cv = blockIdx.x * 8 + tx;
+    const bool active = cv < CV;
+    const float4* col = reinterpret_cast<const float4*>(x) + (active ? cv : 0);
+    float4 K = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) K = __ldg(col);                                       // row 0
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int r0 = ty; r0 < R; r0 += 128 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = r0 + u * 128;
+            v[u] = K;                                                  // (rows past the end contribute a zero deviation)
+            if (active && r < R) v[u] = __ldg(col + (int64_t)r * CV);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float dx = v[u].x - K.x, dy = v[u].y - K.y, dz = v[u].z - K.z, dw = v[u].w - K.w;
+            a.x += dx; a.y += dy; a.z += dz; a.w += dw;
+            b.x = fmaf(dx, dx, b.x); b.y = fmaf(dy, dy, b.y); b.z = fmaf(dz, dz, b.z); b.w = fmaf(dw, dw, b.w);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {                               // the 4 row lanes of the warp that share a column
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+        b.x += __shfl_xor_sync(0xffffffffu, b.x, o); b.y += __shfl_xor_sync(0xffffffffu, b.y, o);
+        b.z += __shfl_xor_sync(0xffffffffu, b.z, o); b.w += __shfl_xor_sync(0xffffffffu, b.w, o);
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane < 8) { s_1[warp][lane] = a; s_2[warp][lane] = b; }       // lane < 8: row lane 0 of the warp, column = lane
+    __syncthreads();
+    if (tid < 32) {                                                    // thread (column tid >> 2, component tid & 3)
+        const int c8 = tid >> 2, k = tid & 3;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) {                                 // fixed order: deterministic
+            s1 += reinterpret_cast<const float*>(&s_1[w][c8])[k];
+            s2 += reinterpret_cast<const float*>(&s_2[w][c8])[k];
+        }
+        const int ch = (blockIdx.x * 8 + c8) * 4 + k;
+        if (ch < C) {
+            const float Kc = __ldg(x + ch);
+            const float invR = 1.0f / (float)R;
+            const float mean = Kc + s1 * invR;
+            const float var = fmaxf(s2 - s1 * s1 * invR, 0.f) * invR;
+            save_mean[ch] = mean;
+            save_invstd[ch] = 1.0f / sqrtf(var + eps);
+            if (running_mean) running_mean[ch] = momentum * running_mean[ch] + (1.f - momentum) * mean;
+            if (running_var) running_var[ch] = momentum * running_var[ch] + (1.f - momentum) * var;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ forward apply: y = gamma*(x-mean)*invstd + beta
 // kRelu: y = max(0, bn(x)) and bit e of `mask` = [bn(x)[e] < 0] (the in-place ReLU protocol's mask), fused
 template <int V, bool kRelu>
@@ -1369,6 +1437,13 @@ int xsb_bn_stats(const float* x, float* running_mean, float* running_var, float*
     XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
     cudaStream_t s = xsb_stream(stream);
     const bool v4 = use_vec4(C, x);
+    static const int small_on = [] { const char* e = getenv("XSB_BN_STATS_SMALL"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (small_on && v4 && R <= kSmallStatsMaxRows && R >= 64) {
+        bn_stats_small_k<<<(C / 4 + 7) / 8, kSmallStatsThreads, 0, s>>>(x, (int)R, C, save_mean, save_invstd, running_mean,
+                                                                         running_var, eps, momentum);
+        XSB_LAUNCH_CHECK();
+        return XSB_OK;
+    }
     const Geom g = make_geom(R, C, v4);
     XSB_CHECK_ARG(g.chunks < kCounterSlots, "bn: C=%d too large", C);
     dim3 grid(g.nb, g.chunks);
