@@ -779,6 +779,43 @@ def test_conv_tf32_at_benchmark_shapes(name, c, h, oc, k, s, p):
         xs.set_math_mode("fp32")
 
 
+def test_stem_fusions_at_benchmark_shape():
+    """BatchNormalization -> ReLU(inplace) -> MaxPooling2D(3, 2, 1) on the stem tensor of the benchmarked configuration
+    (128 x 64 x 112 x 112): the fused forward kernel and the pool-gathering BatchNorm backward against the separate
+    kernels (which the small-shape tests pin to the oracle) -- pooled values and arg-max bit-identical, dX / dgamma /
+    dbeta to 1e-6 (atomics: summation order)."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.layers import BatchNormalization, MaxPooling2D, ReLU
+    rs = np.random.RandomState(11)
+    x = rs.randn(128, 64, 112, 112).astype(np.float32)
+    g = rs.randn(128, 64, 56, 56).astype(np.float32)
+    keep = (xs.runtime.fuse_bn_relu_pool, xs.runtime.fuse_pool_bn_bwd)
+    res, calls = [], []
+    orig_f, orig_b = lib.xsb_bn_relu_maxpool_fwd, lib.xsb_bn_bwd_pool_dxsum
+    lib.xsb_bn_relu_maxpool_fwd = lambda *a: (calls.append("fwd"), orig_f(*a))[1]
+    lib.xsb_bn_bwd_pool_dxsum = lambda *a: (calls.append("bwd"), orig_b(*a))[1]
+    try:
+        for fuse in (True, False):
+            xs.runtime.fuse_bn_relu_pool = xs.runtime.fuse_pool_bn_bwd = fuse
+            np.random.seed(0)
+            bn, relu, pool = BatchNormalization(), ReLU(True), MaxPooling2D(3, 2, 1)
+            tx = xs.tensor(x, requires_grad=True)
+            y = pool(relu(bn(tx)))
+            yv, am = y.eval, np.asarray(y.cache["pool_argmax"])
+            y.backward(gradients=g)
+            res.append((yv, am, tx.grad.eval, bn.parameters()[0].grad.eval, bn.parameters()[1].grad.eval))
+            del tx, y, bn, relu, pool
+    finally:
+        lib.xsb_bn_relu_maxpool_fwd, lib.xsb_bn_bwd_pool_dxsum = orig_f, orig_b
+        xs.runtime.fuse_bn_relu_pool, xs.runtime.fuse_pool_bn_bwd = keep
+    assert calls == ["fwd", "bwd"]
+    (y1, a1, dx1, dg1, db1), (y0, a0, dx0, dg0, db0) = res
+    assert np.array_equal(y1, y0) and np.array_equal(a1, a0)
+    assert X.rel_err(dx1, dx0) <= 1e-6 and X.rel_err(dg1, dg0) <= 1e-5 and X.rel_err(db1, db0) <= 1e-5
+
+
 # ------------------------------------------------------------------ data parallel over NCCL (needs >= 2 GPUs)
 @pytest.mark.parametrize("optimizer,graph", [("sgd", False), ("adam", False), ("sgd", True), ("adam", True)])
 def test_data_parallel_nccl_matches_per_shard_oracle(optimizer, graph):
