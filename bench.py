@@ -306,15 +306,27 @@ def parity_check(wl, args, xs, nn):
     tol = 1e-5 if args.math in ("fp32", "fp32x3") else PARITY_TOL_NET
     # fp32 modes through a whole network: fp32 storage rounding of every activation on the way (the per-op bar is 1e-5)
     net_tol = max(tol, 1e-4) if wl["kind"] == "resnet" else max(tol, 2e-5)
-    passed = bool(all(v <= net_tol for v in errs.values()))
+    tols = {k: net_tol for k in errs}
     info = dict(first_layer_dw_rel_err=float(X.rel_err(got_first.reshape(ref["dw_first"].shape), ref["dw_first"])))
     if args.math == "tf32" and wl["kind"] == "resnet":
+        # how far the float64 oracle ITSELF moves when only its GEMM operands are cut to tf32: the floor of any tf32
+        # implementation through 18 layers. A quantity passes within max(5e-3, 2 x that floor) -- the per-op 2e-3 bar is
+        # what tests/test_parity_gpu.py enforces; this check is there to catch a broken kernel at the benched shape
         model_ref = oracle_step0(True)
+        floor = dict(loss_rel_err=abs(model_ref["loss"] - ref["loss"]) / abs(ref["loss"]),
+                     logits_rel_err=float(X.rel_err(model_ref["logits"], ref["logits"])),
+                     last_layer_dw_rel_err=float(X.rel_err(model_ref["dw_last"], ref["dw_last"])))
+        for k, v in floor.items():
+            tols[k] = max(net_tol, 2.0 * v)
         info["oracle_tf32_model_first_layer_dw_dev"] = float(X.rel_err(model_ref["dw_first"], ref["dw_first"]))
-        info["oracle_tf32_model_logits_dev"] = float(X.rel_err(model_ref["logits"], ref["logits"]))
+        info["oracle_tf32_model_logits_dev"] = floor["logits_rel_err"]
+        info["oracle_tf32_model_last_layer_dw_dev"] = floor["last_layer_dw_rel_err"]
         info["first_layer_dw_vs_tf32_model"] = float(X.rel_err(got_first.reshape(ref["dw_first"].shape), model_ref["dw_first"]))
+    passed = bool(all(v <= tols[k] for k, v in errs.items()))
+    tol_by = {k: float(t) for k, t in tols.items()}
     errs.update(info)
     errs.update(sample=f"{n} samples, step 0, identical seeded weights, float64 oracle", math_mode=args.math, tol=net_tol,
+                tol_by_quantity=tol_by,
                 tol_applies_to="loss, logits, last_layer_dw (first_layer_dw is informational: chaotic amplification)",
                 metric="max|a-b|/max|b|", passed=passed)
     return errs
