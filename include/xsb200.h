@@ -153,6 +153,13 @@ int xsb_bn_bwd_dxsum(const float* dy, const float* x, const float* gamma, const 
                      int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
                      const uint8_t* relu_mask /* nullable */, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done,
                      void* stream);
+/* The tail of a residual block -- BatchNormalization -> add -> ReLU(inplace) (xs/nn/functional.py:727-738 + 6-21 + 297-313)
+ * -- in one pass: z = max(0, bn_a(xa) + rhs) and the (sum < 0) bit mask; rhs = b (mean_b == NULL: identity shortcut) or a
+ * second BatchNorm applied on the fly, bn_b(b) (down-sampling shortcut). Bit-identical to xsb_bn_apply (+ xsb_bn_apply)
+ * + xsb_add_relu; the BatchNorm outputs are not written. XSB_ERR_UNSUPPORTED (3): nothing launched. */
+int xsb_bn_add_relu(const float* xa, const float* mean_a, const float* invstd_a, const float* gamma_a, const float* beta_a,
+                    const float* b, const float* mean_b /* nullable */, const float* invstd_b, const float* gamma_b,
+                    const float* beta_b, float* z, uint8_t* relu_mask, int64_t R, int C, void* stream);
 /* xsb_bn_bwd_dxsum for a BatchNorm whose (in-place rectified) output feeds a 3x3 / stride 2 / pad 1 max-pool: dy is the
  * pool's backward gather of dpool[N,OH,OW,C] through argmax (xs/nn/grad_fn.py:206-235), masked by relu_mask
  * (xs/nn/grad_fn.py:146-157) -- formed on the fly in both passes, the full-size dy[N,H,W,C] is never written.

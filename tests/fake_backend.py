@@ -186,6 +186,19 @@ class FakeLib:
         self._maxpool2d_fwd(z.data_ptr(), y, amax, N, H, W, C, k, sh, sw, pad, s)
         return 0
 
+    def _bn_add_relu(self, xa, mean_a, invstd_a, gamma_a, beta_a, b, mean_b, invstd_b, gamma_b, beta_b, z, mask, R, C, s):
+        # contract: xsb_bn_apply(xa) [+ xsb_bn_apply(b)] into scratch, then xsb_add_relu
+        n = R * C
+        ta = torch.empty(n, dtype=torch.float32)
+        self._bn_apply(xa, ta.data_ptr(), mean_a, invstd_a, gamma_a, beta_a, R, C, 0, None, s)
+        rhs = b
+        if mean_b:
+            tb = torch.empty(n, dtype=torch.float32)
+            self._bn_apply(b, tb.data_ptr(), mean_b, invstd_b, gamma_b, beta_b, R, C, 0, None, s)
+            rhs = tb.data_ptr()
+        self._add_relu(ta.data_ptr(), rhs, z, mask, n, s)
+        return 0
+
     def _add_relu(self, a, b, y, mask, n, s):
         t = f32(a, n) + f32(b, n)
         u8(mask, (n + 7) // 8)[...] = np.packbits(t < 0, bitorder="little")

@@ -240,3 +240,44 @@ def test_stem_pool_fusions_host_logic():
     for a in (f, p):
         for u, v in zip(a[:4], q[:4]):
             assert np.abs(u - v).max() <= TOL * max(1.0, np.abs(v).max())
+
+
+def test_residual_tail_fusion_host_logic():
+    """BatchNormalization -> add -> ReLU(inplace): one xsb_bn_add_relu call reads the BatchNorm INPUT(s) (identity shortcut:
+    one parked apply pass; down-sampling shortcut: two); the BatchNorm outputs stay parked and are still produced for a
+    later reader; results equal the separate kernels."""
+    import numpy as np
+    import xshinnosuke_b200 as xs
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.layers import BatchNormalization, ReLU
+    rs = np.random.RandomState(3)
+    x1 = rs.randn(4, 8, 6, 6).astype(np.float32)
+    x2 = rs.randn(4, 8, 6, 6).astype(np.float32)
+    g = rs.randn(4, 8, 6, 6).astype(np.float32)
+    keep = xs.runtime.fuse_bn_add_relu
+    out = {}
+    try:
+        for two in (False, True):
+            for fuse in (True, False):
+                xs.runtime.fuse_bn_add_relu = fuse
+                np.random.seed(0)
+                bn_a, bn_b, relu = BatchNormalization(), BatchNormalization(), ReLU(True)
+                ta, tb = xs.tensor(x1, requires_grad=True), xs.tensor(x2, requires_grad=True)
+                n0 = len(lib.calls)
+                a = bn_a(ta)
+                b = bn_b(tb) if two else tb
+                z = relu(xs.nn.functional.add(a, b))
+                zv = z.eval
+                av = a.eval                                  # a later reader of the BatchNorm output: plain apply kernel
+                z.backward(gradients=g)
+                calls = lib.calls[n0:]
+                out[(two, fuse)] = (zv, av, ta.grad.eval, tb.grad.eval, calls)
+    finally:
+        xs.runtime.fuse_bn_add_relu = keep
+    for two in (False, True):
+        f, p = out[(two, True)], out[(two, False)]
+        assert f[4].count("xsb_bn_add_relu") == 1 and "xsb_add_relu" not in f[4]
+        assert f[4].count("xsb_bn_apply") == 1              # only the explicit read of `a` materialised a BatchNorm output
+        assert "xsb_bn_add_relu" not in p[4] and p[4].count("xsb_add_relu") == 1
+        for u, v in zip(f[:4], p[:4]):
+            assert np.abs(u - v).max() <= TOL * max(1.0, np.abs(v).max())

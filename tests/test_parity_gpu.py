@@ -779,6 +779,45 @@ def test_conv_tf32_at_benchmark_shapes(name, c, h, oc, k, s, p):
         xs.set_math_mode("fp32")
 
 
+@pytest.mark.parametrize("n,c,h,two", [(4, 64, 14, False), (4, 64, 14, True), (3, 8, 9, False), (2, 512, 7, True),
+                                       (128, 128, 28, False), (128, 256, 14, True)])
+def test_residual_tail_fused_equals_unfused(n, c, h, two):
+    """BatchNormalization -> add -> ReLU(inplace) (the tail of a residual block; `two`: the shortcut ends in a BatchNorm as
+    well): xsb_bn_add_relu against xsb_bn_apply (x2) + xsb_add_relu -- forward output bit-identical (same arithmetic,
+    rounded at the same points), gradients to 1e-6 (atomics), incl. the last two shapes of the benchmarked configuration."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.layers import BatchNormalization, ReLU
+    rs = np.random.RandomState(n + c + h)
+    x1 = rs.randn(n, c, h, h).astype(np.float32)
+    x2 = rs.randn(n, c, h, h).astype(np.float32)
+    g = rs.randn(n, c, h, h).astype(np.float32)
+    keep = xs.runtime.fuse_bn_add_relu
+    res, calls = [], []
+    orig = lib.xsb_bn_add_relu
+    lib.xsb_bn_add_relu = lambda *a: (calls.append(1), orig(*a))[1]
+    try:
+        for fuse in (True, False):
+            xs.runtime.fuse_bn_add_relu = fuse
+            np.random.seed(0)
+            bn_a, bn_b, relu = BatchNormalization(), BatchNormalization(), ReLU(True)
+            ta, tb = xs.tensor(x1, requires_grad=True), xs.tensor(x2, requires_grad=True)
+            a = bn_a(ta)
+            b = bn_b(tb) if two else tb
+            z = relu(xs.nn.functional.add(a, b))
+            zv = z.eval
+            z.backward(gradients=g)
+            res.append((zv, ta.grad.eval, tb.grad.eval, bn_a.parameters()[0].grad.eval))
+    finally:
+        lib.xsb_bn_add_relu = orig
+        xs.runtime.fuse_bn_add_relu = keep
+    assert len(calls) == 1
+    (z1, da1, db1, dg1), (z0, da0, db0, dg0) = res
+    assert np.array_equal(z1, z0)
+    assert X.rel_err(da1, da0) <= 1e-6 and X.rel_err(db1, db0) <= 1e-6 and X.rel_err(dg1, dg0) <= 1e-5
+
+
 def test_stem_fusions_at_benchmark_shape():
     """BatchNormalization -> ReLU(inplace) -> MaxPooling2D(3, 2, 1) on the stem tensor of the benchmarked configuration
     (128 x 64 x 112 x 112): the fused forward kernel and the pool-gathering BatchNorm backward against the separate

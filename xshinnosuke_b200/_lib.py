@@ -13,7 +13,7 @@ HEADER = os.path.join(ROOT, "include", "xsb200.h")
 LIB_PATH = os.path.join(_HERE, "libxsb200.so")
 
 # fused entry points that answer XSB_ERR_UNSUPPORTED (3) for shapes outside their envelope instead of failing
-_MAY_DECLINE = {"xsb_bn_relu_maxpool_fwd", "xsb_bn_bwd_pool_dxsum"}
+_MAY_DECLINE = {"xsb_bn_relu_maxpool_fwd", "xsb_bn_bwd_pool_dxsum", "xsb_bn_add_relu"}
 
 MATH_FP32 = 0
 MATH_TF32 = 1

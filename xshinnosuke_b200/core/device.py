@@ -49,6 +49,9 @@ class Runtime:
         # kernels are instruction-bound: 396 us against 88 + 311 us back to back on L2-warm tensors, but -42 us inside the
         # training step (5.419 -> 5.377 ms), where the 411 MB scattered copy is cold
         self.fuse_pool_bn_bwd = os.environ.get("XSB_FUSE_POOL_BN_BWD", "1") != "0"
+        # BatchNormalization -> add -> ReLU(inplace), the tail of a residual block, as one kernel (xsb_bn_add_relu): the
+        # BatchNorm output(s) are never written and read back
+        self.fuse_bn_add_relu = os.environ.get("XSB_FUSE_BN_ADD_RELU", "1") != "0"
 
     def ensure(self):
         if self.ready:

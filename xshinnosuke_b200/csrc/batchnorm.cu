@@ -452,6 +452,69 @@ bn_apply_persist_k(const float* __restrict__ x, float* __restrict__ y, const flo
     }
 }
 
+// The tail of a residual block in ONE pass: z = max(0, bn_a(xa) + rhs) with the (sum < 0) bit mask, where rhs is a plain
+// tensor (identity shortcut) or a second BatchNorm applied on the fly (kTwoBN: the down-sampling shortcut). Same arithmetic,
+// in the same order and rounded to fp32 at the same points, as bn_apply followed by add_relu -- bit-identical -- but the
+// BatchNorm output(s) are never written and read back: 3e*n (+n/8) bytes instead of 5e*n (7e*n with two BatchNorms).
+template <bool kTwoBN>
+__global__ void __launch_bounds__(kThreads)
+bn_add_relu_persist_k(const float* __restrict__ xa, const float* __restrict__ mean_a, const float* __restrict__ invstd_a,
+                      const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const float* __restrict__ b,
+                      const float* __restrict__ mean_b, const float* __restrict__ invstd_b, const float* __restrict__ gamma_b,
+                      const float* __restrict__ beta_b, float* __restrict__ z, uint8_t* __restrict__ mask, int64_t nvec, int CV) {
+    constexpr int U = 4;
+    const int tid = threadIdx.x;
+    const int c = (tid & (CV - 1)) * 4;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean_a + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd_a + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma_a + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta_a + c));
+    float4 mu2 = mu, is2 = is, ga2 = ga, be2 = be;
+    if (kTwoBN) {
+        mu2 = __ldg(reinterpret_cast<const float4*>(mean_b + c));
+        is2 = __ldg(reinterpret_cast<const float4*>(invstd_b + c));
+        ga2 = __ldg(reinterpret_cast<const float4*>(gamma_b + c));
+        be2 = __ldg(reinterpret_cast<const float4*>(beta_b + c));
+    }
+    const int64_t stride = (int64_t)gridDim.x * (kThreads * U);
+    // block-uniform trip count: the mask nibbles are paired with a full-warp shuffle
+    for (int64_t bbase = (int64_t)blockIdx.x * (kThreads * U); bbase < nvec; bbase += stride) {
+        const int64_t base = bbase + tid;
+        float4 v[U], w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads;
+            v[u] = w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nvec) {
+                v[u] = ldg_stream(reinterpret_cast<const float4*>(xa) + i);
+                w[u] = ldg_stream(reinterpret_cast<const float4*>(b) + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads;
+            float4 o, r = w[u];
+            o.x = fmaf((v[u].x - mu.x) * is.x, ga.x, be.x);
+            o.y = fmaf((v[u].y - mu.y) * is.y, ga.y, be.y);
+            o.z = fmaf((v[u].z - mu.z) * is.z, ga.z, be.z);
+            o.w = fmaf((v[u].w - mu.w) * is.w, ga.w, be.w);
+            if (kTwoBN) {
+                r.x = fmaf((w[u].x - mu2.x) * is2.x, ga2.x, be2.x);
+                r.y = fmaf((w[u].y - mu2.y) * is2.y, ga2.y, be2.y);
+                r.z = fmaf((w[u].z - mu2.z) * is2.z, ga2.z, be2.z);
+                r.w = fmaf((w[u].w - mu2.w) * is2.w, ga2.w, be2.w);
+            }
+            const float4 t = make_float4(__fadd_rn(o.x, r.x), __fadd_rn(o.y, r.y), __fadd_rn(o.z, r.z), __fadd_rn(o.w, r.w));
+            const unsigned nib = (t.x < 0.f ? 1u : 0u) | (t.y < 0.f ? 2u : 0u) | (t.z < 0.f ? 4u : 0u) | (t.w < 0.f ? 8u : 0u);
+            const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);
+            if ((tid & 1) == 0 && i < nvec) mask[i >> 1] = (uint8_t)(nib | (hi << 4));
+            if (i < nvec)
+                stg_stream(reinterpret_cast<float4*>(z) + i,
+                           make_float4(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f), fmaxf(t.w, 0.f)));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ backward sums (and plain column sums)
 // kXhat: also accumulate sum(dy * xhat). ws: [counters][nb][C] s_dy | [nb][C] s_dyxhat
 // finalize writes dgamma/dbeta (+)= and coef[0..C)=sum_dy/M, coef[C..2C)=sum_dyxhat/M, coef[2C..3C)=gamma*invstd
@@ -1427,6 +1490,35 @@ static int launch_bn_apply(const float* x, float* y, const float* mean, const fl
     } else {
         bn_apply_k<1, false><<<blocks, kThreads, 0, s>>>(x, y, mean, invstd, gamma, beta, nvec, CV, cv_mask, nullptr);
     }
+    XSB_LAUNCH_CHECK();
+    return XSB_OK;
+}
+
+// z = max(0, bn_a(xa) + rhs) + ReLU bit mask (see bn_add_relu_persist_k); rhs = b, or bn_b(b) when mean_b != NULL.
+// XSB_ERR_UNSUPPORTED (nothing launched) outside the envelope: the caller runs xsb_bn_apply (x2) + xsb_add_relu.
+int xsb_bn_add_relu(const float* xa, const float* mean_a, const float* invstd_a, const float* gamma_a, const float* beta_a,
+                    const float* b, const float* mean_b, const float* invstd_b, const float* gamma_b, const float* beta_b,
+                    float* z, uint8_t* relu_mask, int64_t R, int C, void* stream) {
+    const int CV = C / 4;
+    const int64_t nvec = R * CV;
+    const bool two = mean_b != nullptr;
+    if (R <= 0 || C <= 0 || C % 4 != 0 || CV > kThreads || (CV & (CV - 1)) != 0 || nvec % 2 != 0 || !relu_mask ||
+        !aligned16(xa) || !aligned16(b) || !aligned16(z) || !aligned16(mean_a) || !aligned16(invstd_a) || !aligned16(gamma_a) ||
+        !aligned16(beta_a) ||
+        (two && (!invstd_b || !gamma_b || !beta_b || !aligned16(mean_b) || !aligned16(invstd_b) || !aligned16(gamma_b) ||
+                 !aligned16(beta_b))))
+        return XSB_ERR_UNSUPPORTED;
+    int64_t pb = ceil_div64(nvec, (int64_t)kThreads * 4 * 2);
+    const int64_t cap = (int64_t)xsb_sm_count_cached() * 8;
+    if (pb > cap) pb = cap;
+    if (pb < 1) pb = 1;
+    cudaStream_t s = xsb_stream(stream);
+    if (two)
+        bn_add_relu_persist_k<true><<<(unsigned)pb, kThreads, 0, s>>>(xa, mean_a, invstd_a, gamma_a, beta_a, b, mean_b, invstd_b,
+                                                                     gamma_b, beta_b, z, relu_mask, nvec, CV);
+    else
+        bn_add_relu_persist_k<false><<<(unsigned)pb, kThreads, 0, s>>>(xa, mean_a, invstd_a, gamma_a, beta_a, b, nullptr, nullptr,
+                                                                      nullptr, nullptr, z, relu_mask, nvec, CV);
     XSB_LAUNCH_CHECK();
     return XSB_OK;
 }

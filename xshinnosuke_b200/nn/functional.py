@@ -101,11 +101,40 @@ def add(lhs: Tensor, rhs: Tensor, out: Tensor = None) -> Tensor:
         if mask is None:
             lib.xsb_add(_a.ptr, _b.ptr, ybuf.data_ptr(), n, rt.stream())
         else:
+            if rt.fuse_bn_add_relu and _bn_add_relu(_a, _b, ybuf, mask):
+                return
             lib.xsb_add_relu(_a.ptr, _b.ptr, ybuf.data_ptr(), mask.data_ptr(), n, rt.stream())
         rt.launches += 1
     run.fusable_relu = n % 8 == 0
     y.pending_op = run
     return _wire(out, (lhs, rhs), lhs.requires_grad or rhs.requires_grad, AddBackward)
+
+
+def _bn_add_relu(a, b, ybuf, mask):
+    """The tail of a residual block: an operand of the add is a BatchNorm output whose apply pass is still parked (F.batch_norm
+    defers it by one op) -- z = max(0, bn(x) + other) and the mask leave from ONE kernel that reads the BatchNorm INPUT; both
+    operands may be such outputs (down-sampling shortcut). The parked apply passes stay parked: whoever reads a BatchNorm
+    output later still gets it from the plain kernel. -> True when the fused kernel ran."""
+    pa, pb = getattr(a.pending_op, "bn", None), getattr(b.pending_op, "bn", None)
+    if pa is None and pb is None:
+        return False
+    if pa is None:                       # (fp32 addition commutes exactly)
+        a, b, pa, pb = b, a, pb, None
+    R, C = pa["R"], pa["C"]
+    if pa["x"].cl != a.cl or a.cl != b.cl or a.size != R * C:
+        return False
+    if pb is not None and (pb["R"] != R or pb["C"] != C or pb["x"].cl != b.cl):
+        pb = None
+    bsrc = pb["x"].ptr if pb is not None else b.ptr
+    rc = lib.xsb_bn_add_relu(pa["x"].ptr, pa["mean"].peek_ptr(), pa["invstd"].peek_ptr(), pa["gamma"].ptr, pa["beta"].ptr, bsrc,
+                             pb["mean"].peek_ptr() if pb is not None else None,
+                             pb["invstd"].peek_ptr() if pb is not None else None,
+                             pb["gamma"].ptr if pb is not None else None, pb["beta"].ptr if pb is not None else None,
+                             ybuf.data_ptr(), mask.data_ptr(), R, C, rt.stream())
+    if rc != 0:
+        return False
+    rt.launches += 1
+    return True
 
 
 def _add_rowvector(lhs, rhs, out):
