@@ -67,6 +67,8 @@ def cost(name, a):
         return "byte", 4.0 * a[5] * a[6]
     if name == "xsb_bn_apply":
         return "byte", 8.0 * a[6] * a[7] + (a[6] * a[7] / 8.0 if a[8] else 0.0)
+    if name == "xsb_bn_add_relu":          # BatchNorm input + shortcut read, rectified sum + bit mask written
+        return "byte", 12.0 * a[12] * a[13] + a[12] * a[13] / 8.0
     if name == "xsb_add_relu":
         return "byte", 12.0 * a[4] + a[4] / 8.0
     if name in ("xsb_bn_bwd", "xsb_bn_bwd_dxsum"):
