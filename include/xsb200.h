@@ -169,6 +169,14 @@ int xsb_bn_bwd_pool_dxsum(const float* dpool, const uint8_t* argmax, const float
                           float* dbeta /* nullable */, int N, int H, int W, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
                           const uint8_t* relu_mask /* nullable */, float* ws, float* dxsum /* nullable */, int acc_dxsum,
                           void* stream);
+/* xsb_bn_bwd_dxsum (dxsum nullable) that also writes dy_masked_out[R,C] = dy with the relu_mask elements zeroed, from the
+ * apply pass that reads the masked dy anyway: the gradient of the identity shortcut of a residual block (AddBackward behind an
+ * in-place ReLU, xs/nn/grad_fn.py:6-16 + 146-157) without a pass of its own. *side_done (HOST int) = 1 when written. */
+int xsb_bn_bwd_dxsum_side(const float* dy, const float* x, const float* gamma, const float* save_mean,
+                          const float* save_invstd, float* dx, float* dgamma /* nullable */, float* dbeta /* nullable */,
+                          int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta, const uint8_t* relu_mask /* nullable */,
+                          float* ws, float* dxsum /* nullable */, int acc_dxsum, int* dxsum_done, float* dy_masked_out,
+                          int* side_done, void* stream);
 /* batch statistics from the per-CTA (count, mean, M2) partials a convolution's epilogue left (xsb_conv2d_fwd_stats):
  * same outputs and running-statistics update as xsb_bn_stats (xs/nn/functional.py:689-706), no pass over x. */
 int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* running_mean, float* running_var,

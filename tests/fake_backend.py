@@ -228,6 +228,21 @@ class FakeLib:
         _store(f32(dxsum, C), contrib.sum(axis=0), acc_dxsum)
         done._obj.value = 1
 
+    def _bn_bwd_dxsum_side(self, dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, rmask, ws,
+                           dxsum, acc_dxsum, done, side, side_done, s):
+        # contract: xsb_bn_bwd_dxsum (dxsum nullable) + side = dy with the masked elements zeroed; side_done (host int) = 1
+        if dxsum:
+            self._bn_bwd_dxsum(dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, rmask, ws, dxsum,
+                               acc_dxsum, done, s)
+        else:
+            self._bn_bwd(dy, x, gamma, smean, sinv, dx, dgamma, dbeta, R, C, acc_dx, acc_dg, acc_db, rmask, ws, s)
+        g = f32(dy, R * C).astype(np.float64)
+        if rmask:
+            m = np.unpackbits(u8(rmask, (R * C + 7) // 8), bitorder="little")[:R * C].astype(bool)
+            g = np.where(m, 0.0, g)
+        f32(side, R * C)[...] = g
+        side_done._obj.value = 1
+
     def _bn_bwd_pool_dxsum(self, dpool, amax, x, gamma, smean, sinv, dx, dgamma, dbeta, N, H, W, C, acc_dx, acc_dg, acc_db,
                            rmask, ws, dxsum, acc_dxsum, s):
         # contract: xsb_maxpool2d_bwd (3x3, stride 2, pad 1) into a scratch dy, then xsb_bn_bwd(_dxsum) on it

@@ -281,3 +281,38 @@ def test_residual_tail_fusion_host_logic():
         assert "xsb_bn_add_relu" not in p[4] and p[4].count("xsb_add_relu") == 1
         for u, v in zip(f[:4], p[:4]):
             assert np.abs(u - v).max() <= TOL * max(1.0, np.abs(v).max())
+
+
+def test_identity_shortcut_gradient_written_by_the_batchnorm_backward():
+    """Residual block with an identity shortcut, backward: the masked dZ the shortcut needs is written by the BatchNorm
+    backward of the other branch (xsb_bn_bwd_dxsum_side) -- no relu_bwd_mask pass; a reader that gets to the shortcut's
+    gradient first still receives it from the plain kernel; results equal the separate kernels."""
+    import numpy as np
+    import xshinnosuke_b200 as xs
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.layers import BatchNormalization, Conv2D, ReLU
+    rs = np.random.RandomState(9)
+    x = rs.randn(3, 8, 6, 6).astype(np.float32)
+    g = rs.randn(3, 8, 6, 6).astype(np.float32)
+    keep = xs.runtime.fuse_add_bwd_side
+    out = {}
+    try:
+        for fuse in (True, False):
+            xs.runtime.fuse_add_bwd_side = fuse
+            np.random.seed(0)
+            pre, conv, bn, relu = ReLU(True), Conv2D(8, 3, padding=1), BatchNormalization(), ReLU(True)
+            tx = xs.tensor(x, requires_grad=True)
+            n0 = len(lib.calls)
+            z0 = pre(BatchNormalization()(tx))               # block input: itself an in-place rectified tensor
+            z = relu(xs.nn.functional.add(bn(conv(z0)), z0))
+            zv = z.eval
+            z.backward(gradients=g)
+            calls = lib.calls[n0:]
+            out[fuse] = (zv, tx.grad.eval, conv.parameters()[0].grad.eval, calls)
+    finally:
+        xs.runtime.fuse_add_bwd_side = keep
+    f, p = out[True], out[False]
+    assert f[3].count("xsb_bn_bwd_dxsum_side") == 1 and p[3].count("xsb_bn_bwd_dxsum_side") == 0
+    assert p[3].count("xsb_relu_bwd_mask") == f[3].count("xsb_relu_bwd_mask") + 1
+    for u, v in zip(f[:3], p[:3]):
+        assert np.abs(u - v).max() <= TOL * max(1.0, np.abs(v).max())

@@ -818,6 +818,48 @@ def test_residual_tail_fused_equals_unfused(n, c, h, two):
     assert X.rel_err(da1, da0) <= 1e-6 and X.rel_err(db1, db0) <= 1e-6 and X.rel_err(dg1, dg0) <= 1e-5
 
 
+@pytest.mark.parametrize("n,c,h,mode", [(4, 64, 14, "fp32"), (3, 8, 9, "fp32"), (128, 64, 56, "tf32"), (128, 256, 14, "tf32")])
+def test_identity_shortcut_side_output_equals_separate_kernel(n, c, h, mode):
+    """Residual block with an identity shortcut, backward: the masked dZ the shortcut needs is written by the BatchNorm
+    backward of the other branch (xsb_bn_bwd_dxsum_side; cooperative kernel for the small tensors, two-launch persistent
+    kernels for the layer1-sized one) instead of by xsb_relu_bwd_mask -- the same values written first, the conv dgrad
+    added second: every gradient equal up to the atomics of the BatchNorm sums."""
+    import xshinnosuke_b200 as xs
+    from oracle import xs_numpy as X
+    from xshinnosuke_b200._lib import lib
+    from xshinnosuke_b200.layers import BatchNormalization, Conv2D, ReLU
+    rs = np.random.RandomState(n + c + h)
+    x = rs.randn(n, c, h, h).astype(np.float32)
+    g = rs.randn(n, c, h, h).astype(np.float32)
+    keep = xs.runtime.fuse_add_bwd_side
+    res, calls = [], []
+    orig = lib.xsb_bn_bwd_dxsum_side
+    lib.xsb_bn_bwd_dxsum_side = lambda *a: (calls.append(1), orig(*a))[1]
+    xs.set_math_mode(mode)
+    try:
+        for fuse in (True, False):
+            xs.runtime.fuse_add_bwd_side = fuse
+            np.random.seed(0)
+            pre, conv, bn, relu = ReLU(True), Conv2D(c, 3, padding=1), BatchNormalization(), ReLU(True)
+            tx = xs.tensor(x, requires_grad=True)
+            z0 = pre(BatchNormalization()(tx))
+            z = relu(xs.nn.functional.add(bn(conv(z0)), z0))
+            zv = z.eval
+            z.backward(gradients=g)
+            res.append((zv, tx.grad.eval, conv.parameters()[0].grad.eval, bn.parameters()[0].grad.eval))
+            del tx, z0, z
+    finally:
+        lib.xsb_bn_bwd_dxsum_side = orig
+        xs.runtime.fuse_add_bwd_side = keep
+        xs.set_math_mode("fp32")
+    assert len(calls) == 1
+    (z1, dx1, dw1, dg1), (z0_, dx0, dw0, dg0) = res
+    assert np.array_equal(z1, z0_)
+    # (the 26 M-element tensors: two runs of the SAME path differ by 2.5e-5 in dX -- atomics in the BatchNorm sums, measured)
+    tol = 1e-6 if mode == "fp32" else 1e-4
+    assert X.rel_err(dx1, dx0) <= tol and X.rel_err(dw1, dw0) <= tol and X.rel_err(dg1, dg0) <= 10 * tol
+
+
 def test_stem_fusions_at_benchmark_shape():
     """BatchNormalization -> ReLU(inplace) -> MaxPooling2D(3, 2, 1) on the stem tensor of the benchmarked configuration
     (128 x 64 x 112 x 112): the fused forward kernel and the pool-gathering BatchNorm backward against the separate

@@ -52,6 +52,9 @@ class Runtime:
         # BatchNormalization -> add -> ReLU(inplace), the tail of a residual block, as one kernel (xsb_bn_add_relu): the
         # BatchNorm output(s) are never written and read back
         self.fuse_bn_add_relu = os.environ.get("XSB_FUSE_BN_ADD_RELU", "1") != "0"
+        # ... and, backward, the identity shortcut's masked gradient written by the BatchNorm backward of the other branch
+        # (xsb_bn_bwd_dxsum_side) instead of by a relu_bwd_mask pass of its own
+        self.fuse_add_bwd_side = os.environ.get("XSB_FUSE_ADD_BWD_SIDE", "1") != "0"
 
     def ensure(self):
         if self.ready:
@@ -151,7 +154,7 @@ class DevArray:
     1 ("+=") afterwards -- which is how `zero_grad` costs no memset and no read-modify-write
     (the reference allocates and fills zeros: xs/utils/common.py:29-32, xs/core/base.py:312-316).
     """
-    __slots__ = ("buf", "shape", "dtype", "cl", "_pz", "_root", "lazy_mask")
+    __slots__ = ("buf", "shape", "dtype", "cl", "_pz", "_root", "lazy_mask", "side_out")
 
     def __init__(self, buf, shape, dtype="float32", cl=None, pending_zero=False, _share=None):
         self.buf = buf
@@ -162,6 +165,9 @@ class DevArray:
         # in this ReLU bit mask zeroed (AddBackward hands dZ to a BatchNorm branch this way; the BN backward kernels apply
         # the mask on the fly, anyone else materialises a masked copy first)
         self.lazy_mask = None
+        # side_out (set on a lazy-masked alias only): (gradient DevArray, parked closure) of the identity shortcut that wants the
+        # same masked dZ written out -- the BatchNorm backward that applies the mask writes it on the way (AddBackward)
+        self.side_out = None
         if _share is None:
             # one cell shared by an array and all its views: [pending_zero, pending_op, deferred_add]
             self._pz = [bool(pending_zero), None, None]

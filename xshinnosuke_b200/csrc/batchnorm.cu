@@ -834,7 +834,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x, float* dx, const float* __restrict__ mean,
                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ sums,
                        float invM, int64_t nvec, int CV, const uint8_t* __restrict__ rmask, float* dgamma, float* dbeta,
-                       int acc_gamma, int acc_beta, float* dxsum, float* sums_rw, unsigned* ticket, int rev) {
+                       int acc_gamma, int acc_beta, float* dxsum, float* sums_rw, unsigned* ticket, int rev,
+                       float* __restrict__ side) {
     __shared__ float4 s_a[kThreads];
     __shared__ unsigned s_last;
     constexpr int U = kPersistUnroll;
@@ -883,6 +884,9 @@ bn_bwd_apply_persist_k(const float* __restrict__ dy, const float* __restrict__ x
                     if (m & 4u) g[u].z = 0.f;
                     if (m & 8u) g[u].w = 0.f;
                 }
+                // side (nullable): the MASKED dy is also the gradient of the identity shortcut of a residual block
+                // (AddBackward behind the in-place ReLU) -- written from here instead of by a relu_bwd_mask pass of its own
+                if (side) stg_stream(reinterpret_cast<float4*>(side) + i, g[u]);
                 float4 o;
                 o.x = kg.x * (g[u].x - k1.x - (xv[u].x - mu.x) * is.x * k2.x);
                 o.y = kg.y * (g[u].y - k1.y - (xv[u].y - mu.y) * is.y * k2.y);
@@ -1212,7 +1216,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 bn_bwd_fused_k(const float* __restrict__ dy, const float* __restrict__ x, float* dx, const float* __restrict__ mean,
                const float* __restrict__ invstd, const float* __restrict__ gamma, float* sums, float invM, int64_t nvec, int CV,
                const uint8_t* __restrict__ rmask, float* dgamma, float* dbeta, int acc_gamma, int acc_beta, float* dxsum,
-               int zero_dxsum, unsigned* ticket, int iters) {
+               int zero_dxsum, unsigned* ticket, int iters, float* __restrict__ side) {
     extern __shared__ float4 park[];                       // [CACHE][iters][U][threads]
     __shared__ float4 s_a[kFusedThreads], s_b[kFusedThreads];
     __shared__ unsigned s_last;
@@ -1316,6 +1320,7 @@ bn_bwd_fused_k(const float* __restrict__ dy, const float* __restrict__ x, float*
             const int64_t i = base + (int64_t)u * T;
             if (i < nvec) {
                 const float4 g = park[(it * U + u) * T + tid];
+                if (side) stg_stream(reinterpret_cast<float4*>(side) + i, g);      // (see bn_bwd_apply_persist_k)
                 const float4 xx = CACHE == 2 ? park_x[(it * U + u) * T + tid] : xv[u];
                 float4 o;
                 o.x = kg.x * (g.x - k1.x - (xx.x - mu.x) * is.x * k2.x);
@@ -1418,7 +1423,7 @@ inline bool use_vec4(int C, const void* a, const void* b = nullptr, const void* 
 static int launch_bn_bwd_fused(const float* dy, const float* x, float* dx, const float* mean, const float* invstd,
                                const float* gamma, float* sums, int64_t R, int64_t nvec, int CV, const uint8_t* rmask,
                                float* dgamma, float* dbeta, int acc_dx, int acc_gamma, int acc_beta, float* dxsum, int acc_dxsum,
-                               unsigned* ticket, cudaStream_t s) {
+                               unsigned* ticket, cudaStream_t s, float* side = nullptr) {
     static const int enabled = [] { const char* e = getenv("XSB_BN_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
     if (!enabled || CV > kFusedThreads) return XSB_ERR_UNSUPPORTED;
     const int64_t chunk = (int64_t)kFusedThreads * kFusedU;
@@ -1437,7 +1442,7 @@ static int launch_bn_bwd_fused(const float* dy, const float* x, float* dx, const
     int iters_arg = iters;
     void* args[] = {(void*)&dy, (void*)&x, (void*)&dx, (void*)&mean, (void*)&invstd, (void*)&gamma, (void*)&sums, (void*)&invM,
                     (void*)&nvec, (void*)&CV, (void*)&rmask, (void*)&dgamma, (void*)&dbeta, (void*)&acc_gamma, (void*)&acc_beta,
-                    (void*)&dxsum, (void*)&zero_dxsum, (void*)&ticket, (void*)&iters_arg};
+                    (void*)&dxsum, (void*)&zero_dxsum, (void*)&ticket, (void*)&iters_arg, (void*)&side};
     const void* fn;
     if (cache == 2) fn = acc_dx ? (const void*)bn_bwd_fused_k<2, true> : (const void*)bn_bwd_fused_k<2, false>;
     else fn = acc_dx ? (const void*)bn_bwd_fused_k<1, true> : (const void*)bn_bwd_fused_k<1, false>;
@@ -1593,7 +1598,8 @@ int xsb_bn_finalize(const float* partials, int P, int64_t R, int C, float* runni
 
 static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                        float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
-                       const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done, void* stream);
+                       const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done, void* stream,
+                       float* side = nullptr, int* side_done = nullptr);
 
 // Backward. dx nullable (input needs no grad); dgamma/dbeta nullable. acc_* : 1 = "+=", 0 = "=".
 // relu_mask (nullable): dy is first masked with the in-place ReLU's bit mask (fused ReLUBackward).
@@ -1614,12 +1620,27 @@ int xsb_bn_bwd_dxsum(const float* dy, const float* x, const float* gamma, const 
                        ws, dxsum, acc_dxsum, dxsum_done, stream);
 }
 
+// Same (dxsum nullable), and dy_masked_out[R, C] = dy with the relu_mask elements zeroed, written by the apply pass that
+// reads the masked dy anyway: the gradient of the identity shortcut of a residual block (xs/nn/grad_fn.py:6-16 behind
+// 146-157) without a relu_bwd_mask pass of its own. *side_done (host) = 1 when written, 0 when this shape runs the generic
+// kernels (then call xsb_relu_bwd_mask).
+int xsb_bn_bwd_dxsum_side(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                          float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
+                          const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done,
+                          float* dy_masked_out, int* side_done, void* stream) {
+    return bn_bwd_impl(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, R, C, acc_dx, acc_dgamma, acc_dbeta, relu_mask,
+                       ws, dxsum, acc_dxsum, dxsum_done, stream, dy_masked_out, side_done);
+}
+
 static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                        float* dx, float* dgamma, float* dbeta, int64_t R, int C, int acc_dx, int acc_dgamma, int acc_dbeta,
-                       const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done, void* stream) {
+                       const uint8_t* relu_mask, float* ws, float* dxsum, int acc_dxsum, int* dxsum_done, void* stream,
+                       float* side, int* side_done) {
     XSB_CHECK_ARG(R > 0 && C > 0, "bn: empty input");
     cudaStream_t s = xsb_stream(stream);
     if (dxsum_done) *dxsum_done = 0;
+    if (side_done) *side_done = 0;
+    if (side && !aligned16(side)) side = nullptr;
     const bool v4 = use_vec4(C, dy, x, dx);
     const int CV4 = C / 4;
     if (v4 && dx && C % 4 == 0 && CV4 <= kThreads && (CV4 & (CV4 - 1)) == 0 && aligned16(save_mean) &&
@@ -1631,9 +1652,10 @@ static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, cons
         const int64_t nvec = R * CV4;
         {
             const int rc = launch_bn_bwd_fused(dy, x, dx, save_mean, save_invstd, gamma, sums, R, nvec, CV4, relu_mask, dgamma,
-                                               dbeta, acc_dx, acc_dgamma, acc_dbeta, dxsum, acc_dxsum, ticket, s);
+                                               dbeta, acc_dx, acc_dgamma, acc_dbeta, dxsum, acc_dxsum, ticket, s, side);
             if (rc != XSB_ERR_UNSUPPORTED) {
                 if (rc == XSB_OK && dxsum && dxsum_done) *dxsum_done = 1;
+                if (rc == XSB_OK && side && side_done) *side_done = 1;
                 return rc;
             }
         }
@@ -1650,13 +1672,14 @@ static int bn_bwd_impl(const float* dy, const float* x, const float* gamma, cons
         if (acc_dx)
             bn_bwd_apply_persist_k<true><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
                                                                               nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
-                                                                              acc_dbeta, dxsum, sums, ticket, rev);
+                                                                              acc_dbeta, dxsum, sums, ticket, rev, side);
         else
             bn_bwd_apply_persist_k<false><<<(unsigned)blocks, kThreads, 0, s>>>(dy, x, dx, save_mean, save_invstd, gamma, sums, invM,
                                                                                nvec, CV4, relu_mask, dgamma, dbeta, acc_dgamma,
-                                                                               acc_dbeta, dxsum, sums, ticket, rev);
+                                                                               acc_dbeta, dxsum, sums, ticket, rev, side);
         XSB_LAUNCH_CHECK();
         if (dxsum && dxsum_done) *dxsum_done = 1;
+        if (side && side_done) *side_done = 1;
         return XSB_OK;
     }
     const Geom g = make_geom(R, C, v4, 2 * 148);   // two streamed arrays per thread: fewer, fatter CTAs measured faster

@@ -88,6 +88,7 @@ def AddBackward(outputs: Tensor, relu_mask=None):
         return
     if relu_mask is not None:
         if all(_grad_arr(t).cl == dy.cl for t in targets):
+            aliases, plain = [], []
             for t in targets:
                 g = _grad_arr(t)
                 if (t.grad_fn is BatchNormBackward and t.is_dynamic and len(t.out_bounds) == 1 and g.pending_zero
@@ -98,9 +99,23 @@ def AddBackward(outputs: Tensor, relu_mask=None):
                     dy.ptr  # noqa: B018 -- dZ itself must be materialised before it is aliased
                     alias.lazy_mask = relu_mask
                     t.grad._arr = alias
+                    aliases.append(alias)
                     continue
-                lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), g.peek_ptr(), g.size, g.take_acc(), rt.stream())
-                rt.launches += 1
+                plain.append((t, g))
+            for t, g in plain:
+                dy_ptr = dy.ptr
+
+                def masked_copy(acc, _g=g, _ptr=dy_ptr, _keep=(dy.buf, relu_mask)):
+                    lib.xsb_relu_bwd_mask(_ptr, relu_mask.data_ptr(), _g.peek_ptr(), _g.size, acc, rt.stream())
+                    rt.launches += 1
+                # identity shortcut next to a BatchNorm branch: that BatchNorm's backward reads the same masked dZ -- it
+                # writes this copy on the way (xsb_bn_bwd_dxsum_side). Parked like a postponed add: a reader that comes
+                # first, or a BatchNorm kernel without the side output, still gets it from relu_bwd_mask
+                if (rt.fuse_add_bwd_side and len(aliases) == 1 and aliases[0].side_out is None and t.is_dynamic
+                        and tuple(g.shape) == tuple(dy.shape) and g.defer_add(masked_copy)):
+                    aliases[0].side_out = (g, masked_copy)
+                else:
+                    masked_copy(g.take_acc())
                 _done(t)
             return
         lib.xsb_relu_bwd_mask(dy.ptr, relu_mask.data_ptr(), dy.peek_ptr(), dy.size, 0, rt.stream())
@@ -370,19 +385,35 @@ def BatchNormBackward(outputs: Tensor, relu_mask=None):
         conv_bias = inputs.in_bounds[2]
         if conv_bias is not None and conv_bias.requires_grad:
             cb = _grad_arr(conv_bias)
-    if cb is not None:
-        was_zero = cb.pending_zero
-        done = ctypes.c_int(0)
-        lib.xsb_bn_bwd_dxsum(dy_ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
-                             gx.peek_ptr(), gg.peek_ptr() if gg is not None else None,
-                             gb.peek_ptr() if gb is not None else None, R, C, gx.take_acc(),
-                             gg.take_acc() if gg is not None else 0, gb.take_acc() if gb is not None else 0,
-                             relu_mask.data_ptr() if relu_mask is not None else None, rt.ws_small.data_ptr(),
-                             cb.peek_ptr(), cb.take_acc(), ctypes.byref(done), rt.stream())
-        if done.value:
-            inputs.cache["bias_grad_done"] = True
+    # the identity shortcut of the residual block wants the same masked dZ written out (AddBackward parked that copy): the
+    # apply pass writes it on the way, if it is still parked and the gradient it belongs to is still untouched
+    side = None
+    want = getattr(outputs.grad.arr, "side_out", None)
+    if want is not None and relu_mask is not None and gx is not None and x.ndim == 4:
+        sg, parked = want
+        if sg._pz[2] is parked and sg.pending_zero and sg.lazy_mask is None and sg.size == R * C:
+            side = sg
+    if cb is not None or side is not None:
+        was_zero = cb.pending_zero if cb is not None else False
+        done, sdone = ctypes.c_int(0), ctypes.c_int(0)
+        args = (dy_ptr, x.ptr, gamma.arr.ptr, outputs.cache["save_mean"].ptr, outputs.cache["save_invstd"].ptr,
+                gx.peek_ptr(), gg.peek_ptr() if gg is not None else None,
+                gb.peek_ptr() if gb is not None else None, R, C, gx.take_acc(),
+                gg.take_acc() if gg is not None else 0, gb.take_acc() if gb is not None else 0,
+                relu_mask.data_ptr() if relu_mask is not None else None, rt.ws_small.data_ptr(),
+                cb.peek_ptr() if cb is not None else None, cb.take_acc() if cb is not None else 0, ctypes.byref(done))
+        if side is not None:
+            lib.xsb_bn_bwd_dxsum_side(*args, side.buf.data_ptr(), ctypes.byref(sdone), rt.stream())
+            if sdone.value:                 # written as the first "=" writer: the parked relu_bwd_mask is void
+                side._pz[2] = None
+                side.pending_zero = False
         else:
-            cb.pending_zero = was_zero
+            lib.xsb_bn_bwd_dxsum(*args, rt.stream())
+        if cb is not None:
+            if done.value:
+                inputs.cache["bias_grad_done"] = True
+            else:
+                cb.pending_zero = was_zero
         rt.launches += 2
         _done(gamma)
         _done(beta)

@@ -73,6 +73,8 @@ def cost(name, a):
         return "byte", 12.0 * a[4] + a[4] / 8.0
     if name in ("xsb_bn_bwd", "xsb_bn_bwd_dxsum"):
         return "byte", (20.0 if a[5] else 8.0) * a[8] * a[9]
+    if name == "xsb_bn_bwd_dxsum_side":     # + the masked dy written out for the identity shortcut
+        return "byte", 24.0 * a[8] * a[9]
     if name == "xsb_bn_bwd_pool_dxsum":
         # two passes over (x, dpool, argmax, mask) + dx; the scattered dy the unfused pair writes and reads twice is gone
         N, H, W, C = a[9:13]
