@@ -112,6 +112,7 @@ def AddBackward(outputs: Tensor, relu_mask=None):
                 # writes this copy on the way (xsb_bn_bwd_dxsum_side). Parked like a postponed add: a reader that comes
                 # first, or a BatchNorm kernel without the side output, still gets it from relu_bwd_mask
                 if (rt.fuse_add_bwd_side and len(aliases) == 1 and aliases[0].side_out is None and t.is_dynamic
+                        and not isinstance(t, Parameter)      # (a parameter's gradient may be all-reduced as soon as _done)
                         and tuple(g.shape) == tuple(dy.shape) and g.defer_add(masked_copy)):
                     aliases[0].side_out = (g, masked_copy)
                 else:
